@@ -1,0 +1,394 @@
+// conv_igemm.cu — tcgen05/TMEM/TMA implicit-GEMM convolution (fprop + dgrad) for sm_100a.
+//
+// Replaces, on the TERRA-GAN hot path, nn.Conv2d forward and backward-data for
+//   PConv2d.input_conv                    (reference mvp_gan/src/models/pconv.py:30)
+//   Discriminator convs model[2,5,8]      (mvp_gan/src/models/discriminator.py:11)
+//   VGG16 features[:16] convs             (mvp_gan/src/utils/losses.py:31-32,86-89)
+// and fuses into the epilogue the PConv renormalisation `(conv + bias) * ratio`
+// (pconv.py:38-43, ratio via a <=50-entry LUT indexed by the integer window count), the
+// eval-mode BatchNorm affine (pconv.py:47), ReLU / LeakyReLU (pconv.py:48, discriminator.py:14)
+// and the per-channel sum / sum-of-squares partials train-mode BatchNorm needs.
+//
+// GEMM view: M = output pixels (128 per tile = a Bt x Ht x Wt box of the output grid), N = output
+// channels, K = taps x input channels. One K block = one tap x 64 channels: the A tile is ONE TMA
+// box load of the channels-last input shifted by the tap offset (out-of-range rows/cols are
+// zero-filled by TMA = conv zero padding), landing as 128 rows x 128 B in SWIZZLE_128B layout,
+// which is exactly the K-major UMMA operand layout. Stride-2 convs read a parity-split input so
+// every tap is still a dense shifted box. Accumulators live in TMEM (double buffered) so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4..7 epilogue (TMEM lane quarter = warp_idx % 4).
+#include "conv_igemm.cuh"
+#include "tg_common.cuh"
+#include "../../include/terragan_b200.h"
+
+namespace tg {
+
+constexpr int kStages = 4;
+constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
+
+template <int BN>
+struct ConvSmem {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTiles = kStages * kStageBytes;
+  static constexpr int kStatsFloats = 4 * 2 * 512;  // per epilogue warp (sum, sumsq) x channel
+  static constexpr int kVecFloats = 3 * 512;        // bias / scale / shift
+  static constexpr int kTotal = kTiles + (kStatsFloats + kVecFloats) * 4 + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  using S = ConvSmem<BN>;
+  float* s_stats = reinterpret_cast<float*>(smem + S::kTiles);
+  float* s_vec = s_stats + S::kStatsFloats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + S::kVecFloats);
+  uint64_t* full_bar = bars;                    // [kStages]
+  uint64_t* empty_bar = bars + kStages;         // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                 : (2 * BN <= 256) ? 256 : 512;
+
+  // ---- one-time setup ----
+  for (int i = threadIdx.x; i < S::kStatsFloats; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+    s_vec[i] = p.bias ? p.bias[i] : 0.f;
+    s_vec[512 + i] = p.scale ? p.scale[i] : 1.f;
+    s_vec[1024 + i] = p.shift ? p.shift[i] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = p.tiles_b * p.tiles_h * p.tiles_w;
+  const int total_tiles = p.num_sub * m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int rest = tile / p.n_tiles;
+        const int mt = rest % m_tiles;
+        const int sb = rest / m_tiles;
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int tb = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
+        const ConvSubK sub = p.sub[sb];
+        for (int t = 0; t < sub.tap_count; ++t) {
+          const int tt = sub.tap_begin + t;
+          const int dh = p.tap_dh[tt], dw = p.tap_dw[tt], pl = p.tap_plane[tt];
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * S::kStageBytes;
+            uint8_t* sbm = sa + kABytes;
+            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            tma_load_5d(sa, &tmA, &full_bar[stage], cb * 64, w0 + dw, h0 + dh, pl, b0);
+            tma_load_2d(sbm, &tmB, &full_bar[stage], sub.k_off + (t * p.cin_blocks + cb) * 64,
+                        nt * BN);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int sb = (tile / p.n_tiles) / m_tiles;
+        const int kblocks = p.sub[sb].tap_count * p.cin_blocks;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+          const uint64_t da = make_smem_desc(a_addr, 16, 1024);
+          const uint64_t db = make_smem_desc(b_addr, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 16 bf16 (32 B) along K inside the 128 B swizzle row: +2 in (addr >> 4) units
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;  // TMEM lane quarter == warp_idx % 4
+    float* my_stats = s_stats + q * (2 * 512);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      const int mt = rest % m_tiles;
+      const int sb = rest / m_tiles;
+      const int tw = mt % p.tiles_w;
+      const int th = (mt / p.tiles_w) % p.tiles_h;
+      const int tb = mt / (p.tiles_w * p.tiles_h);
+      const int r = q * 32 + lane;  // row of the tile = pixel in box order
+      const int wt = r % p.Wt;
+      const int ht = (r / p.Wt) % p.Ht;
+      const int bt = r / (p.Wt * p.Ht);
+      const int w = tw * p.Wt + wt, h = th * p.Ht + ht, b = tb * p.Bt + bt;
+      const bool valid = (w < p.Wo) && (h < p.Ho) && (b < p.B);
+      const long pix =
+          ((static_cast<long>(b) * p.Po + p.sub[sb].out_plane) * p.Ho + h) * p.Wo + w;
+      float rs = 1.f;
+      if (p.code != nullptr && valid) rs = p.lut[p.code[pix]];
+      __nv_bfloat16* orow = p.out + pix * p.Cout + nt * BN;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t raw[32];
+        tmem_ld_32x32(t_addr + ch * 32, raw);
+        tmem_ld_wait();
+        const int n0 = nt * BN + ch * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = (__uint_as_float(raw[j]) + s_vec[n0 + j]) * rs;
+          v[j] = valid ? x : 0.f;
+        }
+        if (p.stats != nullptr) {
+          float sq[32], sm[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            sm[j] = v[j];
+            sq[j] = v[j] * v[j];
+          }
+          const float csum = warp_transpose_sum32(sm);
+          const float csq = warp_transpose_sum32(sq);
+          my_stats[n0 + lane] += csum;
+          my_stats[512 + n0 + lane] += csq;
+        }
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a = v[j] * s_vec[512 + n0 + j] + s_vec[1024 + n0 + j];
+          float c = v[j + 1] * s_vec[512 + n0 + j + 1] + s_vec[1024 + n0 + j + 1];
+          if (p.act == 1) {
+            a = fmaxf(a, 0.f);
+            c = fmaxf(c, 0.f);
+          } else if (p.act == 2) {
+            a = a > 0.f ? a : a * p.slope;
+            c = c > 0.f ? c : c * p.slope;
+          }
+          packed[j >> 1] = pack_bf16x2(a, c);
+        }
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2],
+                                packed[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    // flush the per-CTA BatchNorm partials: one row per CTA, summed by tg_bn_finalize
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = threadIdx.x - 128;
+      float* dst = p.stats + static_cast<long>(blockIdx.x) * 2 * p.Cout;
+      for (int c = et; c < p.Cout; c += 128) {
+        float a = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          a += s_stats[qq * 1024 + c];
+          s2 += s_stats[qq * 1024 + 512 + c];
+        }
+        dst[c] = a;
+        dst[p.Cout + c] = s2;
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static void choose_box(int Ho, int Wo, int pixels, int* Bt, int* Ht, int* Wt) {
+  int wt = 1;
+  while (wt * 2 <= Wo && wt * 2 <= 16 && wt * 2 <= pixels) wt *= 2;
+  int ht = 1;
+  while (ht * 2 <= Ho && wt * ht * 2 <= pixels) ht *= 2;
+  *Wt = wt;
+  *Ht = ht;
+  *Bt = pixels / (wt * ht);
+}
+
+template <int BN>
+static int launch_conv(const tg_conv_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                       const ConvKParams& kp, int grid, cudaStream_t st) {
+  using S = ConvSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  conv_igemm_kernel<BN><<<grid, 256, S::kTotal, st>>>(tmA, tmB, kp);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tg
+
+extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(a != nullptr, "tg_conv_igemm: null args");
+  TG_REQUIRE(a->C > 0 && a->C % 64 == 0, "tg_conv_igemm: C=%d must be a positive multiple of 64", a->C);
+  TG_REQUIRE(a->N > 0 && a->N % 64 == 0 && a->N <= 512,
+             "tg_conv_igemm: N=%d must be a multiple of 64 and <= 512", a->N);
+  TG_REQUIRE(a->num_sub >= 1 && a->num_sub <= TG_MAX_SUB, "tg_conv_igemm: bad num_sub %d", a->num_sub);
+  TG_REQUIRE(a->num_taps >= 1 && a->num_taps <= TG_MAX_TAPS, "tg_conv_igemm: bad num_taps %d", a->num_taps);
+  TG_REQUIRE(a->code == nullptr || (a->lut != nullptr && a->lut_len >= 1 && a->lut_len <= TG_MAX_TAPS),
+             "tg_conv_igemm: code given without a valid lut");
+  TG_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+             "tg_conv_igemm: x/w/out must be 16-byte aligned");
+  TG_REQUIRE(a->Ktot % 64 == 0, "tg_conv_igemm: Ktot=%d must be a multiple of 64", a->Ktot);
+  for (int s = 0; s < a->num_sub; ++s) {
+    const tg_conv_sub& sb = a->sub[s];
+    TG_REQUIRE(sb.tap_begin >= 0 && sb.tap_count >= 1 && sb.tap_begin + sb.tap_count <= a->num_taps,
+               "tg_conv_igemm: sub %d taps out of range", s);
+    TG_REQUIRE(sb.k_off >= 0 && sb.k_off + sb.tap_count * a->C <= a->Ktot,
+               "tg_conv_igemm: sub %d weight slab out of range", s);
+    TG_REQUIRE(sb.out_plane >= 0 && sb.out_plane < a->Po, "tg_conv_igemm: sub %d bad out_plane", s);
+  }
+  const int BN = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : 64;
+
+  ConvKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  choose_box(a->Ho, a->Wo, 128, &kp.Bt, &kp.Ht, &kp.Wt);
+  kp.tiles_w = (a->Wo + kp.Wt - 1) / kp.Wt;
+  kp.tiles_h = (a->Ho + kp.Ht - 1) / kp.Ht;
+  kp.tiles_b = (a->B + kp.Bt - 1) / kp.Bt;
+  kp.n_tiles = a->N / BN;
+  kp.num_sub = a->num_sub;
+  for (int s = 0; s < a->num_sub; ++s) {
+    kp.sub[s].tap_begin = a->sub[s].tap_begin;
+    kp.sub[s].tap_count = a->sub[s].tap_count;
+    kp.sub[s].k_off = a->sub[s].k_off;
+    kp.sub[s].out_plane = a->sub[s].out_plane;
+  }
+  for (int t = 0; t < a->num_taps; ++t) {
+    TG_REQUIRE(a->tap_plane[t] >= 0 && a->tap_plane[t] < a->P, "tg_conv_igemm: tap %d bad plane", t);
+    kp.tap_plane[t] = a->tap_plane[t];
+    kp.tap_dh[t] = a->tap_dh[t];
+    kp.tap_dw[t] = a->tap_dw[t];
+  }
+  kp.cin_blocks = a->C / 64;
+  kp.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  kp.B = a->B;
+  kp.Ho = a->Ho;
+  kp.Wo = a->Wo;
+  kp.Po = a->Po;
+  kp.Cout = a->N;
+  kp.code = a->code;
+  kp.bias = a->bias;
+  kp.scale = a->scale;
+  kp.shift = a->shift;
+  if (a->code != nullptr)
+    for (int i = 0; i < a->lut_len; ++i) kp.lut[i] = a->lut[i];
+  kp.act = a->act;
+  kp.slope = a->slope;
+  kp.stats = a->stats;
+
+  // A: channels-last activations as a 5-D tensor (C, W, H, P, B)
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->P, (uint64_t)a->B};
+    uint64_t str[4] = {(uint64_t)a->C * 2, (uint64_t)a->C * 2 * a->W, (uint64_t)a->C * 2 * a->W * a->H,
+                       (uint64_t)a->C * 2 * a->W * a->H * a->P};
+    uint32_t box[5] = {64, (uint32_t)kp.Wt, (uint32_t)kp.Ht, 1, (uint32_t)kp.Bt};
+    if (make_tmap_bf16(&tmA, a->x, 5, dims, str, box) != 0) return -3;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->Ktot, (uint64_t)a->N};
+    uint64_t str[1] = {(uint64_t)a->Ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)BN};
+    if (make_tmap_bf16(&tmB, a->w, 2, dims, str, box) != 0) return -3;
+  }
+  const long total_tiles = (long)kp.num_sub * kp.tiles_b * kp.tiles_h * kp.tiles_w * kp.n_tiles;
+  const int sms = num_sms();
+  TG_REQUIRE(sms > 0, "tg_conv_igemm: no CUDA device");
+  int grid = (int)(total_tiles < sms ? total_tiles : sms);
+  if (a->stats != nullptr) {
+    TG_REQUIRE(a->stats_rows_cap >= grid, "tg_conv_igemm: stats_rows_cap %d < grid %d", a->stats_rows_cap, grid);
+  }
+  a->stats_rows_used = grid;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (BN == 256) return launch_conv<256>(a, tmA, tmB, kp, grid, st);
+  if (BN == 128) return launch_conv<128>(a, tmA, tmB, kp, grid, st);
+  return launch_conv<64>(a, tmA, tmB, kp, grid, st);
+}

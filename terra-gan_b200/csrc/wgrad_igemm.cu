@@ -1,0 +1,335 @@
+// wgrad_igemm.cu — tcgen05 implicit-GEMM weight gradient for sm_100a.
+//
+// Replaces autograd's convolution_backward(weight) for PConv2d.input_conv (reference
+// mvp_gan/src/models/pconv.py:30) and the Discriminator convs (discriminator.py:11):
+//   dW[co][ci][kh][kw] = sum_{b,ho,wo} g[b][ho][wo][co] * xm[b][(ho,wo) (+) tap(kh,kw)][ci]
+// where xm is the masked layer input the forward pass consumed and g already carries the
+// BatchNorm/ReLU/mask-ratio backward factors (pconv.py:43-48).
+//
+// GEMM view: D^T[(tap,ci)][co], M = 128 rows = two 64-row blocks of the (tap, ci-block) list,
+// N = Cout tile, K = output pixels (64 per K block = a Bt x Ht x Wt pixel box). Both operands are
+// channels-last tiles [pixel][64 channels] brought in by TMA boxes (the X tile shifted by the tap
+// offset; zero fill = conv padding), i.e. MN-major SWIZZLE_128B UMMA operands: no transposes are
+// ever materialised. The pixel axis is split over CTAs (split-K); each share is written to an fp32
+// partial buffer and tg_wgrad_reduce sums the shares in a fixed order (deterministic) while
+// scattering into PyTorch's [Cout][Cin][kh][kw] gradient layout.
+#include "conv_igemm.cuh"
+#include "tg_common.cuh"
+#include "../../include/terragan_b200.h"
+
+namespace tg {
+
+constexpr int kWStages = 4;
+constexpr int kBoxBytes = 64 * 128;  // 64 pixels x 64 bf16
+
+template <int BN>
+struct WgradSmem {
+  static constexpr int kABytes = 2 * kBoxBytes;
+  static constexpr int kBBytes = (BN / 64) * kBoxBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTiles = kWStages * kStageBytes;
+  static constexpr int kTotal = kTiles + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                   const __grid_constant__ WgradKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  using S = WgradSmem<BN>;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kTiles);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kWStages;
+  uint64_t* tfull_bar = bars + 2 * kWStages;
+  uint64_t* tempty_bar = bars + 2 * kWStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kboxes = p.tiles_b * p.tiles_h * p.tiles_w;
+  const int per_split = (kboxes + p.splits - 1) / p.splits;
+  const int total_units = p.m_tiles * p.n_tiles * p.splits;
+  // unit -> (split, m tile, n tile), n fastest so CTAs sharing an X tile run together
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int nt = u % p.n_tiles;
+        const int mt = (u / p.n_tiles) % p.m_tiles;
+        const int sp = u / (p.n_tiles * p.m_tiles);
+        const int i0 = 2 * mt;
+        const int i1 = (2 * mt + 1 < p.num_blk) ? 2 * mt + 1 : 2 * mt;
+        const WgradBlk e0 = p.blks[i0];
+        const WgradBlk e1 = p.blks[i1];
+        const int kb_begin = sp * per_split;
+        const int kb_end = min(kboxes, kb_begin + per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const int tw = kb % p.tiles_w;
+          const int th = (kb / p.tiles_w) % p.tiles_h;
+          const int tb = kb / (p.tiles_w * p.tiles_h);
+          const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          tma_load_5d(sa, &tmX, &full_bar[stage], e0.cb * 64, w0 + e0.dw, h0 + e0.dh, e0.plane, b0);
+          tma_load_5d(sa + kBoxBytes, &tmX, &full_bar[stage], e1.cb * 64, w0 + e1.dw, h0 + e1.dh,
+                      e1.plane, b0);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_5d(sb + j * kBoxBytes, &tmG, &full_bar[stage], nt * BN + j * 64, w0, h0, 0, b0);
+          if (++stage == kWStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int sp = u / (p.n_tiles * p.m_tiles);
+        const int kb_begin = sp * per_split;
+        const int kb_end = min(kboxes, kb_begin + per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t b_addr = a_addr + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // 16 pixels (= 16 rows of 128 B = two 8-row swizzle atoms) per MMA
+            const uint64_t da = make_smem_desc(a_addr + k * 2048, kBoxBytes, 1024);
+            const uint64_t db = make_smem_desc(b_addr + k * 2048, kBoxBytes, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb_begin) || (k > 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kWStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int nt = u % p.n_tiles;
+      const int mt = (u / p.n_tiles) % p.m_tiles;
+      const int sp = u / (p.n_tiles * p.m_tiles);
+      const int r = q * 32 + lane;
+      const int bi = 2 * mt + (r >> 6);
+      const bool valid = bi < p.num_blk;
+      const int row = valid ? p.blks[bi].row + (r & 63) : 0;
+      float* dst = p.partial + (static_cast<long>(sp) * p.rows + row) * p.Cout + nt * BN;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t raw[32];
+        tmem_ld_32x32(t_addr + ch * 32, raw);
+        tmem_ld_wait();
+        if (valid) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d4[j] = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// partial[s][tap*C + c][n]  ->  dw[n][c][perm[tap]]  (kk = number of kernel positions)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int C,
+                                    int N, const int32_t* __restrict__ perm, float* __restrict__ dw,
+                                    int accumulate) {
+  // one thread per (row, n); threads along n are contiguous in `partial` (coalesced reads)
+  const long total = static_cast<long>(taps) * C * N;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i % N);
+    const long row = i / N;
+    const int c = static_cast<int>(row % C);
+    const int t = static_cast<int>(row / C);
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[static_cast<long>(s) * total + i];
+    const long o = (static_cast<long>(n) * C + c) * taps + perm[t];
+    dw[o] = accumulate ? dw[o] + acc : acc;
+  }
+}
+
+static void choose_kbox(int Ho, int Wo, int* Bt, int* Ht, int* Wt) {
+  int wt = 1;
+  while (wt * 2 <= Wo && wt * 2 <= 16) wt *= 2;
+  int ht = 1;
+  while (ht * 2 <= Ho && wt * ht * 2 <= 64) ht *= 2;
+  *Wt = wt;
+  *Ht = ht;
+  *Bt = 64 / (wt * ht);
+}
+
+static int choose_splits(int B, int Ho, int Wo, int num_blk, int N, int sms) {
+  int Bt, Ht, Wt;
+  choose_kbox(Ho, Wo, &Bt, &Ht, &Wt);
+  const long kboxes = (long)((B + Bt - 1) / Bt) * ((Ho + Ht - 1) / Ht) * ((Wo + Wt - 1) / Wt);
+  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
+  const long mn = (long)((num_blk + 1) / 2) * (N / BN);
+  long splits = (2L * sms + mn - 1) / mn;  // aim for ~2 units per SM
+  const long max_by_k = (kboxes + 7) / 8;  // at least 8 K blocks per unit
+  if (splits > max_by_k) splits = max_by_k;
+  if (splits < 1) splits = 1;
+  if (splits > 256) splits = 256;
+  // no empty trailing share: shrink until every split owns at least one box
+  const long per = (kboxes + splits - 1) / splits;
+  splits = (kboxes + per - 1) / per;
+  return (int)splits;
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmG, const WgradKParams& kp,
+                        int grid, cudaStream_t st) {
+  using S = WgradSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_igemm_kernel<BN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  wgrad_igemm_kernel<BN><<<grid, 256, S::kTotal, st>>>(tmX, tmG, kp);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tg
+
+extern "C" int64_t tg_wgrad_partial_floats(int B, int Ho, int Wo, int num_taps, int C, int N) {
+  const int sms = tg::num_sms() > 0 ? tg::num_sms() : 148;
+  const int splits = tg::choose_splits(B, Ho, Wo, num_taps * (C / 64), N, sms);
+  return (int64_t)splits * num_taps * C * N;
+}
+
+extern "C" int tg_wgrad_igemm(tg_wgrad_args* a, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(a != nullptr, "tg_wgrad_igemm: null args");
+  TG_REQUIRE(a->C > 0 && a->C % 64 == 0, "tg_wgrad_igemm: C=%d must be a multiple of 64", a->C);
+  TG_REQUIRE(a->N > 0 && a->N % 64 == 0, "tg_wgrad_igemm: N=%d must be a multiple of 64", a->N);
+  TG_REQUIRE(a->num_taps >= 1 && a->num_taps <= TG_MAX_TAPS, "tg_wgrad_igemm: bad num_taps");
+  const int sms = num_sms();
+  TG_REQUIRE(sms > 0, "tg_wgrad_igemm: no CUDA device");
+  const int BN = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : 64;
+  const int num_blk = a->num_taps * (a->C / 64);
+
+  WgradKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  choose_kbox(a->Ho, a->Wo, &kp.Bt, &kp.Ht, &kp.Wt);
+  kp.tiles_w = (a->Wo + kp.Wt - 1) / kp.Wt;
+  kp.tiles_h = (a->Ho + kp.Ht - 1) / kp.Ht;
+  kp.tiles_b = (a->B + kp.Bt - 1) / kp.Bt;
+  kp.n_tiles = a->N / BN;
+  kp.num_blk = num_blk;
+  kp.m_tiles = (num_blk + 1) / 2;
+  kp.splits = choose_splits(a->B, a->Ho, a->Wo, num_blk, a->N, sms);
+  kp.Cout = a->N;
+  kp.rows = a->num_taps * a->C;
+  kp.partial = a->partial;
+  kp.blks = reinterpret_cast<const WgradBlk*>(a->blks);
+  TG_REQUIRE(a->blks != nullptr && a->num_blk == num_blk, "tg_wgrad_igemm: blks table must hold num_taps*C/64 = %d entries", num_blk);
+  TG_REQUIRE((int64_t)kp.splits * kp.rows * a->N <= a->partial_cap,
+             "tg_wgrad_igemm: partial workspace too small (%lld floats needed)",
+             (long long)((int64_t)kp.splits * kp.rows * a->N));
+  a->splits = kp.splits;
+
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  CUtensorMap tmX, tmG;
+  {
+    uint64_t dims[5] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->P, (uint64_t)a->B};
+    uint64_t str[4] = {(uint64_t)a->C * 2, (uint64_t)a->C * 2 * a->W, (uint64_t)a->C * 2 * a->W * a->H,
+                       (uint64_t)a->C * 2 * a->W * a->H * a->P};
+    uint32_t box[5] = {64, (uint32_t)kp.Wt, (uint32_t)kp.Ht, 1, (uint32_t)kp.Bt};
+    if (make_tmap_bf16(&tmX, a->x, 5, dims, str, box) != 0) return -3;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)a->N, (uint64_t)a->Wo, (uint64_t)a->Ho, 1, (uint64_t)a->B};
+    uint64_t str[4] = {(uint64_t)a->N * 2, (uint64_t)a->N * 2 * a->Wo, (uint64_t)a->N * 2 * a->Wo * a->Ho,
+                       (uint64_t)a->N * 2 * a->Wo * a->Ho};
+    uint32_t box[5] = {64, (uint32_t)kp.Wt, (uint32_t)kp.Ht, 1, (uint32_t)kp.Bt};
+    if (make_tmap_bf16(&tmG, a->g, 5, dims, str, box) != 0) return -3;
+  }
+  const long total_units = (long)kp.m_tiles * kp.n_tiles * kp.splits;
+  const int grid = (int)(total_units < sms ? total_units : sms);
+  if (BN == 256) return launch_wgrad<256>(tmX, tmG, kp, grid, st);
+  if (BN == 128) return launch_wgrad<128>(tmX, tmG, kp, grid, st);
+  return launch_wgrad<64>(tmX, tmG, kp, grid, st);
+}
+
+extern "C" int tg_wgrad_reduce(const float* partial, int splits, int num_taps, int C, int N,
+                               const int32_t* tap_perm_dev, float* dw, int accumulate, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(partial && dw && tap_perm_dev, "tg_wgrad_reduce: null pointer");
+  const long total = (long)num_taps * C * N;
+  int grid = (int)((total + 255) / 256);
+  const int cap = num_sms() * 16;
+  if (grid > cap) grid = cap;
+  wgrad_reduce_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, splits, num_taps, C, N, tap_perm_dev, dw, accumulate);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

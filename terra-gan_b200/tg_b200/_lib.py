@@ -1,0 +1,116 @@
+"""ctypes binding of libtg_b200.so — the C ABI declared in include/terragan_b200.h.
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C terra-gan_b200/csrc`. There is
+deliberately NO fallback: if the shared object is missing or a call fails, a RuntimeError is raised
+(the north star forbids a CPU / eager fallback on the hot path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtg_b200.so")
+
+TG_MAX_TAPS = 64
+TG_MAX_SUB = 4
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+c_void_p, c_int, c_long, c_float, c_size_t = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_size_t
+
+
+class ConvSub(C.Structure):
+    _fields_ = [("tap_begin", C.c_int32), ("tap_count", C.c_int32), ("k_off", C.c_int32),
+                ("out_plane", C.c_int32)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("B", C.c_int32), ("P", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("C", C.c_int32),
+        ("w", c_void_p), ("N", C.c_int32), ("Ktot", C.c_int32),
+        ("num_sub", C.c_int32), ("sub", ConvSub * TG_MAX_SUB),
+        ("num_taps", C.c_int32),
+        ("tap_plane", C.c_int8 * TG_MAX_TAPS), ("tap_dh", C.c_int8 * TG_MAX_TAPS),
+        ("tap_dw", C.c_int8 * TG_MAX_TAPS),
+        ("out", c_void_p), ("Po", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
+        ("code", c_void_p), ("lut", C.POINTER(C.c_float)), ("lut_len", C.c_int32),
+        ("bias", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+        ("act", C.c_int32), ("slope", C.c_float),
+        ("stats", c_void_p), ("stats_rows_cap", C.c_int32), ("stats_rows_used", C.c_int32),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("B", C.c_int32), ("P", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("C", C.c_int32),
+        ("g", c_void_p), ("Ho", C.c_int32), ("Wo", C.c_int32), ("N", C.c_int32),
+        ("num_taps", C.c_int32),
+        ("tap_plane", C.c_int8 * TG_MAX_TAPS), ("tap_dh", C.c_int8 * TG_MAX_TAPS),
+        ("tap_dw", C.c_int8 * TG_MAX_TAPS),
+        ("partial", c_void_p), ("partial_cap", C.c_int64), ("splits", C.c_int32),
+        ("blks", c_void_p), ("num_blk", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes). Every symbol include/terragan_b200.h declares appears here; the
+# CPU test-suite checks the library exports all of them.
+PROTOTYPES = {
+    "tg_version": (c_int, []),
+    "tg_last_error": (c_size_t, [C.c_char_p, c_size_t]),
+    "tg_num_sms": (c_int, []),
+    "tg_mask_window_sum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tg_mask_merge_up": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tg_mask_from_f32": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
+    "tg_mask_to_f32": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
+    "tg_conv_igemm": (c_int, [C.POINTER(ConvArgs), c_void_p]),
+    "tg_wgrad_igemm": (c_int, [C.POINTER(WgradArgs), c_void_p]),
+    "tg_wgrad_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                c_void_p]),
+    "tg_wgrad_partial_floats": (C.c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the kernel library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C terra-gan_b200/csrc`. There is no CPU fallback for the TERRA-GAN hot path.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(l, name)  # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(1024)
+    lib().tg_last_error(buf, 1024)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
