@@ -100,6 +100,9 @@ typedef struct tg_conv_args {
   float* stats;             /* device [stats_rows_cap][2][N] or NULL */
   int32_t stats_rows_cap;   /* in: rows allocated (>= tg_num_sms()) */
   int32_t stats_rows_used;  /* out: rows written by this launch */
+  const void* gate;         /* bf16, same shape as out, or NULL: out *= (gate > 0 ? 1 : gate_slope) —
+                               ReLU/LeakyReLU derivative of the tensor a dgrad result flows into */
+  float gate_slope;
 } tg_conv_args;
 int tg_conv_igemm(tg_conv_args* args, void* stream);
 
@@ -133,6 +136,122 @@ int tg_wgrad_reduce(const float* partial, int splits, int num_taps, int C, int N
                     const int32_t* tap_perm_dev, float* dw, int accumulate, void* stream);
 /* How many fp32 the `partial` workspace of tg_wgrad_igemm needs for this problem. */
 int64_t tg_wgrad_partial_floats(int B, int Ho, int Wo, int num_taps, int C, int N);
+
+
+/* ---- BatchNorm2d + activation (HBM-bound, 16-byte vectorised) -------------------------------
+ * Replaces `self.bn` + `self.activation` of PConv2d (pconv.py:46-48) and BatchNorm2d + LeakyReLU of
+ * the Discriminator blocks (discriminator.py:12-14), forward and backward. Train-mode statistics
+ * come from the (sum, sumsq) partial rows written by the conv kernels. */
+
+/* partial [rows][2][C] -> scale = gamma*invstd, shift = beta - mean*scale, saved mean / invstd and
+ * (if running_mean != NULL) the running-stat update with `momentum` and the unbiased variance. */
+int tg_bn_finalize(const float* partial, int rows, int C, double count, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean,
+                   float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                   void* stream);
+/* eval mode: scale / shift from the running statistics. */
+int tg_bn_eval_coeff(int C, const float* gamma, const float* beta, const float* running_mean,
+                     const float* running_var, float eps, float* scale, float* shift, void* stream);
+/* y = act(z*scale + shift). z is bf16 [B][H][W][C]. Writes y_nhwc (same layout) and/or y_split
+ * (parity-split [B][4][H/2][W/2][C]); if mask_split, y_split is multiplied by [code[pixel] > 0]
+ * (the layer's updated mask), i.e. it is the `input * mask` the next PConv2d consumes (pconv.py:27). */
+int tg_bn_apply(const void* z, int B, int H, int W, int C, const float* scale, const float* shift,
+                int act, float slope, const uint8_t* code, void* y_nhwc, void* y_split,
+                int mask_split, void* stream);
+
+/* A gradient arriving at a layer output: bf16, pixel p of the [B][H][W] grid at
+ * ptr + pix(p)*pix_stride + chan_off, pix(p) = p (split = 0) or its parity-split index (split = 1). */
+typedef struct tg_grad_src {
+  const void* ptr;
+  int64_t pix_stride;
+  int32_t chan_off;
+  int32_t split;
+} tg_grad_src;
+/* One pass over (g0 [+ g1], z): per-channel sums needed by BN backward and the conv-bias gradient.
+ * partial is [rows_cap][5][C]; *rows_used rows are written. lut_dev: device LUT for `code`. */
+int tg_bn_bwd_reduce(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H, int W,
+                     int C, const float* scale, const float* shift, int act, float slope,
+                     const uint8_t* code, const float* lut_dev, float* partial, int rows_cap,
+                     int* rows_used, void* stream);
+/* -> coeff [5][C] for tg_bn_bwd_apply, dgamma, dbeta, dbias (each may be NULL; accumulate: +=).
+ * batch_stats = 1: train-mode BN (mean/var depend on the batch); 0: eval-mode BN / plain affine. */
+int tg_bn_bwd_finalize(const float* partial, int rows, int C, double count, const float* scale,
+                       const float* mean, const float* invstd, float* coeff, float* dgamma,
+                       float* dbeta, float* dbias, int accumulate, int batch_stats, void* stream);
+/* gz = lut[code] * scale * (g*act' - dbeta/M - zhat*dgamma/M): bf16 [B][H][W][C], the gradient w.r.t.
+ * (conv + bias) that tg_conv_igemm (dgrad) and tg_wgrad_igemm consume. */
+int tg_bn_bwd_apply(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H, int W,
+                    int C, const float* shift, const float* coeff, int act, float slope,
+                    const uint8_t* code, const float* lut_dev, void* gz, void* stream);
+
+/* ---- decoder input assembly and pooling ----------------------------------------------------- */
+/* out[B][2h][2w][Cu+Cs] = cat(bilinear_up2(up[B][h][w][Cu]), skip[B][2h][2w][Cs]) * merged_mask
+ * (generator.py:66-76 / :50-55 + pconv.py:27). skip may be NULL with Cs = 0 (dec1). */
+int tg_upsample_concat(const void* up, int B, int h, int w, int Cu, const void* skip, int Cs,
+                       const uint8_t* merged_mask, void* out, void* stream);
+/* d_up[B][h][w][Cu] = bilinear_up2^T applied to channels [0,Cu) of d_merged[B][2h][2w][Ctot]. */
+int tg_upsample_concat_bwd(const void* d_merged, int B, int h, int w, int Cu, int Ctot, void* d_up,
+                           void* stream);
+/* nn.MaxPool2d(2,2) of VGG16 features[4], [9] (losses.py:31-32) on bf16 NHWC, and its backward
+ * (gradient to the first maximum in scan order; relu_gate: also multiply by [x > 0]). */
+int tg_maxpool2(const void* x, int B, int H, int W, int C, void* y, void* stream);
+int tg_maxpool2_bwd(const void* x, const void* gy, int B, int H, int W, int C, int relu_gate, void* gx,
+                    void* stream);
+
+/* ---- bandwidth-bound convolutions: 1 input channel or 1 output channel ------------------------ */
+/* x fp32 [B][H][W] (times xmask if given) -> bf16 [B][Ho][Wo][64] (out_split: parity-split order):
+ *   out = act((conv_kxk/s(x) + bias) * lut[code]);  stats: per-CTA (sum, sumsq) rows of the pre-act value.
+ * Supported (k, s): (7,2) enc1, (4,2) Discriminator model[0], (3,1) VGG conv0 with folded channels.
+ * wgt is fp32 [64][k*k]. */
+int tg_conv_c1_fwd(const float* x, const uint8_t* xmask, int B, int H, int W, int k, int s, int pad,
+                   const float* wgt, const float* bias, const uint8_t* code, const float* lut_dev, int act,
+                   float slope, void* out, int out_split, float* stats, int stats_rows_cap,
+                   int* stats_rows_used, void* stream);
+/* dw[64][k*k] (+)= sum_p g[p][co] * x[p (+) tap];  db[64] (+)= sum_p g[p][co]  (db may be NULL).
+ * g is bf16 [B][Ho][Wo][64] (g_split: parity-split order). partial: >= rows_cap*64*(k*k+1) floats. */
+int tg_conv_c1_wgrad(const float* x, const uint8_t* xmask, int B, int H, int W, int k, int s, int pad,
+                     const void* g, int g_split, float* partial, int rows_cap, float* dw, float* db,
+                     int accumulate, void* stream);
+int tg_conv_c1_wgrad_rows(void);
+/* C -> 1 gather convolution with tap classes (see direct_conv.cu): x bf16 [B][H][W][C] (x_split:
+ * parity-split), wgt fp32 [ntaps][C], bias device scalar or NULL.
+ * mode 0: out = acc + bias.  mode 1: sig = sigmoid(acc + bias); out = sig*(1-mask) + xin*mask
+ * (generator.py:56-62; sig_out receives sig for backward). */
+int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, int C, const float* wgt, int ncls,
+                    const int* cls_count, const int8_t* tap_dh, const int8_t* tap_dw, const float* bias,
+                    int Ho, int Wo, int mode, const uint8_t* mask, const float* xin, float* out,
+                    float* sig_out, void* stream);
+/* dx[B][H][W][C] (bf16) = sum_t g[b][h - dh_t][w - dw_t] * wgt[t][c];  g fp32 [B][Ho][Wo]. */
+int tg_conv_to1_bwd_data(const float* g, int B, int Ho, int Wo, const float* wgt, int ntaps,
+                         const int8_t* tap_dh, const int8_t* tap_dw, int H, int W, int C, void* dx,
+                         void* stream);
+/* dw[C][ntaps] (+)= sum_o g[o] * x[o + d_t][c];  db[1] (+)= sum_o g[o].  ntaps in {9, 16}. */
+int tg_conv_to1_wgrad(const void* x, int B, int H, int W, int C, const float* g, int Ho, int Wo, int ntaps,
+                      const int8_t* tap_dh, const int8_t* tap_dw, float* partial, float* partial_b,
+                      int rows_cap, float* dw, float* db, int accumulate, void* stream);
+int tg_conv_to1_wgrad_rows(void);
+/* g_pre = g_out * (1 - mask) * sig * (1 - sig): backward of sigmoid + composite (generator.py:57-62). */
+int tg_final_bwd_pre(const float* g_out, const float* sig, const uint8_t* mask, long n, float* g_pre,
+                     void* stream);
+
+/* ---- fused losses ---------------------------------------------------------------------------
+ * terms[0] = mean|pred-target| (flags&1: weighted by [mask>0], the human-region L1 of losses.py:172)
+ * terms[1] = total_variation_loss(pred*(1-mask)) (losses.py:118-127; skipped if flags&2)
+ * terms[2] = BoundaryAwareLoss(pred, target, mask) (losses.py:406-423), terms[3] = boundary count.
+ * pred / target / mask are fp32 [B][1][H][W]; partial: >= rows_cap*5 floats. No host sync. */
+int tg_loss_rows(void);
+int tg_inpaint_loss_fwd(const float* pred, const float* target, const float* mask, int B, int H, int W,
+                        int flags, float eps, float* partial, int rows_cap, float* terms, void* stream);
+/* grad_pred = grad_terms[0]*dterms0 + grad_terms[1]*dterms1 + grad_terms[2]*dterms2. */
+int tg_inpaint_loss_bwd(const float* pred, const float* target, const float* mask, int B, int H, int W,
+                        int flags, float eps, const float* terms, const float* grad_terms, float* grad_pred,
+                        void* stream);
+/* out[0] = mean|a - b| over n bf16 elements (perceptual L1 on VGG features, losses.py:86-89), and
+ * ga = grad_out[0]*sign(a-b)/n (* [a > 0] if relu_gate). n % 8 == 0. */
+int tg_l1_bf16_fwd(const void* a, const void* b, long n, float* partial, int rows_cap, float* out,
+                   void* stream);
+int tg_l1_bf16_bwd(const void* a, const void* b, long n, const float* grad_out, int relu_gate, void* ga,
+                   void* stream);
 
 #ifdef __cplusplus
 }

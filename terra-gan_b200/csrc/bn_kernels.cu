@@ -1,0 +1,416 @@
+// bn_kernels.cu — BatchNorm2d (train-mode statistics) + activation, forward and backward, as
+// coalesced 16-byte-vectorised HBM-bound kernels over channels-last bf16 activations.
+//
+// Reference ops replaced: `self.bn(output)` + `self.activation(output)` in PConv2d.forward
+// (mvp_gan/src/models/pconv.py:46-48; nn.BatchNorm2d eps 1e-5, momentum 0.1 + ReLU) and
+// BatchNorm2d + LeakyReLU(0.2) in the Discriminator blocks (mvp_gan/src/models/discriminator.py:12-14),
+// plus their autograd backward together with the `output * mask_ratio` factor (pconv.py:43).
+//
+// Forward:  the conv epilogue already produced per-CTA (sum, sumsq) partials of z; tg_bn_finalize
+//           turns them into scale = gamma*invstd, shift = beta - mean*scale (and the running-stat
+//           EMA); tg_bn_apply writes y = act(z*scale + shift) in the layouts the consumers need
+//           (plain NHWC and/or parity-split, optionally multiplied by the layer's output mask so
+//           the next PConv sees x*mask without another pass).
+// Backward: tg_bn_bwd_reduce accumulates the five per-channel sums BN backward needs in one pass
+//           over (g, z); tg_bn_bwd_finalize produces dgamma, dbeta, the conv-bias gradient and the
+//           per-channel coefficients; tg_bn_bwd_apply writes gz = dL/d(conv+bias) (bf16), which
+//           the dgrad / wgrad tensor-core kernels consume.
+#include "tg_common.cuh"
+#include "../../include/terragan_b200.h"
+
+namespace tg {
+
+struct __align__(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 raw;
+  raw.x = pack_bf16x2(f[0], f[1]);
+  raw.y = pack_bf16x2(f[2], f[3]);
+  raw.z = pack_bf16x2(f[4], f[5]);
+  raw.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+__device__ __forceinline__ void ldg8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// pixel index of (b, h, w) in parity-split order [B][4][H/2][W/2]
+__device__ __forceinline__ long split_index(int b, int h, int w, int H, int W) {
+  return ((static_cast<long>(b) * 4 + 2 * (h & 1) + (w & 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+// One thread per channel: sums the per-CTA partial rows in fp64, then the usual BN bookkeeping.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, s2 = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    s += partial[(static_cast<long>(r) * 2) * C + c];
+    s2 += partial[(static_cast<long>(r) * 2 + 1) * C + c];
+  }
+  const double mean = s / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma ? gamma[c] : 1.f;
+  const float b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = b - static_cast<float>(mean) * sc;
+  mean_out[c] = static_cast<float>(mean);
+  invstd_out[c] = invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// eval mode: scale/shift from the running statistics
+__global__ void bn_eval_coeff_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ running_mean,
+                                     const float* __restrict__ running_var, float eps,
+                                     float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = rsqrtf(running_var[c] + eps);
+  // rsqrtf is approximate: refine once so eval-mode outputs match 1/sqrt to fp32 rounding
+  const float v = running_var[c] + eps;
+  const float is = invstd * (1.5f - 0.5f * v * invstd * invstd);
+  const float sc = (gamma ? gamma[c] : 1.f) * is;
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - running_mean[c] * sc;
+}
+
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long M, int C, int H, int W,
+                                const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                float slope, const uint8_t* __restrict__ code,
+                                __nv_bfloat16* __restrict__ y_nhwc, __nv_bfloat16* __restrict__ y_split,
+                                int mask_split) {
+  const int cv = C >> 3;
+  const long total = M * cv;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = i / cv;
+    const int c = static_cast<int>(i % cv) << 3;
+    float v[8], sc[8], sh[8];
+    load8(z + p * C + c, v);
+    ldg8f(scale + c, sc);
+    ldg8f(shift + c, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = v[j] * sc[j] + sh[j];
+      if (act == 1) t = fmaxf(t, 0.f);
+      else if (act == 2) t = t > 0.f ? t : t * slope;
+      v[j] = t;
+    }
+    if (y_nhwc) store8(y_nhwc + p * C + c, v);
+    if (y_split) {
+      const int w = static_cast<int>(p % W);
+      const int h = static_cast<int>((p / W) % H);
+      const int b = static_cast<int>(p / (static_cast<long>(W) * H));
+      if (mask_split && code[p] == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+      store8(y_split + split_index(b, h, w, H, W) * C + c, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct GradSrc {
+  const __nv_bfloat16* ptr;  // null = absent
+  long pix_stride;           // elements between consecutive pixels
+  int chan_off;              // first channel of this layer's slice inside the source tensor
+  int split;                 // 1: source pixels are in parity-split order
+};
+
+__device__ __forceinline__ void load_grad(const GradSrc& s0, const GradSrc& s1, long p, long ps, int c,
+                                          float (&g)[8]) {
+  load8(s0.ptr + (s0.split ? ps : p) * s0.pix_stride + s0.chan_off + c, g);
+  if (s1.ptr) {
+    float t[8];
+    load8(s1.ptr + (s1.split ? ps : p) * s1.pix_stride + s1.chan_off + c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += t[j];
+  }
+}
+
+// sums per channel over all pixels: [0] g', [1] g'*z, [2] r*g', [3] r*z, [4] r   (g' = g * act'(z*scale+shift))
+// block = 256 threads = (C/8 channel vectors) x (256/(C/8) pixel lanes); partial[block][5][C]
+__global__ void bn_bwd_reduce_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16* __restrict__ z, long M,
+                                     int C, int H, int W, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, int act, float slope,
+                                     const uint8_t* __restrict__ code, const float* __restrict__ lut,
+                                     float* __restrict__ partial) {
+  extern __shared__ float red[];  // [lanes][5*8] per channel vector -> reduced below
+  const int cv = C >> 3;
+  const int lanes = blockDim.x / cv;
+  const int my_cv = threadIdx.x % cv;
+  const int my_lane = threadIdx.x / cv;
+  const int c = my_cv << 3;
+  float acc[5][8];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  float sc[8], sh[8];
+  ldg8f(scale + c, sc);
+  ldg8f(shift + c, sh);
+  const bool need_split = s0.split || (s1.ptr && s1.split);
+  if (my_lane < lanes) {
+    for (long p = static_cast<long>(blockIdx.x) * lanes + my_lane; p < M;
+         p += static_cast<long>(gridDim.x) * lanes) {
+      long ps = 0;
+      if (need_split) {
+        const int w = static_cast<int>(p % W);
+        const int h = static_cast<int>((p / W) % H);
+        const int b = static_cast<int>(p / (static_cast<long>(W) * H));
+        ps = split_index(b, h, w, H, W);
+      }
+      float g[8], zz[8];
+      load_grad(s0, s1, p, ps, c, g);
+      load8(z + p * C + c, zz);
+      const float r = code ? __ldg(lut + code[p]) : 1.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = zz[j] * sc[j] + sh[j];
+        float gg = g[j];
+        if (act == 1) gg = pre > 0.f ? gg : 0.f;
+        else if (act == 2) gg = pre > 0.f ? gg : gg * slope;
+        acc[0][j] += gg;
+        acc[1][j] += gg * zz[j];
+        acc[2][j] += r * gg;
+        acc[3][j] += r * zz[j];
+        acc[4][j] += r;
+      }
+    }
+  }
+  // reduce over pixel lanes through shared memory
+  float* mine = red + (static_cast<long>(my_lane) * cv + my_cv) * 40;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[k * 8 + j] = acc[k][j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < cv * 40; i += blockDim.x) {
+    const int v = i / 40, kj = i % 40;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[(static_cast<long>(l) * cv + v) * 40 + kj];
+    const int k = kj / 8, j = kj % 8;
+    partial[(static_cast<long>(blockIdx.x) * 5 + k) * C + v * 8 + j] = s;
+  }
+}
+
+// coeff[0]=scale [1]=mean [2]=invstd [3]=c1 (= dbeta/M) [4]=c2 (= dgamma/M), each [C]
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
+                                       const float* __restrict__ scale, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, float* __restrict__ coeff,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ dbias, int accumulate, int batch_stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s[5] = {0, 0, 0, 0, 0};
+  for (int r = 0; r < rows; ++r)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s[k] += partial[(static_cast<long>(r) * 5 + k) * C + c];
+  const double mu = mean[c], is = invstd[c], sc = scale[c];
+  const double db = s[0];                          // dL/dbeta
+  const double dg = is * (s[1] - mu * s[0]);       // dL/dgamma = sum g' * zhat
+  // eval-mode BatchNorm (running statistics) has no dependence of mean/var on the batch
+  const double c1 = batch_stats ? db / count : 0.0, c2 = batch_stats ? dg / count : 0.0;
+  coeff[c] = static_cast<float>(sc);
+  coeff[C + c] = static_cast<float>(mu);
+  coeff[2 * C + c] = static_cast<float>(is);
+  coeff[3 * C + c] = static_cast<float>(c1);
+  coeff[4 * C + c] = static_cast<float>(c2);
+  // conv bias: out = (conv + b) * r  ->  db = sum_p r * dL/dz,  dL/dz = scale * (g' - c1 - zhat*c2)
+  const double dbi = sc * (s[2] - c1 * s[4] - c2 * is * (s[3] - mu * s[4]));
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + static_cast<float>(dg);
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + static_cast<float>(db);
+  if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + static_cast<float>(dbi);
+}
+
+// gz[p][c] = r[p] * scale[c] * (g' - c1[c] - zhat * c2[c])
+__global__ void bn_bwd_apply_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16* __restrict__ z, long M, int C,
+                                    int H, int W, const float* __restrict__ shift,
+                                    const float* __restrict__ coeff, int act, float slope,
+                                    const uint8_t* __restrict__ code, const float* __restrict__ lut,
+                                    __nv_bfloat16* __restrict__ gz) {
+  const int cv = C >> 3;
+  const long total = M * cv;
+  const bool need_split = s0.split || (s1.ptr && s1.split);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = i / cv;
+    const int c = static_cast<int>(i % cv) << 3;
+    long ps = 0;
+    if (need_split) {
+      const int w = static_cast<int>(p % W);
+      const int h = static_cast<int>((p / W) % H);
+      const int b = static_cast<int>(p / (static_cast<long>(W) * H));
+      ps = split_index(b, h, w, H, W);
+    }
+    float g[8], zz[8], sc[8], sh[8], mu[8], is[8], c1[8], c2[8];
+    load_grad(s0, s1, p, ps, c, g);
+    load8(z + p * C + c, zz);
+    ldg8f(coeff + c, sc);
+    ldg8f(shift + c, sh);
+    ldg8f(coeff + C + c, mu);
+    ldg8f(coeff + 2 * C + c, is);
+    ldg8f(coeff + 3 * C + c, c1);
+    ldg8f(coeff + 4 * C + c, c2);
+    const float r = code ? __ldg(lut + code[p]) : 1.f;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float pre = zz[j] * sc[j] + sh[j];
+      float gg = g[j];
+      if (act == 1) gg = pre > 0.f ? gg : 0.f;
+      else if (act == 2) gg = pre > 0.f ? gg : gg * slope;
+      const float zhat = (zz[j] - mu[j]) * is[j];
+      o[j] = r * sc[j] * (gg - c1[j] - zhat * c2[j]);
+    }
+    store8(gz + p * C + c, o);
+  }
+}
+
+static int ew_grid(long n, int block) {
+  long g = (n + block - 1) / block;
+  const long cap = static_cast<long>(num_sms() > 0 ? num_sms() : 148) * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+static GradSrc to_src(const tg_grad_src& s) {
+  GradSrc r;
+  r.ptr = reinterpret_cast<const __nv_bfloat16*>(s.ptr);
+  r.pix_stride = s.pix_stride;
+  r.chan_off = s.chan_off;
+  r.split = s.split;
+  return r;
+}
+
+}  // namespace tg
+
+extern "C" int tg_bn_finalize(const float* partial, int rows, int C, double count, const float* gamma,
+                              const float* beta, float eps, float momentum, float* running_mean,
+                              float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                              void* stream) {
+  using namespace tg;
+  TG_REQUIRE(partial && scale && shift && mean && invstd && rows > 0 && C > 0 && count > 0,
+             "tg_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, rows, C, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_bn_eval_coeff(int C, const float* gamma, const float* beta, const float* running_mean,
+                                const float* running_var, float eps, float* scale, float* shift, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(running_mean && running_var && scale && shift && C > 0, "tg_bn_eval_coeff: bad arguments");
+  bn_eval_coeff_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      C, gamma, beta, running_mean, running_var, eps, scale, shift);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_bn_apply(const void* z, int B, int H, int W, int C, const float* scale, const float* shift,
+                           int act, float slope, const uint8_t* code, void* y_nhwc, void* y_split,
+                           int mask_split, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(z && scale && shift && C % 8 == 0, "tg_bn_apply: bad arguments (C=%d)", C);
+  TG_REQUIRE(y_nhwc || y_split, "tg_bn_apply: no output requested");
+  TG_REQUIRE(!y_split || (H % 2 == 0 && W % 2 == 0), "tg_bn_apply: parity-split output needs even H, W");
+  TG_REQUIRE(!(mask_split && y_split) || code, "tg_bn_apply: mask_split needs code");
+  const long M = static_cast<long>(B) * H * W;
+  bn_apply_kernel<<<ew_grid(M * (C / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(z), M, C, H, W, scale, shift, act, slope, code,
+      reinterpret_cast<__nv_bfloat16*>(y_nhwc), reinterpret_cast<__nv_bfloat16*>(y_split), mask_split);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_bn_bwd_reduce(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H,
+                                int W, int C, const float* scale, const float* shift, int act, float slope,
+                                const uint8_t* code, const float* lut_dev, float* partial, int rows_cap,
+                                int* rows_used, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(g0 && g0->ptr && z && scale && shift && partial && rows_used, "tg_bn_bwd_reduce: null pointer");
+  TG_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "tg_bn_bwd_reduce: unsupported C=%d", C);
+  TG_REQUIRE(!code || lut_dev, "tg_bn_bwd_reduce: code needs a device LUT");
+  const long M = static_cast<long>(B) * H * W;
+  const int cv = C / 8, lanes = 256 / cv;
+  long grid = (M + lanes - 1) / lanes;
+  const long cap = static_cast<long>(num_sms()) * 4;
+  if (grid > cap) grid = cap;
+  if (grid > rows_cap) grid = rows_cap;
+  TG_REQUIRE(grid >= 1, "tg_bn_bwd_reduce: rows_cap must be >= 1");
+  *rows_used = static_cast<int>(grid);
+  GradSrc s0 = to_src(*g0), s1;
+  if (g1 && g1->ptr) s1 = to_src(*g1);
+  else { s1.ptr = nullptr; s1.pix_stride = 0; s1.chan_off = 0; s1.split = 0; }
+  const size_t smem = static_cast<size_t>(lanes) * cv * 40 * sizeof(float);
+  bn_bwd_reduce_kernel<<<static_cast<int>(grid), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      s0, s1, reinterpret_cast<const __nv_bfloat16*>(z), M, C, H, W, scale, shift, act, slope, code, lut_dev,
+      partial);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_bn_bwd_finalize(const float* partial, int rows, int C, double count, const float* scale,
+                                  const float* mean, const float* invstd, float* coeff, float* dgamma,
+                                  float* dbeta, float* dbias, int accumulate, int batch_stats, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(partial && scale && mean && invstd && coeff && rows > 0, "tg_bn_bwd_finalize: bad arguments");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, rows, C, count, scale, mean, invstd, coeff, dgamma, dbeta, dbias, accumulate, batch_stats);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_bn_bwd_apply(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H, int W,
+                               int C, const float* shift, const float* coeff, int act, float slope,
+                               const uint8_t* code, const float* lut_dev, void* gz, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(g0 && g0->ptr && z && shift && coeff && gz, "tg_bn_bwd_apply: null pointer");
+  TG_REQUIRE(C % 8 == 0, "tg_bn_bwd_apply: C must be a multiple of 8");
+  TG_REQUIRE(!code || lut_dev, "tg_bn_bwd_apply: code needs a device LUT");
+  const long M = static_cast<long>(B) * H * W;
+  GradSrc s0 = to_src(*g0), s1;
+  if (g1 && g1->ptr) s1 = to_src(*g1);
+  else { s1.ptr = nullptr; s1.pix_stride = 0; s1.chan_off = 0; s1.split = 0; }
+  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      s0, s1, reinterpret_cast<const __nv_bfloat16*>(z), M, C, H, W, shift, coeff, act, slope, code, lut_dev,
+      reinterpret_cast<__nv_bfloat16*>(gz));
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

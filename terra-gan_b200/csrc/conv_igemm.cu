@@ -63,10 +63,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   // ---- one-time setup ----
   for (int i = threadIdx.x; i < S::kStatsFloats; i += blockDim.x) s_stats[i] = 0.f;
-  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
-    s_vec[i] = p.bias ? p.bias[i] : 0.f;
-    s_vec[512 + i] = p.scale ? p.scale[i] : 1.f;
-    s_vec[1024 + i] = p.shift ? p.shift[i] : 0.f;
+  // per-channel epilogue vectors are staged once (channels <= 512 whenever any of them is used)
+  const bool has_vec = p.bias != nullptr || p.scale != nullptr || p.shift != nullptr;
+  if (has_vec) {
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+      s_vec[i] = p.bias ? p.bias[i] : 0.f;
+      s_vec[512 + i] = p.scale ? p.scale[i] : 1.f;
+      s_vec[1024 + i] = p.shift ? p.shift[i] : 0.f;
+    }
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -190,6 +194,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float rs = 1.f;
       if (p.code != nullptr && valid) rs = p.lut[p.code[pix]];
       __nv_bfloat16* orow = p.out + pix * p.Cout + nt * BN;
+      const __nv_bfloat16* grow = p.gate ? p.gate + pix * p.Cout + nt * BN : nullptr;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -203,8 +208,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = (__uint_as_float(raw[j]) + s_vec[n0 + j]) * rs;
-          v[j] = valid ? x : 0.f;
+          float x = __uint_as_float(raw[j]);
+          if (has_vec) x += s_vec[n0 + j];
+          v[j] = valid ? x * rs : 0.f;
         }
         if (p.stats != nullptr) {
           float sq[32], sm[32];
@@ -219,10 +225,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           my_stats[512 + n0 + lane] += csq;
         }
         uint32_t packed[16];
+        uint32_t gbits[16];
+        if (grow != nullptr && valid) {
+          const uint4* gsrc = reinterpret_cast<const uint4*>(grow + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 t = gsrc[j];
+            gbits[4 * j] = t.x; gbits[4 * j + 1] = t.y; gbits[4 * j + 2] = t.z; gbits[4 * j + 3] = t.w;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float a = v[j] * s_vec[512 + n0 + j] + s_vec[1024 + n0 + j];
-          float c = v[j + 1] * s_vec[512 + n0 + j + 1] + s_vec[1024 + n0 + j + 1];
+          float a = v[j], c = v[j + 1];
+          if (has_vec) {
+            a = a * s_vec[512 + n0 + j] + s_vec[1024 + n0 + j];
+            c = c * s_vec[512 + n0 + j + 1] + s_vec[1024 + n0 + j + 1];
+          }
+          if (grow != nullptr && valid) {
+            // derivative of ReLU / LeakyReLU of the tensor this gradient flows into
+            const float2 gv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gbits[j >> 1]));
+            if (!(gv.x > 0.f)) a *= p.gate_slope;
+            if (!(gv.y > 0.f)) c *= p.gate_slope;
+          }
           if (p.act == 1) {
             a = fmaxf(a, 0.f);
             c = fmaxf(c, 0.f);
@@ -307,8 +331,9 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   using namespace tg;
   TG_REQUIRE(a != nullptr, "tg_conv_igemm: null args");
   TG_REQUIRE(a->C > 0 && a->C % 64 == 0, "tg_conv_igemm: C=%d must be a positive multiple of 64", a->C);
-  TG_REQUIRE(a->N > 0 && a->N % 64 == 0 && a->N <= 512,
-             "tg_conv_igemm: N=%d must be a multiple of 64 and <= 512", a->N);
+  const bool per_channel = a->bias || a->scale || a->shift || a->stats;
+  TG_REQUIRE(a->N > 0 && a->N % 64 == 0 && a->N <= (per_channel ? 512 : 1024),
+             "tg_conv_igemm: N=%d must be a multiple of 64 and <= %d", a->N, per_channel ? 512 : 1024);
   TG_REQUIRE(a->num_sub >= 1 && a->num_sub <= TG_MAX_SUB, "tg_conv_igemm: bad num_sub %d", a->num_sub);
   TG_REQUIRE(a->num_taps >= 1 && a->num_taps <= TG_MAX_TAPS, "tg_conv_igemm: bad num_taps %d", a->num_taps);
   TG_REQUIRE(a->code == nullptr || (a->lut != nullptr && a->lut_len >= 1 && a->lut_len <= TG_MAX_TAPS),
@@ -363,6 +388,8 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   kp.act = a->act;
   kp.slope = a->slope;
   kp.stats = a->stats;
+  kp.gate = reinterpret_cast<const __nv_bfloat16*>(a->gate);
+  kp.gate_slope = a->gate_slope;
 
   // A: channels-last activations as a 5-D tensor (C, W, H, P, B)
   CUtensorMap tmA, tmB;

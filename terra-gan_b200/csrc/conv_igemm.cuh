@@ -39,6 +39,8 @@ struct ConvKParams {
   int act;                        // 0 none, 1 ReLU, 2 LeakyReLU(slope)
   float slope;
   float* stats;                   // [gridDim.x][2][Cout] per-CTA (sum, sum of squares) or null
+  const __nv_bfloat16* gate;      // same shape as out, or null: out *= (gate > 0 ? 1 : gate_slope)
+  float gate_slope;
 };
 
 struct WgradBlk {                 // one 64-row block of dW^T: (tap, 64-channel block of the input)

@@ -1,0 +1,532 @@
+// direct_conv.cu — the bandwidth-bound convolutions of the path (arithmetic intensity <= 46 FLOP/B,
+// SURVEY.md §8a): one input channel (enc1 7x7/s2, Discriminator model[0] 4x4/s2, VGG conv0 with its
+// three identical input channels folded into one) and one output channel (`final` 3x3 64->1 with
+// sigmoid + composite, Discriminator model[11] 4x4 512->1), forward, data- and weight-gradient.
+// These are CUDA-core kernels on purpose: K = 16..49 or N = 1 cannot feed a 128xN tensor-core tile.
+//
+// Reference ops replaced:
+//   PConv2d enc1: input*mask, input_conv, mask ratio       mvp_gan/src/models/pconv.py:27-43
+//   Discriminator model[0] (+LeakyReLU) and model[11]       mvp_gan/src/models/discriminator.py:17,22
+//   VGG16 features[0] on input.repeat(1,3,1,1)              mvp_gan/src/utils/losses.py:79-89
+//   final conv + sigmoid + `out*(1-mask) + x*mask`          mvp_gan/src/models/generator.py:56-62
+// and the autograd backward of each.
+#include "tg_common.cuh"
+#include "../../include/terragan_b200.h"
+
+namespace tg {
+
+__device__ __forceinline__ long dc_split_index(int b, int h, int w, int H, int W) {
+  return ((static_cast<long>(b) * 4 + 2 * (h & 1) + (w & 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1 -> 64 channels, forward.  One thread = one output pixel x 64 channels; block = 32x4 pixel tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kC1TW = 32, kC1TH = 4;
+
+template <int K, int S>
+__global__ void __launch_bounds__(128)
+conv_c1_fwd_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmask, int B, int H, int W, int pad,
+                   const float* __restrict__ wgt /*[64][K*K]*/, const float* __restrict__ bias, int Ho, int Wo,
+                   const uint8_t* __restrict__ code, const float* __restrict__ lut, int act, float slope,
+                   __nv_bfloat16* __restrict__ out, int out_split, float* __restrict__ stats) {
+  constexpr int IW = (kC1TW - 1) * S + K, IH = (kC1TH - 1) * S + K;
+  __shared__ float s_w[K * K][64];
+  __shared__ float s_in[IH][IW + 1];
+  __shared__ float s_stats[4][2][64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 64 * K * K; i += 128) s_w[i % (K * K)][i / (K * K)] = wgt[i];
+  for (int i = tid; i < 4 * 2 * 64; i += 128) (&s_stats[0][0][0])[i] = 0.f;
+  const int tiles_w = (Wo + kC1TW - 1) / kC1TW, tiles_h = (Ho + kC1TH - 1) / kC1TH;
+  const long total_tiles = static_cast<long>(B) * tiles_h * tiles_w;
+  const int tx = tid % kC1TW, ty = tid / kC1TW;
+
+  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tw = static_cast<int>(tile % tiles_w);
+    const int th = static_cast<int>((tile / tiles_w) % tiles_h);
+    const int b = static_cast<int>(tile / (static_cast<long>(tiles_w) * tiles_h));
+    const int ih0 = th * kC1TH * S - pad, iw0 = tw * kC1TW * S - pad;
+    __syncthreads();  // previous tile's s_in consumers are done (also covers the s_w fill)
+    for (int i = tid; i < IH * IW; i += 128) {
+      const int r = i / IW, c = i % IW;
+      const int h = ih0 + r, w = iw0 + c;
+      float v = 0.f;
+      if (h >= 0 && h < H && w >= 0 && w < W) {
+        const long o = (static_cast<long>(b) * H + h) * W + w;
+        v = x[o];
+        if (xmask != nullptr && xmask[o] == 0) v = 0.f;
+      }
+      s_in[r][c] = v;
+    }
+    __syncthreads();
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int kh = 0; kh < K; ++kh) {
+#pragma unroll
+      for (int kw = 0; kw < K; ++kw) {
+        const float xv = s_in[ty * S + kh][tx * S + kw];
+        const float4* wr = reinterpret_cast<const float4*>(&s_w[kh * K + kw][0]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 wv = wr[j];
+          acc[4 * j] += xv * wv.x;
+          acc[4 * j + 1] += xv * wv.y;
+          acc[4 * j + 2] += xv * wv.z;
+          acc[4 * j + 3] += xv * wv.w;
+        }
+      }
+    }
+    const int ho = th * kC1TH + ty, wo = tw * kC1TW + tx;
+    const bool valid = ho < Ho && wo < Wo;
+    const long pix = (static_cast<long>(b) * Ho + ho) * Wo + wo;
+    float rs = 1.f;
+    if (code != nullptr && valid) rs = __ldg(lut + code[pix]);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = valid ? (acc[j] + __ldg(bias + j)) * rs : 0.f;
+    if (stats != nullptr) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float sm[32], sq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          sm[j] = acc[half * 32 + j];
+          sq[j] = sm[j] * sm[j];
+        }
+        const float a = warp_transpose_sum32(sm);
+        const float q2 = warp_transpose_sum32(sq);
+        s_stats[warp][0][half * 32 + lane] += a;
+        s_stats[warp][1][half * 32 + lane] += q2;
+      }
+    }
+    if (valid) {
+      const long opix = out_split ? dc_split_index(b, ho, wo, Ho, Wo) : pix;
+      uint4* dst = reinterpret_cast<uint4*>(out + opix * 64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float t = acc[8 * j + q];
+          if (act == 1) t = fmaxf(t, 0.f);
+          else if (act == 2) t = t > 0.f ? t : t * slope;
+          v[q] = t;
+        }
+        dst[j] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                            pack_bf16x2(v[6], v[7]));
+      }
+    }
+  }
+  if (stats != nullptr) {
+    __syncthreads();
+    const int c = tid % 64, which = tid / 64;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += s_stats[q][which][c];
+    stats[(static_cast<long>(blockIdx.x) * 2 + which) * 64 + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1 -> 64 channels, weight (and bias) gradient. Warp = pixel stream, lane = output-channel pair.
+// partial[block][64][K*K (+1 for bias)]
+// ------------------------------------------------------------------------------------------------
+template <int K, int S>
+__global__ void __launch_bounds__(256)
+conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmask, int B, int H, int W, int pad,
+                     const __nv_bfloat16* __restrict__ g /*[B][Ho][Wo][64]*/, int Ho, int Wo, int g_split,
+                     float* __restrict__ partial) {
+  constexpr int T = K * K;
+  __shared__ float s_red[64][T + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 64 * (T + 1); i += 256) (&s_red[0][0])[i] = 0.f;
+  __syncthreads();
+  float acc[T + 1][2];
+#pragma unroll
+  for (int t = 0; t <= T; ++t) acc[t][0] = acc[t][1] = 0.f;
+  const long M = static_cast<long>(B) * Ho * Wo;
+  for (long p = static_cast<long>(blockIdx.x) * 8 + warp; p < M; p += static_cast<long>(gridDim.x) * 8) {
+    const int wo = static_cast<int>(p % Wo);
+    const int ho = static_cast<int>((p / Wo) % Ho);
+    const int b = static_cast<int>(p / (static_cast<long>(Wo) * Ho));
+    const long gp = g_split ? dc_split_index(b, ho, wo, Ho, Wo) : p;
+    const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(g + gp * 64 + 2 * lane);
+    const float2 gf = __bfloat1622float2(g2);
+    acc[T][0] += gf.x;
+    acc[T][1] += gf.y;
+    const float* xb = x + static_cast<long>(b) * H * W;
+    const uint8_t* mb = xmask ? xmask + static_cast<long>(b) * H * W : nullptr;
+#pragma unroll
+    for (int kh = 0; kh < K; ++kh) {
+      const int h = ho * S + kh - pad;
+#pragma unroll
+      for (int kw = 0; kw < K; ++kw) {
+        const int w = wo * S + kw - pad;
+        float xv = 0.f;
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+          xv = __ldg(xb + h * W + w);
+          if (mb != nullptr && mb[h * W + w] == 0) xv = 0.f;
+        }
+        acc[kh * K + kw][0] += xv * gf.x;
+        acc[kh * K + kw][1] += xv * gf.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t <= T; ++t) {
+    atomicAdd(&s_red[2 * lane][t], acc[t][0]);
+    atomicAdd(&s_red[2 * lane + 1][t], acc[t][1]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * (T + 1); i += 256)
+    partial[static_cast<long>(blockIdx.x) * 64 * (T + 1) + i] = (&s_red[0][0])[i];
+}
+
+// dw[co][t] (+)= sum_rows partial[row][co][t];  db[co] (+)= partial[..][co][T]
+__global__ void conv_c1_wgrad_reduce_kernel(const float* __restrict__ partial, int rows, int T,
+                                            float* __restrict__ dw, float* __restrict__ db, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * (T + 1)) return;
+  const int co = i / (T + 1), t = i % (T + 1);
+  double s = 0.0;
+  for (int r = 0; r < rows; ++r) s += partial[static_cast<long>(r) * 64 * (T + 1) + i];
+  if (t < T) {
+    float* d = dw + co * T + t;
+    *d = (accumulate ? *d : 0.f) + static_cast<float>(s);
+  } else if (db != nullptr) {
+    db[co] = (accumulate ? db[co] : 0.f) + static_cast<float>(s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C -> 1 channel "gather" convolution with per-parity tap classes.
+//   acc[b][oh][ow] = sum_{t in class} sum_c x[b][base + d_t][c] * w[cls][t][c]
+// ncls = 1: base = (oh, ow). ncls = 4: cls = 2*(oh&1)+(ow&1), base = (oh>>1, ow>>1)  (this form is
+// the data-gradient of a stride-2 1->C convolution: Discriminator model[0]).
+// mode 0: out = acc + bias.   mode 1 (generator.py:56-62): sig = sigmoid(acc + bias) is saved and
+// out = sig * (1 - mask) + xin * mask.
+// 8 lanes per output pixel (8 channels each, 16-byte loads), 4 pixels per warp.
+// ------------------------------------------------------------------------------------------------
+struct To1Taps {
+  int ncls;
+  int count[4];
+  int begin[4];
+  int8_t dh[TG_MAX_TAPS], dw[TG_MAX_TAPS];
+};
+
+__global__ void __launch_bounds__(256)
+conv_to1_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_split, int B, int H, int W, int C,
+                    const float* __restrict__ wgt /*[ntaps][C]*/, To1Taps taps, const float* __restrict__ bias, int Ho, int Wo, int mode,
+                    const uint8_t* __restrict__ mask, const float* __restrict__ xin, float* __restrict__ out,
+                    float* __restrict__ sig_out) {
+  const int sub = threadIdx.x & 7;
+  const long gpix = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 3;
+  const long stride = (static_cast<long>(gridDim.x) * blockDim.x) >> 3;
+  const long M = static_cast<long>(B) * Ho * Wo;
+  const long iters = (M + stride - 1) / stride;
+  for (long it = 0; it < iters; ++it) {
+    const long p = gpix + it * stride;
+    const bool live = p < M;
+    float acc = 0.f;
+    int ow = 0, oh = 0, b = 0;
+    if (live) {
+      ow = static_cast<int>(p % Wo);
+      oh = static_cast<int>((p / Wo) % Ho);
+      b = static_cast<int>(p / (static_cast<long>(Wo) * Ho));
+      int cls = 0, bh = oh, bw = ow;
+      if (taps.ncls == 4) {
+        cls = 2 * (oh & 1) + (ow & 1);
+        bh = oh >> 1;
+        bw = ow >> 1;
+      }
+      const __nv_bfloat16* xb = x + static_cast<long>(b) * H * W * C;
+      for (int t = taps.begin[cls]; t < taps.begin[cls] + taps.count[cls]; ++t) {
+        const int h = bh + taps.dh[t], w = bw + taps.dw[t];
+        if (h < 0 || h >= H || w < 0 || w >= W) continue;
+        const __nv_bfloat16* xp = x_split ? x + dc_split_index(b, h, w, H, W) * C
+                                          : xb + (static_cast<long>(h) * W + w) * C;
+        const float* wp = wgt + static_cast<long>(t) * C;
+        for (int c = sub * 8; c < C; c += 64) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(xp + c);
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + c));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + c) + 1);
+          const float2 a = __bfloat1622float2(hh[0]), bq = __bfloat1622float2(hh[1]);
+          const float2 cq = __bfloat1622float2(hh[2]), d = __bfloat1622float2(hh[3]);
+          acc += a.x * w0.x + a.y * w0.y + bq.x * w0.z + bq.y * w0.w + cq.x * w1.x + cq.y * w1.y + d.x * w1.z +
+                 d.y * w1.w;
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (live && sub == 0) {
+      const float v = acc + (bias ? __ldg(bias) : 0.f);
+      if (mode == 0) {
+        out[p] = v;
+      } else {
+        const float s = 1.f / (1.f + __expf(-v));
+        if (sig_out) sig_out[p] = s;
+        const float m = mask[p] ? 1.f : 0.f;
+        out[p] = s * (1.f - m) + xin[p] * m;
+      }
+    }
+  }
+}
+
+// data gradient of a stride-1 C->1 conv: dx[b][h][w][c] = sum_t g[b][h - dh_t][w - dw_t] * w[t][c]
+__global__ void conv_to1_bwd_data_kernel(const float* __restrict__ g, int B, int Ho, int Wo,
+                                         const float* __restrict__ wgt, To1Taps taps, int H, int W, int C,
+                                         __nv_bfloat16* __restrict__ dx) {
+  const int cv = C >> 3;
+  const long total = static_cast<long>(B) * H * W * cv;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = i / cv;
+    const int c = static_cast<int>(i % cv) << 3;
+    const int w = static_cast<int>(p % W);
+    const int h = static_cast<int>((p / W) % H);
+    const int b = static_cast<int>(p / (static_cast<long>(W) * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int t = 0; t < taps.count[0]; ++t) {
+      const int oh = h - taps.dh[t], ow = w - taps.dw[t];
+      if (oh < 0 || oh >= Ho || ow < 0 || ow >= Wo) continue;
+      const float gv = __ldg(g + (static_cast<long>(b) * Ho + oh) * Wo + ow);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wgt + static_cast<long>(t) * C + c));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wgt + static_cast<long>(t) * C + c) + 1);
+      acc[0] += gv * w0.x; acc[1] += gv * w0.y; acc[2] += gv * w0.z; acc[3] += gv * w0.w;
+      acc[4] += gv * w1.x; acc[5] += gv * w1.y; acc[6] += gv * w1.z; acc[7] += gv * w1.w;
+    }
+    *reinterpret_cast<uint4*>(dx + p * C + c) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                   pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// weight gradient of a stride-1 C->1 conv: dw[t][c] = sum_o g[o] * x[o + d_t][c]; db = sum_o g[o].
+// grid = (pixel blocks, C/64); 8 lanes per pixel; each lane keeps T x 8 accumulators.
+template <int T>
+__global__ void __launch_bounds__(128)
+conv_to1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ g,
+                      int Ho, int Wo, To1Taps taps, float* __restrict__ partial /*[gridDim.x][T][C]*/,
+                      float* __restrict__ partial_b /*[gridDim.x]*/) {
+  __shared__ float s_red[T][64];  // [tap][channel of the slab], accumulated with shared atomics
+  __shared__ float s_b;
+  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;  // 16 pixel groups
+  for (int i = threadIdx.x; i < T * 64; i += 128) (&s_red[0][0])[i] = 0.f;
+  if (threadIdx.x == 0) s_b = 0.f;
+  __syncthreads();
+  const int c0 = blockIdx.y * 64 + sub * 8;
+  float acc[T][8];
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  float gsum = 0.f;
+  const long M = static_cast<long>(B) * Ho * Wo;
+  for (long p = static_cast<long>(blockIdx.x) * 16 + grp; p < M; p += static_cast<long>(gridDim.x) * 16) {
+    const int ow = static_cast<int>(p % Wo);
+    const int oh = static_cast<int>((p / Wo) % Ho);
+    const int b = static_cast<int>(p / (static_cast<long>(Wo) * Ho));
+    const float gv = __ldg(g + p);
+    gsum += gv;
+    const __nv_bfloat16* xb = x + static_cast<long>(b) * H * W * C + c0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int h = oh + taps.dh[t], w = ow + taps.dw[t];
+      if (h < 0 || h >= H || w < 0 || w >= W) continue;
+      const uint4 raw = *reinterpret_cast<const uint4*>(xb + (static_cast<long>(h) * W + w) * C);
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(hh[q]);
+        acc[t][2 * q] += gv * f.x;
+        acc[t][2 * q + 1] += gv * f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_red[t][sub * 8 + j], acc[t][j]);
+  if (sub == 0) atomicAdd(&s_b, gsum);
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * 64; i += 128) {
+    const int t = i / 64, c = i % 64;
+    partial[(static_cast<long>(blockIdx.x) * T + t) * C + blockIdx.y * 64 + c] = s_red[t][c];
+  }
+  if (threadIdx.x == 0 && blockIdx.y == 0 && partial_b != nullptr) partial_b[blockIdx.x] = s_b;
+}
+
+// dw_out[c][perm[t]] (+)= sum_rows partial[row][t][c]   (PyTorch layout [1][C][kh][kw]);  db (+)= sum partial_b
+__global__ void conv_to1_wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_b,
+                                             int rows, int T, int C, float* __restrict__ dw, float* __restrict__ db,
+                                             int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T * C) {
+    const int t = i / C, c = i % C;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += partial[(static_cast<long>(r) * T + t) * C + c];
+    float* d = dw + static_cast<long>(c) * T + t;
+    *d = (accumulate ? *d : 0.f) + static_cast<float>(s);
+  }
+  if (i == 0 && db != nullptr && partial_b != nullptr) {
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += partial_b[r];
+    db[0] = (accumulate ? db[0] : 0.f) + static_cast<float>(s);
+  }
+}
+
+static int fill_taps(To1Taps* t, int ncls, const int* count, const int8_t* dh, const int8_t* dw) {
+  int n = 0;
+  t->ncls = ncls;
+  for (int c = 0; c < 4; ++c) {
+    t->begin[c] = n;
+    t->count[c] = c < ncls ? count[c] : 0;
+    n += t->count[c];
+  }
+  if (n > TG_MAX_TAPS) return -1;
+  for (int i = 0; i < n; ++i) {
+    t->dh[i] = dh[i];
+    t->dw[i] = dw[i];
+  }
+  return n;
+}
+
+static int dc_grid(long n, int block, int per_sm) {
+  long g = (n + block - 1) / block;
+  const long cap = static_cast<long>(num_sms() > 0 ? num_sms() : 148) * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace tg
+
+#define TG_C1_DISPATCH(K_, S_, CALL)            \
+  if (k == K_ && s == S_) {                     \
+    constexpr int K = K_, S = S_;               \
+    CALL;                                       \
+    handled = true;                             \
+  }
+
+extern "C" int tg_conv_c1_fwd(const float* x, const uint8_t* xmask, int B, int H, int W, int k, int s, int pad,
+                              const float* wgt, const float* bias, const uint8_t* code, const float* lut_dev, int act,
+                              float slope, void* out, int out_split, float* stats, int stats_rows_cap,
+                              int* stats_rows_used, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && wgt && bias && out, "tg_conv_c1_fwd: null pointer");
+  TG_REQUIRE(!code || lut_dev, "tg_conv_c1_fwd: code needs a device LUT");
+  const int Ho = (H + 2 * pad - k) / s + 1, Wo = (W + 2 * pad - k) / s + 1;
+  TG_REQUIRE(!out_split || (Ho % 2 == 0 && Wo % 2 == 0), "tg_conv_c1_fwd: parity-split output needs even Ho, Wo");
+  const long tiles = static_cast<long>(B) * ((Ho + kC1TH - 1) / kC1TH) * ((Wo + kC1TW - 1) / kC1TW);
+  int grid = static_cast<int>(tiles < 4L * num_sms() ? tiles : 4L * num_sms());
+  if (stats) {
+    TG_REQUIRE(stats_rows_used != nullptr, "tg_conv_c1_fwd: stats_rows_used is null");
+    if (grid > stats_rows_cap) grid = stats_rows_cap;
+    TG_REQUIRE(grid >= 1, "tg_conv_c1_fwd: stats_rows_cap must be >= 1");
+    *stats_rows_used = grid;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  bool handled = false;
+  TG_C1_DISPATCH(7, 2, (conv_c1_fwd_kernel<K, S><<<grid, 128, 0, st>>>(x, xmask, B, H, W, pad, wgt, bias, Ho, Wo, code, lut_dev, act, slope, o, out_split, stats)))
+  TG_C1_DISPATCH(4, 2, (conv_c1_fwd_kernel<K, S><<<grid, 128, 0, st>>>(x, xmask, B, H, W, pad, wgt, bias, Ho, Wo, code, lut_dev, act, slope, o, out_split, stats)))
+  TG_C1_DISPATCH(3, 1, (conv_c1_fwd_kernel<K, S><<<grid, 128, 0, st>>>(x, xmask, B, H, W, pad, wgt, bias, Ho, Wo, code, lut_dev, act, slope, o, out_split, stats)))
+  TG_REQUIRE(handled, "tg_conv_c1_fwd: unsupported window k=%d s=%d (supported: 7/2, 4/2, 3/1)", k, s);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_conv_c1_wgrad(const float* x, const uint8_t* xmask, int B, int H, int W, int k, int s, int pad,
+                                const void* g, int g_split, float* partial, int rows_cap, float* dw, float* db,
+                                int accumulate, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && g && partial && dw, "tg_conv_c1_wgrad: null pointer");
+  const int Ho = (H + 2 * pad - k) / s + 1, Wo = (W + 2 * pad - k) / s + 1;
+  const long M = static_cast<long>(B) * Ho * Wo;
+  int grid = dc_grid(M, 8, 2);
+  if (grid > rows_cap) grid = rows_cap;
+  TG_REQUIRE(grid >= 1, "tg_conv_c1_wgrad: rows_cap must be >= 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* gg = reinterpret_cast<const __nv_bfloat16*>(g);
+  bool handled = false;
+  TG_C1_DISPATCH(7, 2, (conv_c1_wgrad_kernel<K, S><<<grid, 256, 0, st>>>(x, xmask, B, H, W, pad, gg, Ho, Wo, g_split, partial)))
+  TG_C1_DISPATCH(4, 2, (conv_c1_wgrad_kernel<K, S><<<grid, 256, 0, st>>>(x, xmask, B, H, W, pad, gg, Ho, Wo, g_split, partial)))
+  TG_C1_DISPATCH(3, 1, (conv_c1_wgrad_kernel<K, S><<<grid, 256, 0, st>>>(x, xmask, B, H, W, pad, gg, Ho, Wo, g_split, partial)))
+  TG_REQUIRE(handled, "tg_conv_c1_wgrad: unsupported window k=%d s=%d", k, s);
+  TG_CHECK_CUDA(cudaGetLastError());
+  const int T = k * k;
+  conv_c1_wgrad_reduce_kernel<<<(64 * (T + 1) + 127) / 128, 128, 0, st>>>(partial, grid, T, dw, db, accumulate);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_conv_c1_wgrad_rows(void) { return tg::num_sms() * 2; }
+
+extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, int C, const float* wgt, int ncls,
+                               const int* cls_count, const int8_t* tap_dh, const int8_t* tap_dw, const float* bias, int Ho,
+                               int Wo, int mode, const uint8_t* mask, const float* xin, float* out, float* sig_out,
+                               void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && wgt && out && cls_count && tap_dh && tap_dw, "tg_conv_to1_fwd: null pointer");
+  TG_REQUIRE(C % 64 == 0, "tg_conv_to1_fwd: C=%d must be a multiple of 64", C);
+  TG_REQUIRE(ncls == 1 || ncls == 4, "tg_conv_to1_fwd: ncls must be 1 or 4");
+  TG_REQUIRE(mode == 0 || (mask && xin), "tg_conv_to1_fwd: composite mode needs mask and xin");
+  To1Taps taps;
+  TG_REQUIRE(fill_taps(&taps, ncls, cls_count, tap_dh, tap_dw) > 0, "tg_conv_to1_fwd: bad tap table");
+  const long M = static_cast<long>(B) * Ho * Wo;
+  const int grid = dc_grid(M * 8, 256, 8);
+  conv_to1_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), x_split, B, H, W, C, wgt, taps, bias, Ho, Wo, mode, mask, xin, out,
+      sig_out);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_conv_to1_bwd_data(const float* g, int B, int Ho, int Wo, const float* wgt, int ntaps,
+                                    const int8_t* tap_dh, const int8_t* tap_dw, int H, int W, int C, void* dx,
+                                    void* stream) {
+  using namespace tg;
+  TG_REQUIRE(g && wgt && dx && tap_dh && tap_dw && C % 8 == 0, "tg_conv_to1_bwd_data: bad arguments");
+  To1Taps taps;
+  TG_REQUIRE(fill_taps(&taps, 1, &ntaps, tap_dh, tap_dw) > 0, "tg_conv_to1_bwd_data: bad tap table");
+  const long total = static_cast<long>(B) * H * W * (C / 8);
+  conv_to1_bwd_data_kernel<<<dc_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      g, B, Ho, Wo, wgt, taps, H, W, C, reinterpret_cast<__nv_bfloat16*>(dx));
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_conv_to1_wgrad(const void* x, int B, int H, int W, int C, const float* g, int Ho, int Wo, int ntaps,
+                                 const int8_t* tap_dh, const int8_t* tap_dw, float* partial, float* partial_b,
+                                 int rows_cap, float* dw, float* db, int accumulate, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && g && partial && dw && tap_dh && tap_dw, "tg_conv_to1_wgrad: null pointer");
+  TG_REQUIRE(C % 64 == 0, "tg_conv_to1_wgrad: C must be a multiple of 64");
+  To1Taps taps;
+  TG_REQUIRE(fill_taps(&taps, 1, &ntaps, tap_dh, tap_dw) > 0, "tg_conv_to1_wgrad: bad tap table");
+  const long M = static_cast<long>(B) * Ho * Wo;
+  int gx = dc_grid(M, 16, 4);
+  const int slabs = C / 64;
+  if (gx * slabs > 8 * num_sms()) gx = (8 * num_sms() + slabs - 1) / slabs;
+  if (gx > rows_cap) gx = rows_cap;
+  TG_REQUIRE(gx >= 1, "tg_conv_to1_wgrad: rows_cap must be >= 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+  dim3 grid(gx, slabs);
+  if (ntaps == 9) conv_to1_wgrad_kernel<9><<<grid, 128, 0, st>>>(xx, B, H, W, C, g, Ho, Wo, taps, partial, partial_b);
+  else if (ntaps == 16) conv_to1_wgrad_kernel<16><<<grid, 128, 0, st>>>(xx, B, H, W, C, g, Ho, Wo, taps, partial, partial_b);
+  else TG_REQUIRE(false, "tg_conv_to1_wgrad: unsupported tap count %d (supported: 9, 16)", ntaps);
+  TG_CHECK_CUDA(cudaGetLastError());
+  conv_to1_wgrad_reduce_kernel<<<(ntaps * C + 127) / 128, 128, 0, st>>>(partial, partial_b, gx, ntaps, C, dw, db,
+                                                                       accumulate);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_conv_to1_wgrad_rows(void) { return tg::num_sms() * 8; }

@@ -1,0 +1,248 @@
+// resample.cu — decoder input assembly and pooling as fused, vectorised bandwidth kernels.
+//
+// tg_upsample_concat replaces, for one decoder stage of PConvUNet.decode_step
+// (mvp_gan/src/models/generator.py:66-76 and :50-55 for dec1):
+//     interpolate(up, x2, bilinear, align_corners=False)  ++  skip   (channel concat, up first)
+//     followed by the `input * mask` of the consuming PConv2d (pconv.py:27) with the merged mask
+//     max(nearest_up2(up_mask), skip_mask), which tg_mask_merge_up precomputed.
+// One pass: reads the low-res feature and the skip feature, writes the masked merged tensor the
+// tensor-core conv consumes (5 ATen kernels in the reference). tg_upsample_concat_bwd is the
+// transpose of the bilinear part (the skip part of the gradient is consumed in place).
+//
+// tg_maxpool2 / tg_maxpool2_bwd replace nn.MaxPool2d(2,2) of VGG16 features[4], [9]
+// (mvp_gan/src/utils/losses.py:31-32) with the ReLU gate of the preceding layer folded into bwd.
+#include "tg_common.cuh"
+#include "../../include/terragan_b200.h"
+
+namespace tg {
+
+__device__ __forceinline__ void rs_load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void rs_store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 raw;
+  raw.x = pack_bf16x2(f[0], f[1]);
+  raw.y = pack_bf16x2(f[2], f[3]);
+  raw.z = pack_bf16x2(f[4], f[5]);
+  raw.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+
+// PyTorch's upsample_bilinear2d source index for scale 2, align_corners=False:
+// src = max(0, (o + 0.5) / 2 - 0.5); i0 = floor(src); i1 = min(i0 + 1, n - 1); l1 = src - i0.
+__device__ __forceinline__ void bilinear_src(int o, int n, int& i0, int& i1, float& l0, float& l1) {
+  float src = (o + 0.5f) * 0.5f - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < n - 1 ? 1 : 0);
+  l1 = src - i0;
+  l0 = 1.f - l1;
+}
+
+// out[b][oh][ow][0:Cu] = bilinear_up2(up)[...] * mm ; out[...][Cu:Cu+Cs] = skip * mm
+__global__ void upsample_concat_kernel(const __nv_bfloat16* __restrict__ up, int B, int h, int w, int Cu,
+                                       const __nv_bfloat16* __restrict__ skip, int Cs,
+                                       const uint8_t* __restrict__ mm, __nv_bfloat16* __restrict__ out) {
+  const int H = 2 * h, W = 2 * w, C = Cu + Cs, cv = C >> 3;
+  const long total = static_cast<long>(B) * H * W * cv;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = i / cv;
+    const int c = static_cast<int>(i % cv) << 3;
+    float v[8];
+    if (mm != nullptr && mm[p] == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    } else if (c < Cu) {
+      const int ow = static_cast<int>(p % W);
+      const int oh = static_cast<int>((p / W) % H);
+      const int b = static_cast<int>(p / (static_cast<long>(W) * H));
+      int h0, h1, w0, w1;
+      float lh0, lh1, lw0, lw1;
+      bilinear_src(oh, h, h0, h1, lh0, lh1);
+      bilinear_src(ow, w, w0, w1, lw0, lw1);
+      const __nv_bfloat16* base = up + static_cast<long>(b) * h * w * Cu + c;
+      float a00[8], a01[8], a10[8], a11[8];
+      rs_load8(base + (static_cast<long>(h0) * w + w0) * Cu, a00);
+      rs_load8(base + (static_cast<long>(h0) * w + w1) * Cu, a01);
+      rs_load8(base + (static_cast<long>(h1) * w + w0) * Cu, a10);
+      rs_load8(base + (static_cast<long>(h1) * w + w1) * Cu, a11);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = lh0 * (lw0 * a00[j] + lw1 * a01[j]) + lh1 * (lw0 * a10[j] + lw1 * a11[j]);
+    } else {
+      rs_load8(skip + p * Cs + (c - Cu), v);
+    }
+    rs_store8(out + p * C + c, v);
+  }
+}
+
+// d_up[b][i][j][c] = sum over the (<= 4x4) output pixels whose bilinear footprint touches (i, j)
+// of weight * d_merged[b][oh][ow][c]   (d_merged already carries the merged-mask factor)
+__global__ void upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dm, int B, int h, int w, int Cu,
+                                           int Ctot, __nv_bfloat16* __restrict__ dup) {
+  const int H = 2 * h, W = 2 * w, cv = Cu >> 3;
+  const long total = static_cast<long>(B) * h * w * cv;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = i / cv;
+    const int c = static_cast<int>(i % cv) << 3;
+    const int jj = static_cast<int>(p % w);
+    const int ii = static_cast<int>((p / w) % h);
+    const int b = static_cast<int>(p / (static_cast<long>(w) * h));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const __nv_bfloat16* base = dm + static_cast<long>(b) * H * W * Ctot + c;
+    for (int oh = 2 * ii - 1; oh <= 2 * ii + 2; ++oh) {
+      if (oh < 0 || oh >= H) continue;
+      int h0, h1;
+      float lh0, lh1;
+      bilinear_src(oh, h, h0, h1, lh0, lh1);
+      const float wh = (h0 == ii ? lh0 : 0.f) + (h1 == ii ? lh1 : 0.f);
+      if (wh == 0.f) continue;
+      for (int ow = 2 * jj - 1; ow <= 2 * jj + 2; ++ow) {
+        if (ow < 0 || ow >= W) continue;
+        int w0, w1;
+        float lw0, lw1;
+        bilinear_src(ow, w, w0, w1, lw0, lw1);
+        const float ww = (w0 == jj ? lw0 : 0.f) + (w1 == jj ? lw1 : 0.f);
+        if (ww == 0.f) continue;
+        float g[8];
+        rs_load8(base + (static_cast<long>(oh) * W + ow) * Ctot, g);
+        const float wt = wh * ww;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += wt * g[j];
+      }
+    }
+    rs_store8(dup + p * Cu + c, acc);
+  }
+}
+
+__global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
+                                __nv_bfloat16* __restrict__ y) {
+  const int h = H >> 1, w = W >> 1, cv = C >> 3;
+  const long total = static_cast<long>(B) * h * w * cv;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = i / cv;
+    const int c = static_cast<int>(i % cv) << 3;
+    const int j = static_cast<int>(p % w);
+    const int ii = static_cast<int>((p / w) % h);
+    const int b = static_cast<int>(p / (static_cast<long>(w) * h));
+    const __nv_bfloat16* base = x + ((static_cast<long>(b) * H + 2 * ii) * W + 2 * j) * C + c;
+    float a[8], t[8];
+    rs_load8(base, a);
+    rs_load8(base + C, t);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = fmaxf(a[q], t[q]);
+    rs_load8(base + static_cast<long>(W) * C, t);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = fmaxf(a[q], t[q]);
+    rs_load8(base + static_cast<long>(W) * C + C, t);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = fmaxf(a[q], t[q]);
+    rs_store8(y + p * C + c, a);
+  }
+}
+
+// gx[b][H][W][C]: the pooled gradient goes to the first maximum of each 2x2 window (scan order, as
+// ATen's max_pool2d_with_indices does), times the ReLU gate [x > 0] of the layer that produced x.
+__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy,
+                                    int B, int H, int W, int C, int relu_gate,
+                                    __nv_bfloat16* __restrict__ gx) {
+  const int h = H >> 1, w = W >> 1, cv = C >> 3;
+  const long total = static_cast<long>(B) * h * w * cv;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = i / cv;
+    const int c = static_cast<int>(i % cv) << 3;
+    const int j = static_cast<int>(p % w);
+    const int ii = static_cast<int>((p / w) % h);
+    const int b = static_cast<int>(p / (static_cast<long>(w) * h));
+    const long o00 = ((static_cast<long>(b) * H + 2 * ii) * W + 2 * j) * C + c;
+    const long offs[4] = {o00, o00 + C, o00 + static_cast<long>(W) * C, o00 + static_cast<long>(W) * C + C};
+    float v[4][8], g[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rs_load8(x + offs[k], v[k]);
+    rs_load8(gy + p * C + c, g);
+    float o[4][8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      int best = 0;
+      float m = v[0][q];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k][q] > m) { m = v[k][q]; best = k; }
+      const float gg = (relu_gate && !(m > 0.f)) ? 0.f : g[q];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k][q] = (k == best) ? gg : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rs_store8(gx + offs[k], o[k]);
+  }
+}
+
+static int rs_grid(long n, int block) {
+  long g = (n + block - 1) / block;
+  const long cap = static_cast<long>(num_sms() > 0 ? num_sms() : 148) * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace tg
+
+extern "C" int tg_upsample_concat(const void* up, int B, int h, int w, int Cu, const void* skip, int Cs,
+                                  const uint8_t* merged_mask, void* out, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(up && out && Cu > 0 && Cu % 8 == 0 && Cs >= 0 && Cs % 8 == 0, "tg_upsample_concat: bad arguments");
+  TG_REQUIRE(Cs == 0 || skip, "tg_upsample_concat: skip missing");
+  const long total = static_cast<long>(B) * 4 * h * w * ((Cu + Cs) / 8);
+  upsample_concat_kernel<<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(up), B, h, w, Cu, reinterpret_cast<const __nv_bfloat16*>(skip), Cs,
+      merged_mask, reinterpret_cast<__nv_bfloat16*>(out));
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_upsample_concat_bwd(const void* d_merged, int B, int h, int w, int Cu, int Ctot, void* d_up,
+                                      void* stream) {
+  using namespace tg;
+  TG_REQUIRE(d_merged && d_up && Cu > 0 && Cu % 8 == 0 && Ctot >= Cu && Ctot % 8 == 0,
+             "tg_upsample_concat_bwd: bad arguments");
+  const long total = static_cast<long>(B) * h * w * (Cu / 8);
+  upsample_concat_bwd_kernel<<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_merged), B, h, w, Cu, Ctot, reinterpret_cast<__nv_bfloat16*>(d_up));
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_maxpool2(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && y && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "tg_maxpool2: bad arguments");
+  const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_kernel<<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_maxpool2_bwd(const void* x, const void* gy, int B, int H, int W, int C, int relu_gate, void* gx,
+                               void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && gy && gx && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "tg_maxpool2_bwd: bad arguments");
+  const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_bwd_kernel<<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gy), B, H, W, C, relu_gate,
+      reinterpret_cast<__nv_bfloat16*>(gx));
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -39,7 +39,12 @@ class ConvArgs(C.Structure):
         ("bias", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
         ("act", C.c_int32), ("slope", C.c_float),
         ("stats", c_void_p), ("stats_rows_cap", C.c_int32), ("stats_rows_used", C.c_int32),
+        ("gate", c_void_p), ("gate_slope", C.c_float),
     ]
+
+
+class GradSrc(C.Structure):
+    _fields_ = [("ptr", c_void_p), ("pix_stride", C.c_int64), ("chan_off", C.c_int32), ("split", C.c_int32)]
 
 
 class WgradArgs(C.Structure):
@@ -71,6 +76,47 @@ PROTOTYPES = {
     "tg_wgrad_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                 c_void_p]),
     "tg_wgrad_partial_floats": (C.c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "tg_bn_finalize": (c_int, [c_void_p, c_int, c_int, C.c_double, c_void_p, c_void_p, c_float, c_float,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tg_bn_eval_coeff": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                 c_void_p]),
+    "tg_bn_apply": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                            c_void_p, c_void_p, c_int, c_void_p]),
+    "tg_bn_bwd_reduce": (c_int, [C.POINTER(GradSrc), C.POINTER(GradSrc), c_void_p, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int,
+                                 C.POINTER(c_int), c_void_p]),
+    "tg_bn_bwd_finalize": (c_int, [c_void_p, c_int, c_int, C.c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "tg_bn_bwd_apply": (c_int, [C.POINTER(GradSrc), C.POINTER(GradSrc), c_void_p, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tg_upsample_concat": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                   c_void_p]),
+    "tg_upsample_concat_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tg_maxpool2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tg_maxpool2_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tg_conv_c1_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p, c_int,
+                               C.POINTER(c_int), c_void_p]),
+    "tg_conv_c1_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                 c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "tg_conv_c1_wgrad_rows": (c_int, []),
+    "tg_conv_to1_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, C.POINTER(c_int),
+                                C.POINTER(C.c_int8), C.POINTER(C.c_int8), c_void_p, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tg_conv_to1_bwd_data": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, C.POINTER(C.c_int8),
+                                     C.POINTER(C.c_int8), c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tg_conv_to1_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                  C.POINTER(C.c_int8), C.POINTER(C.c_int8), c_void_p, c_void_p, c_int, c_void_p,
+                                  c_void_p, c_int, c_void_p]),
+    "tg_conv_to1_wgrad_rows": (c_int, []),
+    "tg_final_bwd_pre": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_void_p]),
+    "tg_loss_rows": (c_int, []),
+    "tg_inpaint_loss_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                    c_int, c_void_p, c_void_p]),
+    "tg_inpaint_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
+    "tg_l1_bf16_fwd": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]),
+    "tg_l1_bf16_bwd": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

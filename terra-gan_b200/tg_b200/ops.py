@@ -40,7 +40,8 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
                code: Optional[torch.Tensor] = None, lut: Optional[Sequence[float]] = None,
                bias: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
                shift: Optional[torch.Tensor] = None, act: int = 0, slope: float = 0.0,
-               want_stats: bool = False, out: Optional[torch.Tensor] = None):
+               want_stats: bool = False, out: Optional[torch.Tensor] = None,
+               gate: Optional[torch.Tensor] = None, gate_slope: float = 0.0):
     """out[B][Po][Ho][Wo][N] = epilogue(sum_taps x (+) tap . w)  — see tg_conv_igemm.
 
     x: bf16 [B, P, H, W, C];  w_packed: bf16 [N, Ktot];  plan: fprop_plan / dgrad_plan.
@@ -81,6 +82,11 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
                 raise RuntimeError(f"conv_igemm: {name} must have N={N} entries")
         setattr(a, name, ptr(t))
     a.act, a.slope = act, slope
+    if gate is not None:
+        _req(gate, BF16, "gate")
+        if gate.numel() != out.numel():
+            raise RuntimeError("conv_igemm: gate must have the shape of the output")
+        a.gate, a.gate_slope = ptr(gate), gate_slope
     stats = None
     if want_stats:
         rows = num_sms()
@@ -132,3 +138,300 @@ def wgrad_igemm(x: torch.Tensor, g: torch.Tensor, plan: TapPlan, blks: torch.Ten
     check(lib().tg_wgrad_igemm(C.byref(a), stream_ptr()), "tg_wgrad_igemm")
     check(lib().tg_wgrad_reduce(ptr(partial), a.splits, T, Cc, N, ptr(tap_perm), ptr(dw),
                                 1 if accumulate else 0, stream_ptr()), "tg_wgrad_reduce")
+
+
+# ------------------------------------------------------------------------------------------------
+# mask pyramid
+# ------------------------------------------------------------------------------------------------
+def mask_from_f32(mask: torch.Tensor) -> torch.Tensor:
+    _req(mask, torch.float32, "mask")
+    out = torch.empty(mask.shape, dtype=torch.uint8, device=mask.device)
+    check(lib().tg_mask_from_f32(ptr(mask), mask.numel(), ptr(out), stream_ptr()), "tg_mask_from_f32")
+    return out
+
+
+def mask_to_f32(mask: torch.Tensor) -> torch.Tensor:
+    _req(mask, torch.uint8, "mask")
+    out = torch.empty(mask.shape, dtype=torch.float32, device=mask.device)
+    check(lib().tg_mask_to_f32(ptr(mask), mask.numel(), ptr(out), stream_ptr()), "tg_mask_to_f32")
+    return out
+
+
+def mask_window_sum(mask: torch.Tensor, k: int, s: int, pad: int, want_upd_split=False, want_in_split=False):
+    """mask u8 [B,H,W] -> (sum u8 [B,Ho,Wo], upd u8 [B,Ho,Wo], upd_split|None, in_split|None)."""
+    _req(mask, torch.uint8, "mask")
+    B, H, W = mask.shape
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    dev = mask.device
+    ssum = torch.empty((B, Ho, Wo), dtype=torch.uint8, device=dev)
+    upd = torch.empty((B, Ho, Wo), dtype=torch.uint8, device=dev)
+    upd_split = torch.empty((B, 4, Ho // 2, Wo // 2), dtype=torch.uint8, device=dev) if want_upd_split else None
+    in_split = torch.empty((B, 4, H // 2, W // 2), dtype=torch.uint8, device=dev) if want_in_split else None
+    check(lib().tg_mask_window_sum(ptr(mask), B, H, W, k, s, pad, ptr(ssum), ptr(upd), ptr(upd_split),
+                                   ptr(in_split), stream_ptr()), "tg_mask_window_sum")
+    return ssum, upd, upd_split, in_split
+
+
+def mask_merge_up(up: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+    _req(up, torch.uint8, "up")
+    _req(skip, torch.uint8, "skip")
+    B, H, W = skip.shape
+    out = torch.empty_like(skip)
+    check(lib().tg_mask_merge_up(ptr(up), ptr(skip), B, H, W, ptr(out), stream_ptr()), "tg_mask_merge_up")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm + activation
+# ------------------------------------------------------------------------------------------------
+def bn_finalize(partial, count, gamma, beta, eps, momentum, running_mean, running_var):
+    """partial fp32 [rows,2,C] -> (scale, shift, mean, invstd); updates running stats in place."""
+    rows, _, Cc = partial.shape
+    dev = partial.device
+    out = torch.empty((4, Cc), dtype=torch.float32, device=dev)
+    check(lib().tg_bn_finalize(ptr(partial), rows, Cc, float(count), ptr(gamma), ptr(beta), eps, momentum,
+                               ptr(running_mean), ptr(running_var), ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                               ptr(out[3]), stream_ptr()), "tg_bn_finalize")
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_eval_coeff(gamma, beta, running_mean, running_var, eps):
+    Cc = running_mean.numel()
+    out = torch.empty((2, Cc), dtype=torch.float32, device=running_mean.device)
+    check(lib().tg_bn_eval_coeff(Cc, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), eps, ptr(out[0]),
+                                 ptr(out[1]), stream_ptr()), "tg_bn_eval_coeff")
+    return out[0], out[1]
+
+
+def bn_apply(z, scale, shift, act, slope=0.0, code=None, want_nhwc=True, want_split=False, mask_split=False):
+    """z bf16 [B,1,H,W,C] or [B,H,W,C] -> (y_nhwc [B,H,W,C] | None, y_split [B,4,H/2,W/2,C] | None)."""
+    _req(z, BF16, "z")
+    if z.dim() == 5:
+        z = z[:, 0]
+    B, H, W, Cc = z.shape
+    y = torch.empty((B, H, W, Cc), dtype=BF16, device=z.device) if want_nhwc else None
+    ys = torch.empty((B, 4, H // 2, W // 2, Cc), dtype=BF16, device=z.device) if want_split else None
+    check(lib().tg_bn_apply(ptr(z), B, H, W, Cc, ptr(scale), ptr(shift), act, slope, ptr(code), ptr(y), ptr(ys),
+                            1 if mask_split else 0, stream_ptr()), "tg_bn_apply")
+    return y, ys
+
+
+def grad_src(t: Optional[torch.Tensor], chan_off: int = 0, split: bool = False) -> _lib.GradSrc:
+    """Describe a bf16 gradient tensor whose last dim is the channel dim (pixel stride = last dim)."""
+    s = _lib.GradSrc()
+    if t is None:
+        s.ptr, s.pix_stride, s.chan_off, s.split = None, 0, 0, 0
+    else:
+        _req(t, BF16, "grad")
+        s.ptr, s.pix_stride, s.chan_off, s.split = ptr(t), t.shape[-1], chan_off, 1 if split else 0
+        s._keep = t  # the descriptor only holds a raw pointer: keep the tensor alive with it
+    return s
+
+
+def bn_bwd(g0: _lib.GradSrc, g1: Optional[_lib.GradSrc], z, scale, shift, mean, invstd, act, slope, code,
+           lut_dev, want_dbias=True, batch_stats=True):
+    """BN(+act, +mask ratio) backward. Returns (gz bf16 [B,1,H,W,C], dgamma, dbeta, dbias)."""
+    if z.dim() == 5:
+        z = z[:, 0]
+    B, H, W, Cc = z.shape
+    dev = z.device
+    rows_cap = num_sms() * 4
+    partial = torch.empty((rows_cap, 5, Cc), dtype=torch.float32, device=dev)
+    used = C.c_int(0)
+    g1p = C.byref(g1) if g1 is not None else None
+    check(lib().tg_bn_bwd_reduce(C.byref(g0), g1p, ptr(z), B, H, W, Cc, ptr(scale), ptr(shift), act, slope,
+                                 ptr(code), ptr(lut_dev), ptr(partial), rows_cap, C.byref(used), stream_ptr()),
+          "tg_bn_bwd_reduce")
+    outs = torch.empty((8, Cc), dtype=torch.float32, device=dev)  # coeff[5], dgamma, dbeta, dbias
+    check(lib().tg_bn_bwd_finalize(ptr(partial), used.value, Cc, float(B * H * W), ptr(scale), ptr(mean),
+                                   ptr(invstd), ptr(outs), ptr(outs[5]), ptr(outs[6]),
+                                   ptr(outs[7]) if want_dbias else None, 0, 1 if batch_stats else 0, stream_ptr()),
+          "tg_bn_bwd_finalize")
+    gz = torch.empty((B, 1, H, W, Cc), dtype=BF16, device=dev)
+    check(lib().tg_bn_bwd_apply(C.byref(g0), g1p, ptr(z), B, H, W, Cc, ptr(shift), ptr(outs), act, slope, ptr(code),
+                                ptr(lut_dev), ptr(gz), stream_ptr()), "tg_bn_bwd_apply")
+    return gz, outs[5], outs[6], outs[7]
+
+
+# ------------------------------------------------------------------------------------------------
+# resampling
+# ------------------------------------------------------------------------------------------------
+def upsample_concat(up, skip, merged_mask):
+    """up bf16 [B,h,w,Cu], skip bf16 [B,2h,2w,Cs] | None, merged_mask u8 [B,2h,2w] -> [B,1,2h,2w,Cu+Cs]."""
+    _req(up, BF16, "up")
+    B, h, w, Cu = up.shape
+    Cs = 0
+    if skip is not None:
+        _req(skip, BF16, "skip")
+        Cs = skip.shape[-1]
+    out = torch.empty((B, 1, 2 * h, 2 * w, Cu + Cs), dtype=BF16, device=up.device)
+    check(lib().tg_upsample_concat(ptr(up), B, h, w, Cu, ptr(skip), Cs, ptr(merged_mask), ptr(out), stream_ptr()),
+          "tg_upsample_concat")
+    return out
+
+
+def upsample_concat_bwd(d_merged, Cu):
+    """d_merged bf16 [B,1,2h,2w,Ctot] -> d_up bf16 [B,h,w,Cu]."""
+    _req(d_merged, BF16, "d_merged")
+    B, _, H, W, Ct = d_merged.shape
+    out = torch.empty((B, H // 2, W // 2, Cu), dtype=BF16, device=d_merged.device)
+    check(lib().tg_upsample_concat_bwd(ptr(d_merged), B, H // 2, W // 2, Cu, Ct, ptr(out), stream_ptr()),
+          "tg_upsample_concat_bwd")
+    return out
+
+
+def maxpool2(x):
+    _req(x, BF16, "x")
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, H // 2, W // 2, Cc), dtype=BF16, device=x.device)
+    check(lib().tg_maxpool2(ptr(x), B, H, W, Cc, ptr(y), stream_ptr()), "tg_maxpool2")
+    return y
+
+
+def maxpool2_bwd(x, gy, relu_gate=True):
+    _req(x, BF16, "x")
+    _req(gy, BF16, "gy")
+    B, H, W, Cc = x.shape
+    gx = torch.empty_like(x)
+    check(lib().tg_maxpool2_bwd(ptr(x), ptr(gy), B, H, W, Cc, 1 if relu_gate else 0, ptr(gx), stream_ptr()),
+          "tg_maxpool2_bwd")
+    return gx
+
+
+# ------------------------------------------------------------------------------------------------
+# bandwidth-bound convolutions
+# ------------------------------------------------------------------------------------------------
+def conv_c1_fwd(x, xmask, k, s, pad, wgt, bias, code=None, lut_dev=None, act=0, slope=0.0, out_split=False,
+                want_stats=False):
+    """x fp32 [B,H,W] -> bf16 [B,1,Ho,Wo,64] (or [B,4,Ho/2,Wo/2,64] if out_split), stats|None."""
+    _req(x, torch.float32, "x")
+    _req(wgt, torch.float32, "wgt")
+    B, H, W = x.shape
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    shape = (B, 4, Ho // 2, Wo // 2, 64) if out_split else (B, 1, Ho, Wo, 64)
+    out = torch.empty(shape, dtype=BF16, device=x.device)
+    stats, used = None, C.c_int(0)
+    rows = 0
+    if want_stats:
+        rows = num_sms() * 4
+        stats = torch.empty((rows, 2, 64), dtype=torch.float32, device=x.device)
+    check(lib().tg_conv_c1_fwd(ptr(x), ptr(xmask), B, H, W, k, s, pad, ptr(wgt), ptr(bias), ptr(code), ptr(lut_dev),
+                               act, slope, ptr(out), 1 if out_split else 0, ptr(stats), rows, C.byref(used),
+                               stream_ptr()), "tg_conv_c1_fwd")
+    if stats is not None:
+        stats = stats[: used.value]
+    return out, stats
+
+
+def conv_c1_wgrad(x, xmask, k, s, pad, g, g_split, dw, db=None, accumulate=False):
+    _req(x, torch.float32, "x")
+    _req(g, BF16, "g")
+    B, H, W = x.shape
+    rows = lib().tg_conv_c1_wgrad_rows()
+    partial = torch.empty((rows * 64 * (k * k + 1),), dtype=torch.float32, device=x.device)
+    check(lib().tg_conv_c1_wgrad(ptr(x), ptr(xmask), B, H, W, k, s, pad, ptr(g), 1 if g_split else 0, ptr(partial),
+                                 rows, ptr(dw), ptr(db), 1 if accumulate else 0, stream_ptr()), "tg_conv_c1_wgrad")
+
+
+def _tap_arrays(taps):
+    n = len(taps)
+    dh = (C.c_int8 * n)(*[t[0] for t in taps])
+    dw = (C.c_int8 * n)(*[t[1] for t in taps])
+    return dh, dw
+
+
+def conv_to1_fwd(x, x_split, hw, wgt, cls_counts, taps, bias, out_hw, mode=0, mask=None, xin=None, want_sig=False):
+    """x bf16 [B,H,W,C] (or parity-split of it), wgt fp32 [ntaps,C], taps [(dh,dw)] -> fp32 [B,Ho,Wo]."""
+    _req(x, BF16, "x")
+    _req(wgt, torch.float32, "wgt")
+    B = x.shape[0]
+    Cc = x.shape[-1]
+    H, W = hw
+    Ho, Wo = out_hw
+    out = torch.empty((B, Ho, Wo), dtype=torch.float32, device=x.device)
+    sig = torch.empty((B, Ho, Wo), dtype=torch.float32, device=x.device) if want_sig else None
+    dh, dw = _tap_arrays(taps)
+    cc = (C.c_int * len(cls_counts))(*cls_counts)
+    check(lib().tg_conv_to1_fwd(ptr(x), 1 if x_split else 0, B, H, W, Cc, ptr(wgt), len(cls_counts), cc, dh, dw,
+                                ptr(bias), Ho, Wo, mode, ptr(mask), ptr(xin), ptr(out), ptr(sig), stream_ptr()),
+          "tg_conv_to1_fwd")
+    return out, sig
+
+
+def conv_to1_bwd_data(g, wgt, taps, hw, Cc):
+    """g fp32 [B,Ho,Wo], wgt fp32 [ntaps,C] -> dx bf16 [B,H,W,C]."""
+    _req(g, torch.float32, "g")
+    B, Ho, Wo = g.shape
+    H, W = hw
+    dx = torch.empty((B, H, W, Cc), dtype=BF16, device=g.device)
+    dh, dw = _tap_arrays(taps)
+    check(lib().tg_conv_to1_bwd_data(ptr(g), B, Ho, Wo, ptr(wgt), len(taps), dh, dw, H, W, Cc, ptr(dx),
+                                     stream_ptr()), "tg_conv_to1_bwd_data")
+    return dx
+
+
+def conv_to1_wgrad(x, g, taps, dw, db=None, accumulate=False):
+    """x bf16 [B,H,W,C], g fp32 [B,Ho,Wo] -> dw fp32 [1,C,k,k] (+)=, db fp32 [1] (+)=."""
+    _req(x, BF16, "x")
+    _req(g, torch.float32, "g")
+    B, H, W, Cc = x.shape
+    _, Ho, Wo = g.shape
+    rows = lib().tg_conv_to1_wgrad_rows()
+    partial = torch.empty((rows * len(taps) * Cc,), dtype=torch.float32, device=x.device)
+    partial_b = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    dh, dww = _tap_arrays(taps)
+    check(lib().tg_conv_to1_wgrad(ptr(x), B, H, W, Cc, ptr(g), Ho, Wo, len(taps), dh, dww, ptr(partial),
+                                  ptr(partial_b), rows, ptr(dw), ptr(db), 1 if accumulate else 0, stream_ptr()),
+          "tg_conv_to1_wgrad")
+
+
+def final_bwd_pre(g_out, sig, mask_u8):
+    _req(g_out, torch.float32, "g_out")
+    out = torch.empty_like(sig)
+    check(lib().tg_final_bwd_pre(ptr(g_out), ptr(sig), ptr(mask_u8), sig.numel(), ptr(out), stream_ptr()),
+          "tg_final_bwd_pre")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+def inpaint_loss_fwd(pred, target, mask, flags=0, eps=1e-6):
+    """fp32 [B,1,H,W] x3 -> terms fp32 [4] = (l1, tv, boundary, boundary_count)."""
+    for n, t in (("pred", pred), ("target", target), ("mask", mask)):
+        _req(t, torch.float32, n)
+    B, _, H, W = pred.shape
+    rows = lib().tg_loss_rows()
+    partial = torch.empty((rows * 5,), dtype=torch.float32, device=pred.device)
+    terms = torch.empty((4,), dtype=torch.float32, device=pred.device)
+    check(lib().tg_inpaint_loss_fwd(ptr(pred), ptr(target), ptr(mask), B, H, W, flags, eps, ptr(partial), rows,
+                                    ptr(terms), stream_ptr()), "tg_inpaint_loss_fwd")
+    return terms
+
+
+def inpaint_loss_bwd(pred, target, mask, terms, grad_terms, flags=0, eps=1e-6):
+    _req(grad_terms, torch.float32, "grad_terms")
+    B, _, H, W = pred.shape
+    grad = torch.empty_like(pred)
+    check(lib().tg_inpaint_loss_bwd(ptr(pred), ptr(target), ptr(mask), B, H, W, flags, eps, ptr(terms),
+                                    ptr(grad_terms), ptr(grad), stream_ptr()), "tg_inpaint_loss_bwd")
+    return grad
+
+
+def l1_bf16_fwd(a, b):
+    _req(a, BF16, "a")
+    _req(b, BF16, "b")
+    rows = lib().tg_loss_rows()
+    partial = torch.empty((rows,), dtype=torch.float32, device=a.device)
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    check(lib().tg_l1_bf16_fwd(ptr(a), ptr(b), a.numel(), ptr(partial), rows, ptr(out), stream_ptr()),
+          "tg_l1_bf16_fwd")
+    return out
+
+
+def l1_bf16_bwd(a, b, grad_out, relu_gate=True):
+    _req(grad_out, torch.float32, "grad_out")
+    ga = torch.empty_like(a)
+    check(lib().tg_l1_bf16_bwd(ptr(a), ptr(b), a.numel(), ptr(grad_out), 1 if relu_gate else 0, ptr(ga),
+                               stream_ptr()), "tg_l1_bf16_bwd")
+    return ga

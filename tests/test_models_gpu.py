@@ -1,0 +1,269 @@
+"""GPU parity of the drop-in modules (PConv2d / PConvUNet / Discriminator / InpaintingLoss /
+HumanGuidedLoss) against the oracle (oracle/terra_oracle.py, fp32 CPU restatement of the reference)
+on identical seeded inputs and weights.
+
+Bars (BASELINE.json north_star): updated masks and mask sums bit-exact; outputs, losses, gradients
+within max|delta|/max|ref| <= 1e-2 per tensor (bf16-in / fp32-accumulate vs the fp32 reference).
+"""
+import pytest
+import torch
+
+from oracle import terra_oracle as O
+from tg_b200 import layers as L, ops
+from mvp_gan.src.models.pconv import PConv2d
+from mvp_gan.src.models.generator import PConvUNet
+from mvp_gan.src.models.discriminator import Discriminator
+from mvp_gan.src.utils.losses import HumanGuidedLoss, InpaintingLoss
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-2
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2)
+
+
+def vgg_seq_state(vgg):
+    return {k: v for k, v in vgg.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["rect", "large", "iid", "ones", "zeros"])
+def test_mask_pyramid_bit_exact(kind):
+    H, B = 128, 2
+    mask = O.make_mask(21, B, H, kind)
+    x = O.make_tiles(11, B, H)
+    trace = {}
+    with torch.no_grad():
+        O.pconv_unet(x * mask, mask, O.make_generator_state(1), False, trace)
+    pyr = L.build_mask_pyramid(ops.mask_from_f32(mask.reshape(B, H, H).to(DEV).contiguous()))
+    for i, (name, *_r) in enumerate(O.ENC):
+        assert torch.equal(pyr.enc_s[i].cpu().float(), trace[name + ".msum"][:, 0]), name       # mask sums
+        assert torch.equal(pyr.enc_m[i].cpu().float(), trace[name + ".mask"][:, 0]), name       # updated masks
+    for i, (name, *_r) in enumerate(O.DEC):
+        assert torch.equal(pyr.dec_mm[i].cpu().float(), trace[name + ".in_mask"][:, 0]), name   # merged masks
+        assert torch.equal(pyr.dec_s[i].cpu().float(), trace[name + ".msum"][:, 0]), name
+        assert torch.equal(pyr.dec_m[i].cpu().float(), trace[name + ".mask"][:, 0]), name
+
+
+@pytest.mark.parametrize("kind", ["rect", "large"])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_generator_forward_parity(kind, mode):
+    H, B = 128, 2
+    x = O.make_tiles(10, B, H)
+    mask = O.make_mask(20, B, H, kind)
+    sd = O.make_generator_state(1)
+    trace = {}
+    with torch.no_grad():
+        ref = O.pconv_unet(x * mask, mask, sd, mode == "train", trace)
+    G = PConvUNet()
+    G.load_state_dict(O.make_generator_state(1))
+    G.to(DEV).train(mode == "train")
+    G._trace = {}
+    with torch.no_grad():
+        out = G((x * mask).to(DEV), mask.to(DEV))
+    errs = {n: rel_err(nchw(G._trace[n + ".y"]), trace[n + ".y"]) for n, *_r in O.ENC + O.DEC}
+    print(mode, kind, {k: f"{v:.2e}" for k, v in errs.items()}, "out", rel_err(out, ref))
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert rel_err(out, ref) < TOL
+    for n, e in errs.items():
+        assert e < 2.5e-2, (n, e)      # intermediate features: looser, they are not part of the contract
+    if mode == "train":                # running statistics after one forward
+        for name in ("enc1", "enc4", "enc7", "dec7", "dec1"):
+            bn = getattr(G, name).bn
+            assert rel_err(bn.running_mean, sd[name + ".bn.running_mean"]) < TOL
+            assert rel_err(bn.running_var, sd[name + ".bn.running_var"]) < TOL
+            assert int(bn.num_batches_tracked) == 1
+
+
+PCONV_CASES = [(1, 64, 7, 2, 3, 1, 64, "iid"), (64, 128, 5, 2, 2, 2, 16, "rect"), (256, 512, 3, 2, 1, 2, 8, "large"),
+               (192, 64, 3, 1, 1, 2, 16, "rect"), (64, 64, 3, 1, 1, 1, 32, "large")]
+
+
+@pytest.mark.parametrize("case", PCONV_CASES)
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_pconv2d_layer_parity(case, mode):
+    """BASELINE.json config 1 (PConv2d(1,64,7,2,3) fwd+bwd) and the other window shapes, stand-alone."""
+    cin, cout, k, s, p, B, H, kind = case
+    sd = O.make_pconv_state(100, cin, cout, k)
+    x = torch.randn((B, cin, H, H), generator=torch.Generator().manual_seed(200))
+    mask = O.make_mask(300, B, H, kind)
+    gy_gen = torch.Generator().manual_seed(400)
+    # oracle
+    names = ["input_conv.weight", "input_conv.bias", "bn.weight", "bn.bias"]
+    osd = {k_: v.clone() for k_, v in sd.items()}
+    for n in names:
+        osd[n] = osd[n].requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    y_ref, m_ref = O.pconv2d(xr, mask, osd, "", s, p, mode == "train")
+    gy = torch.randn(y_ref.shape, generator=gy_gen)
+    g_ref = torch.autograd.grad(y_ref, [xr] + [osd[n] for n in names], gy)
+    # CUDA
+    layer = PConv2d(cin, cout, k, s, p)
+    layer.load_state_dict(sd)
+    layer.to(DEV).train(mode == "train")
+    xc = x.to(DEV).requires_grad_(True)
+    y, m = layer(xc, mask.to(DEV))
+    assert torch.equal(m.cpu(), m_ref)                                   # updated mask: bit-exact
+    assert rel_err(y, y_ref) < TOL
+    y.backward(gy.to(DEV))
+    assert rel_err(layer.input_conv.weight.grad, g_ref[1]) < TOL
+    assert rel_err(layer.input_conv.bias.grad, g_ref[2]) < TOL
+    assert rel_err(layer.bn.weight.grad, g_ref[3]) < TOL
+    assert rel_err(layer.bn.bias.grad, g_ref[4]) < TOL
+    assert rel_err(xc.grad, g_ref[0]) < TOL
+    if mode == "train":
+        assert rel_err(layer.bn.running_var, osd["bn.running_var"]) < TOL
+
+
+def _make_modules():
+    G = PConvUNet()
+    G.load_state_dict(O.make_generator_state(1))
+    D = Discriminator()
+    D.load_state_dict(O.make_discriminator_state(2))
+    vgg = O.make_vgg_state(3)
+    return G.to(DEV).train(), D.to(DEV).train(), vgg
+
+
+def _check_grads(named_params, ref, tol=TOL, what=""):
+    worst = ("", 0.0)
+    for k, p in named_params:
+        if k not in ref:
+            continue
+        assert p.grad is not None, k
+        e = rel_err(p.grad, ref[k])
+        if e > worst[1]:
+            worst = (k, e)
+    print(what, "worst grad rel err", worst)
+    assert worst[1] < tol, worst
+
+
+def test_discriminator_parity():
+    H, B = 128, 2
+    img = O.make_tiles(50, B, H)
+    d_sd = O.make_discriminator_state(2)
+    D = Discriminator()
+    D.load_state_dict(O.make_discriminator_state(2))
+    D.to(DEV).train()
+    osd = O._require_grad(d_sd)
+    xr = img.clone().requires_grad_(True)
+    ref = O.discriminator(xr, osd, True)
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(51))
+    names = O._leaf_params(d_sd)
+    gr = torch.autograd.grad(ref, [xr] + [osd[k] for k in names], g)
+    xc = img.to(DEV).requires_grad_(True)
+    out = D(xc)
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < TOL
+    out.backward(g.to(DEV))
+    assert rel_err(xc.grad, gr[0]) < TOL
+    _check_grads(D.named_parameters(), dict(zip(names, gr[1:])), what="D")
+    for bi in (3, 6, 9):
+        assert rel_err(D.model[bi].running_var, osd[f"model.{bi}.running_var"]) < TOL
+
+
+def test_inpainting_loss_parity():
+    H, B = 128, 2
+    vgg = O.make_vgg_state(3)
+    pred = O.make_tiles(60, B, H)
+    target = O.make_tiles(61, B, H)
+    mask = O.make_mask(62, B, H, "rect")
+    pr = pred.clone().requires_grad_(True)
+    terms = {}
+    ref = O.inpainting_loss(pr, target, mask, vgg, 0.1, 0.1, 0.5, terms)
+    (g_ref,) = torch.autograd.grad(ref, pr)
+    crit = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=torch.device(DEV), vgg_state_dict=vgg)
+    pc = pred.to(DEV).requires_grad_(True)
+    loss = crit(pc, target.to(DEV), mask.to(DEV))
+    loss.backward()
+    print("loss", loss.item(), ref.item(), {k: v.item() for k, v in terms.items()})
+    assert abs(loss.item() - ref.item()) < TOL * abs(ref.item())
+    assert rel_err(pc.grad, g_ref) < TOL
+    b = crit.boundary_loss(pc.detach(), target.to(DEV), mask.to(DEV))
+    assert abs(b.item() - terms["boundary"].item()) < 1e-5
+
+
+def test_adversarial_step_parity():
+    """One iteration of the reference hot loop (train.py:179-225) with the drop-in modules."""
+    H, B = 128, 2
+    real = O.make_tiles(30, B, H)
+    masks = O.make_mask(31, B, H, "rect")
+    g_sd, d_sd, vgg = O.make_generator_state(1), O.make_discriminator_state(2), O.make_vgg_state(3)
+    r = O.adversarial_step(real, masks, g_sd, d_sd, vgg, lr=2e-4, opt_state={})
+    G, D, _ = _make_modules()
+    criterion = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=torch.device(DEV), vgg_state_dict=vgg)
+    adversarial_loss = torch.nn.BCEWithLogitsLoss()
+    optimizer_G = torch.optim.Adam(G.parameters(), lr=2e-4)
+    optimizer_D = torch.optim.Adam(D.parameters(), lr=2e-4)
+    real_imgs, masks_c = real.to(DEV), masks.to(DEV)
+    # ---- train.py:179-219 ----
+    masked_imgs = real_imgs * masks_c
+    optimizer_G.zero_grad()
+    gen_imgs = G(masked_imgs, masks_c)
+    g_loss = criterion(gen_imgs, real_imgs, masks_c)
+    fake_validity = D(gen_imgs)
+    g_adv_loss = adversarial_loss(fake_validity, torch.ones_like(fake_validity, device=DEV))
+    g_total_loss = g_loss + g_adv_loss
+    g_total_loss.backward()
+    assert rel_err(gen_imgs, r["gen"]) < TOL
+    for got, key in ((g_loss, "g_loss"), (g_adv_loss, "g_adv"), (g_total_loss, "g_total")):
+        assert abs(got.item() - r[key].item()) < TOL * abs(r[key].item()), key
+    _check_grads(G.named_parameters(), r["g_grads"], what="G")
+    optimizer_G.step()
+    optimizer_D.zero_grad()
+    real_validity = D(real_imgs)
+    fake_validity = D(gen_imgs.detach())
+    real_loss = adversarial_loss(real_validity, torch.ones_like(real_validity, device=DEV))
+    fake_loss = adversarial_loss(fake_validity, torch.zeros_like(fake_validity, device=DEV))
+    d_loss = 0.5 * (real_loss + fake_loss)
+    d_loss.backward()
+    assert abs(d_loss.item() - r["d_loss"].item()) < TOL * abs(r["d_loss"].item())
+    _check_grads(D.named_parameters(), r["d_grads"], what="D")
+    optimizer_D.step()
+    # BN running statistics (D's advance three times per step) and parameters after Adam
+    for k, v in G.state_dict().items():
+        if "running_" in k:
+            assert rel_err(v, g_sd[k]) < TOL, k
+    for k, v in D.state_dict().items():
+        if "running_" in k:
+            assert rel_err(v, d_sd[k]) < TOL, k
+    # Adam's first step is +-lr*sign(g): only the bf16-noise-free comparison of the big tensors is meaningful
+    for k, p in G.named_parameters():
+        if p.requires_grad and p.numel() > 1000:
+            assert rel_err(p, g_sd[k]) < TOL, k
+
+
+def test_human_guided_step_parity():
+    H, B = 128, 2
+    images = O.make_tiles(40, B, H)
+    masks = O.make_mask(41, B, H, "large")
+    human = 1 - O.make_mask(42, B, H, "rect")
+    g_sd, vgg = O.make_generator_state(1), O.make_vgg_state(3)
+    r = O.human_guided_step(images, masks, human, g_sd, vgg, lr=1e-4, opt_state={})
+    G, _, _ = _make_modules()
+    config = {"training": {"loss_weights": {"perceptual": 0.1, "tv": 0.1, "boundary": 0.5},
+                           "modes": {"human_guided": {"human_feedback_weight": 0.3, "base_loss_weight": 0.7,
+                                                      "learning_rate": 1e-4}}}}
+    criterion = HumanGuidedLoss(config, device=torch.device(DEV), vgg_state_dict=vgg)
+    optimizer = torch.optim.Adam(G.parameters(), lr=1e-4)
+    ic, mc, hc = images.to(DEV), masks.to(DEV), human.to(DEV)
+    generated = G(ic * mc, mc)
+    loss = criterion(generated, ic, mc, {"mask": hc})
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    assert rel_err(generated, r["gen"]) < TOL
+    assert abs(loss.item() - r["loss"].item()) < TOL * abs(r["loss"].item())
+    _check_grads(G.named_parameters(), r["g_grads"], what="G(hg)")
+
+
+def test_no_cpu_fallback():
+    G = PConvUNet()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G(torch.rand(1, 1, 128, 128), torch.ones(1, 1, 128, 128))
