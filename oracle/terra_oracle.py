@@ -52,6 +52,48 @@ VGG_POOL_AFTER = (2, 7)  # a 2x2 max-pool follows the ReLU of these convs (featu
 
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1  # nn.BatchNorm2d defaults used by pconv.py:21 / discriminator.py:13
 
+# --------------------------------------------------------------------------------------------------
+# optional storage-rounding emulation (tests only)
+# --------------------------------------------------------------------------------------------------
+# The CUDA path stores activations and tensor-core weights in bf16 (fp32 accumulate). With
+# `rounding(bf16_ste)` active the oracle rounds at the same points (conv weights of the tensor-core
+# layers, pre-BN z, post-activation y, up-sampled features) but otherwise computes in fp32, which
+# separates "the kernels compute the right thing" from "bf16 storage perturbs ill-conditioned
+# quantities". With ROUND = None (default) this file is the plain fp32 restatement of the reference.
+ROUND = None
+
+
+class _BF16STE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def bf16_ste(x: Tensor) -> Tensor:
+    return _BF16STE.apply(x)
+
+
+class rounding:
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __enter__(self):
+        global ROUND
+        self.prev, ROUND = ROUND, self.fn
+        return self
+
+    def __exit__(self, *a):
+        global ROUND
+        ROUND = self.prev
+
+
+def _q(x: Tensor) -> Tensor:
+    return x if ROUND is None else ROUND(x)
+
 
 # --------------------------------------------------------------------------------------------------
 # deterministic parameter construction (shared by the golden generator and every parity test)
@@ -176,12 +218,14 @@ def pconv2d(x: Tensor, mask: Tensor, sd: SD, prefix: str, stride: int, pad: int,
     b = sd[prefix + "input_conv.bias"]
     mw = sd[prefix + "mask_conv.weight"]
     winsize = w.shape[2] * w.shape[3]                                  # pconv.py:10
+    if w.shape[1] > 1:
+        w = _q(w)                                                      # (tests) bf16 tensor-core operand
     z = F.conv2d(x * mask, w, b, stride, pad)                          # :27,30  (bias inside)
     with torch.no_grad():
         msum = F.conv2d(mask, mw, None, stride, pad)                   # :34 / :38
         new_mask = (msum > 0).float()                                  # :35
         ratio = (winsize / (msum + 1e-8)) * (msum > 0).float()         # :39-40 (reciprocal * k^2)
-    z = z * ratio                                                      # :43
+    z = _q(z * ratio)                                                  # :43
     if trace is not None:
         trace[prefix + "msum"] = msum
         trace[prefix + "z"] = z
@@ -191,7 +235,7 @@ def pconv2d(x: Tensor, mask: Tensor, sd: SD, prefix: str, stride: int, pad: int,
                          BN_MOMENTUM, BN_EPS)
         if training:
             sd[prefix + "bn.num_batches_tracked"] += 1
-    y = F.relu(z)                                                      # :48
+    y = _q(F.relu(z))                                                  # :48
     if trace is not None:
         trace[prefix + "y"] = y
         trace[prefix + "mask"] = new_mask
@@ -216,14 +260,14 @@ def pconv_unet(x: Tensor, mask: Tensor, sd: SD, training: bool, trace: Optional[
     up, um = feats[6], masks[6]
     for i, (name, _, _, _, s, p) in enumerate(DEC[:6]):                # :42-47 -> decode_step :66-76
         skip, smask = feats[5 - i], masks[5 - i]
-        upf = _pad_to(F.interpolate(up, scale_factor=2, mode="bilinear", align_corners=False), skip)
+        upf = _pad_to(_q(F.interpolate(up, scale_factor=2, mode="bilinear", align_corners=False)), skip)
         upm = _pad_to(F.interpolate(um, scale_factor=2, mode="nearest"), smask)
         merged = torch.cat([upf, skip], dim=1)                         # up-sampled channels first
         mm = torch.max(upm, smask)
         if trace is not None:
             trace[name + ".in_mask"] = mm
         up, um = pconv2d(merged, mm, sd, name + ".", s, p, training, True, trace)
-    d0 = _pad_to(F.interpolate(up, scale_factor=2, mode="bilinear", align_corners=False), x)   # :50
+    d0 = _pad_to(_q(F.interpolate(up, scale_factor=2, mode="bilinear", align_corners=False)), x)   # :50
     dm0 = _pad_to(F.interpolate(um, scale_factor=2, mode="nearest"), mask)                      # :51
     mc = torch.max(dm0, mask)                                          # :54
     if trace is not None:
@@ -239,15 +283,18 @@ def pconv_unet(x: Tensor, mask: Tensor, sd: SD, training: bool, trace: Optional[
 def discriminator(img: Tensor, sd: SD, training: bool) -> Tensor:
     h = img
     for idx, _, _, _, s, p, bn in DISC:
-        h = F.conv2d(h, sd[f"model.{idx}.weight"], sd[f"model.{idx}.bias"], s, p)
+        w = sd[f"model.{idx}.weight"]
+        h = F.conv2d(h, _q(w) if idx in (2, 5, 8) else w, sd[f"model.{idx}.bias"], s, p)
         if idx == 11:
             break
+        if bn is not None:
+            h = _q(h)
         if bn is not None:
             h = F.batch_norm(h, sd[f"model.{bn}.running_mean"], sd[f"model.{bn}.running_var"],
                              sd[f"model.{bn}.weight"], sd[f"model.{bn}.bias"], training, BN_MOMENTUM, BN_EPS)
             if training:
                 sd[f"model.{bn}.num_batches_tracked"] += 1
-        h = F.leaky_relu(h, 0.2)
+        h = _q(F.leaky_relu(h, 0.2))
     return h
 
 
@@ -258,7 +305,8 @@ def vgg_features(x3: Tensor, vgg: SD) -> Tensor:
     """torchvision vgg16().features[:16] (conv3x3+ReLU x2, pool, x2, pool, x3), frozen, eval."""
     h = x3
     for idx, _, _ in VGG_CONVS:
-        h = F.relu(F.conv2d(h, vgg[f"{idx}.weight"], vgg[f"{idx}.bias"], 1, 1))
+        w = vgg[f"{idx}.weight"]
+        h = _q(F.relu(F.conv2d(h, _q(w) if idx > 0 else w, vgg[f"{idx}.bias"], 1, 1)))
         if idx in VGG_POOL_AFTER:
             h = F.max_pool2d(h, 2, 2)
     return h

@@ -145,7 +145,26 @@ def last_error() -> str:
     return buf.value.decode("utf-8", "replace")
 
 
+# calls per entry point since the last reset (bench.py turns these into a kernel-launch count)
+CALLS: dict = {}
+# kernels launched by one successful call of each entry point
+KERNELS_PER_CALL = {
+    "tg_mask_window_sum": 1, "tg_mask_merge_up": 1, "tg_mask_from_f32": 1, "tg_mask_to_f32": 1,
+    "tg_conv_igemm": 1, "tg_wgrad_igemm": 1, "tg_wgrad_reduce": 1,
+    "tg_bn_finalize": 1, "tg_bn_eval_coeff": 1, "tg_bn_apply": 1, "tg_bn_bwd_reduce": 1, "tg_bn_bwd_finalize": 1,
+    "tg_bn_bwd_apply": 1, "tg_upsample_concat": 1, "tg_upsample_concat_bwd": 1, "tg_maxpool2": 1,
+    "tg_maxpool2_bwd": 1, "tg_conv_c1_fwd": 1, "tg_conv_c1_wgrad": 2, "tg_conv_to1_fwd": 1,
+    "tg_conv_to1_bwd_data": 1, "tg_conv_to1_wgrad": 2, "tg_final_bwd_pre": 1, "tg_inpaint_loss_fwd": 2,
+    "tg_inpaint_loss_bwd": 1, "tg_l1_bf16_fwd": 2, "tg_l1_bf16_bwd": 1,
+}
+
+
+def kernel_launches() -> int:
+    return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in CALLS.items())
+
+
 def check(rc: int, what: str) -> None:
+    CALLS[what] = CALLS.get(what, 0) + 1
     if rc != 0:
         raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")
 

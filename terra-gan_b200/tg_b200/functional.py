@@ -46,7 +46,7 @@ class GeneratorFn(torch.autograd.Function):
     def forward(ctx, x, mask, module, names, *plist):
         _require_cuda(x, "PConvUNet")
         params = dict(zip(names, plist))
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
+        need = any(ctx.needs_input_grad)      # grad mode is already off inside Function.forward
         save = GenSave() if need else None
         with torch.no_grad():
             out = module._engine.forward(x, mask, params, module._bn_params(), module.training, save,
@@ -75,7 +75,7 @@ class DiscriminatorFn(torch.autograd.Function):
     def forward(ctx, img, module, names, *plist):
         _require_cuda(img, "Discriminator")
         params = dict(zip(names, plist))
-        need = torch.is_grad_enabled() and (img.requires_grad or any(p.requires_grad for p in plist))
+        need = any(ctx.needs_input_grad)
         save = DiscSave() if need else None
         with torch.no_grad():
             out = module._engine.forward(img, params, module._bn_params(), module.training, save)
@@ -99,7 +99,7 @@ class PerceptualFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inp, target, engine: VggEngine, vgg: Dict[str, torch.Tensor]):
         _require_cuda(inp, "InpaintingLoss")
-        need = torch.is_grad_enabled() and inp.requires_grad
+        need = ctx.needs_input_grad[0]
         saved: Optional[list] = [] if need else None
         with torch.no_grad():
             fi = engine.features(inp, vgg, saved)

@@ -16,6 +16,26 @@ from .plan import TapPlan
 
 BF16 = torch.bfloat16
 
+# bench.py sets PROFILE = [] to time every tensor-core launch with CUDA events on the launching stream:
+# entries are (kind, algorithmic FLOPs, start event, end event).
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(kind: str, flops: float, ev0) -> None:
+    if ev0 is None:
+        return
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev1.record()
+    PROFILE.append((kind, flops, ev0, ev1))
+
 
 def _req(t: torch.Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
@@ -92,7 +112,9 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
         rows = num_sms()
         stats = torch.empty((rows, 2, N), dtype=torch.float32, device=x.device)
         a.stats, a.stats_rows_cap = ptr(stats), rows
+    ev0 = _prof_begin()
     check(lib().tg_conv_igemm(C.byref(a), stream_ptr()), "tg_conv_igemm")
+    _prof_end("fprop" if plan.is_fprop else "dgrad", 2.0 * B * Ho * Wo * N * len(plan.taps) * Cc, ev0)
     if stats is not None:
         stats = stats[: a.stats_rows_used]
     return out, stats
@@ -135,7 +157,9 @@ def wgrad_igemm(x: torch.Tensor, g: torch.Tensor, plan: TapPlan, blks: torch.Ten
         a.tap_plane[i], a.tap_dh[i], a.tap_dw[i] = pl, dh, dw_
     a.partial, a.partial_cap = ptr(partial), need
     a.blks, a.num_blk = ptr(blks), T * (Cc // 64)
+    ev0 = _prof_begin()
     check(lib().tg_wgrad_igemm(C.byref(a), stream_ptr()), "tg_wgrad_igemm")
+    _prof_end("wgrad", 2.0 * B * Ho * Wo * N * T * Cc, ev0)
     check(lib().tg_wgrad_reduce(ptr(partial), a.splits, T, Cc, N, ptr(tap_perm), ptr(dw),
                                 1 if accumulate else 0, stream_ptr()), "tg_wgrad_reduce")
 

@@ -28,6 +28,7 @@ class TapPlan:
     k: int = 0
     stride: int = 1
     pad: int = 0
+    is_fprop: bool = True
 
 
 def fprop_plan(k: int, stride: int, pad: int) -> TapPlan:
@@ -60,7 +61,7 @@ def dgrad_plan(k: int, stride: int, pad: int) -> TapPlan:
                 taps.append((0, pad - kh, pad - kw))
                 kpos.append(kh * k + kw)
         subs.append((0, len(taps), 0, 0))
-        return TapPlan(taps, subs, kpos, 1, 1, k, stride, pad)
+        return TapPlan(taps, subs, kpos, 1, 1, k, stride, pad, False)
     for P in range(2):
         for Q in range(2):
             begin = len(taps)
@@ -73,7 +74,7 @@ def dgrad_plan(k: int, stride: int, pad: int) -> TapPlan:
                     taps.append((0, (P + pad - kh) // 2, (Q + pad - kw) // 2))
                     kpos.append(kh * k + kw)
             subs.append((begin, len(taps) - begin, begin, 2 * P + Q))
-    return TapPlan(taps, subs, kpos, 1, 4, k, stride, pad)
+    return TapPlan(taps, subs, kpos, 1, 4, k, stride, pad, False)
 
 
 def pack_w_fprop(w: torch.Tensor) -> torch.Tensor:
