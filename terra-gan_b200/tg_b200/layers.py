@@ -182,6 +182,7 @@ class GeneratorEngine:
     """PConvUNet.forward (generator.py:31-62) and its backward, hand-scheduled over the kernels."""
 
     def __init__(self):
+        self.debug = None        # tests/tools may set a dict to capture per-layer gz tensors in backward
         self.packs = {name: ConvPack(k, s, p) for name, _, _, k, s, p in ENC + DEC}
         self.final_plan = P.fprop_plan(3, 1, 1)
         self.final_taps = [(dh, dw) for (_, dh, dw) in self.final_plan.taps]
@@ -287,6 +288,8 @@ class GeneratorEngine:
             ls = save.layers[name]
             gz, dgam, dbet, dbias = ops.bn_bwd(g_src, None, ls.z, ls.scale, ls.shift, ls.mean, ls.invstd, ACT_RELU,
                                                0.0, pyr.dec_s[i], pk.lut_dev(dev), batch_stats=save.training)
+            if self.debug is not None:
+                self.debug[name + ".gz"] = gz
             wkey = name + ".input_conv.weight"
             grads[wkey] = torch.empty_like(params[wkey])
             ops.wgrad_igemm(ls.xin, gz, pk.fplan, pk.blks(cin, dev), pk.perm(dev), grads[wkey])
@@ -312,6 +315,8 @@ class GeneratorEngine:
                 a, b = skip_grads[i], g_next
             gz, dgam, dbet, dbias = ops.bn_bwd(a, b, ls.z, ls.scale, ls.shift, ls.mean, ls.invstd, ACT_RELU, 0.0,
                                                pyr.enc_s[i], pk.lut_dev(dev), batch_stats=save.training)
+            if self.debug is not None:
+                self.debug[name + ".gz"] = gz
             wkey = name + ".input_conv.weight"
             grads[wkey] = torch.empty_like(params[wkey])
             if i == 0:
