@@ -57,19 +57,31 @@ __device__ __forceinline__ long split_index(int b, int h, int w, int H, int W) {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-// One thread per channel: sums the per-CTA partial rows in fp64, then the usual BN bookkeeping.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float eps, float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float* __restrict__ scale,
-                                   float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// Block = 32 channels x 8 row lanes: the per-CTA partial rows are summed in fp64 (8-way parallel over
+// rows, coalesced over channels), then the usual BN bookkeeping.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ scale,
+                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  __shared__ double s_sum[8][32][2];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s = 0.0, s2 = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s += partial[(static_cast<long>(r) * 2) * C + c];
-    s2 += partial[(static_cast<long>(r) * 2 + 1) * C + c];
+  if (c < C) {
+    for (int r = rl; r < rows; r += 8) {
+      s += partial[(static_cast<long>(r) * 2) * C + c];
+      s2 += partial[(static_cast<long>(r) * 2 + 1) * C + c];
+    }
+  }
+  s_sum[rl][cl][0] = s;
+  s_sum[rl][cl][1] = s2;
+  __syncthreads();
+  if (rl != 0 || c >= C) return;
+#pragma unroll
+  for (int q = 1; q < 8; ++q) {
+    s += s_sum[q][cl][0];
+    s2 += s_sum[q][cl][1];
   }
   const double mean = s / count;
   double var = s2 / count - mean * mean;
@@ -229,17 +241,29 @@ __global__ void bn_bwd_reduce_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16
 }
 
 // coeff[0]=scale [1]=mean [2]=invstd [3]=c1 (= dbeta/M) [4]=c2 (= dgamma/M), each [C]
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
-                                       const float* __restrict__ scale, const float* __restrict__ mean,
-                                       const float* __restrict__ invstd, float* __restrict__ coeff,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ dbias, int accumulate, int batch_stats) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// Block = 32 channels x 8 row lanes (same scheme as bn_finalize_kernel).
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
+                       const float* __restrict__ scale, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, float* __restrict__ coeff, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ dbias, int accumulate, int batch_stats) {
+  __shared__ double s_sum[8][32][5];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s[5] = {0, 0, 0, 0, 0};
-  for (int r = 0; r < rows; ++r)
+  if (c < C) {
+    for (int r = rl; r < rows; r += 8)
 #pragma unroll
-    for (int k = 0; k < 5; ++k) s[k] += partial[(static_cast<long>(r) * 5 + k) * C + c];
+      for (int k = 0; k < 5; ++k) s[k] += partial[(static_cast<long>(r) * 5 + k) * C + c];
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) s_sum[rl][cl][k] = s[k];
+  __syncthreads();
+  if (rl != 0 || c >= C) return;
+#pragma unroll
+  for (int q = 1; q < 8; ++q)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s[k] += s_sum[q][cl][k];
   const double mu = mean[c], is = invstd[c], sc = scale[c];
   const double db = s[0];                          // dL/dbeta
   const double dg = is * (s[1] - mu * s[0]);       // dL/dgamma = sum g' * zhat
@@ -327,7 +351,7 @@ extern "C" int tg_bn_finalize(const float* partial, int rows, int C, double coun
   using namespace tg;
   TG_REQUIRE(partial && scale && shift && mean && invstd && rows > 0 && C > 0 && count > 0,
              "tg_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       partial, rows, C, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -391,7 +415,7 @@ extern "C" int tg_bn_bwd_finalize(const float* partial, int rows, int C, double 
                                   float* dbeta, float* dbias, int accumulate, int batch_stats, void* stream) {
   using namespace tg;
   TG_REQUIRE(partial && scale && mean && invstd && coeff && rows > 0, "tg_bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       partial, rows, C, count, scale, mean, invstd, coeff, dgamma, dbeta, dbias, accumulate, batch_stats);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -137,42 +137,61 @@ __global__ void __launch_bounds__(256)
 conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmask, int B, int H, int W, int pad,
                      const __nv_bfloat16* __restrict__ g /*[B][Ho][Wo][64]*/, int Ho, int Wo, int g_split,
                      float* __restrict__ partial) {
+  // Block = one 32x4 tile of output pixels at a time (persistent over tiles); the masked, zero-padded
+  // input patch is staged in shared memory once, then warp w streams 16 of the 128 pixels: lane =
+  // output-channel pair, per tap one broadcast LDS + 2 FMAs.
   constexpr int T = K * K;
+  constexpr int IW = (kC1TW - 1) * S + K, IH = (kC1TH - 1) * S + K;
   __shared__ float s_red[64][T + 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 64 * (T + 1); i += 256) (&s_red[0][0])[i] = 0.f;
-  __syncthreads();
+  __shared__ float s_in[IH][IW + 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 64 * (T + 1); i += 256) (&s_red[0][0])[i] = 0.f;
   float acc[T + 1][2];
 #pragma unroll
   for (int t = 0; t <= T; ++t) acc[t][0] = acc[t][1] = 0.f;
-  const long M = static_cast<long>(B) * Ho * Wo;
-  for (long p = static_cast<long>(blockIdx.x) * 8 + warp; p < M; p += static_cast<long>(gridDim.x) * 8) {
-    const int wo = static_cast<int>(p % Wo);
-    const int ho = static_cast<int>((p / Wo) % Ho);
-    const int b = static_cast<int>(p / (static_cast<long>(Wo) * Ho));
-    const long gp = g_split ? dc_split_index(b, ho, wo, Ho, Wo) : p;
-    const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(g + gp * 64 + 2 * lane);
-    const float2 gf = __bfloat1622float2(g2);
-    acc[T][0] += gf.x;
-    acc[T][1] += gf.y;
-    const float* xb = x + static_cast<long>(b) * H * W;
-    const uint8_t* mb = xmask ? xmask + static_cast<long>(b) * H * W : nullptr;
+  const int tiles_w = (Wo + kC1TW - 1) / kC1TW, tiles_h = (Ho + kC1TH - 1) / kC1TH;
+  const long total_tiles = static_cast<long>(B) * tiles_h * tiles_w;
+  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tw = static_cast<int>(tile % tiles_w);
+    const int th = static_cast<int>((tile / tiles_w) % tiles_h);
+    const int b = static_cast<int>(tile / (static_cast<long>(tiles_w) * tiles_h));
+    const int ih0 = th * kC1TH * S - pad, iw0 = tw * kC1TW * S - pad;
+    __syncthreads();
+    for (int i = tid; i < IH * IW; i += 256) {
+      const int r = i / IW, c = i % IW;
+      const int h = ih0 + r, w = iw0 + c;
+      float v = 0.f;
+      if (h >= 0 && h < H && w >= 0 && w < W) {
+        const long o = (static_cast<long>(b) * H + h) * W + w;
+        v = x[o];
+        if (xmask != nullptr && xmask[o] == 0) v = 0.f;
+      }
+      s_in[r][c] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int q = 0; q < 16; ++q) {
+      const int pt = warp * 16 + q;               // pixel of the tile handled by this warp
+      const int tx = pt % kC1TW, ty = pt / kC1TW;
+      const int ho = th * kC1TH + ty, wo = tw * kC1TW + tx;
+      if (ho >= Ho || wo >= Wo) continue;         // warp-uniform
+      const long p = (static_cast<long>(b) * Ho + ho) * Wo + wo;
+      const long gp = g_split ? dc_split_index(b, ho, wo, Ho, Wo) : p;
+      const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g + gp * 64 + 2 * lane));
+      acc[T][0] += gf.x;
+      acc[T][1] += gf.y;
 #pragma unroll
-    for (int kh = 0; kh < K; ++kh) {
-      const int h = ho * S + kh - pad;
+      for (int kh = 0; kh < K; ++kh) {
 #pragma unroll
-      for (int kw = 0; kw < K; ++kw) {
-        const int w = wo * S + kw - pad;
-        float xv = 0.f;
-        if (h >= 0 && h < H && w >= 0 && w < W) {
-          xv = __ldg(xb + h * W + w);
-          if (mb != nullptr && mb[h * W + w] == 0) xv = 0.f;
+        for (int kw = 0; kw < K; ++kw) {
+          const float xv = s_in[ty * S + kh][tx * S + kw];
+          acc[kh * K + kw][0] += xv * gf.x;
+          acc[kh * K + kw][1] += xv * gf.y;
         }
-        acc[kh * K + kw][0] += xv * gf.x;
-        acc[kh * K + kw][1] += xv * gf.y;
       }
     }
   }
+  __syncthreads();
 #pragma unroll
   for (int t = 0; t <= T; ++t) {
     atomicAdd(&s_red[2 * lane][t], acc[t][0]);
@@ -276,10 +295,193 @@ conv_to1_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_split, int B, int
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1, C = 64 specialisation of the C->1 gather (final conv fwd + composite, VGG
+// conv0 data gradient) and of its weight gradient. Block = 8x32 output tile; the 10x34-pixel halo
+// tile (43.5 KB of bf16) is staged in shared memory with coalesced 16-byte loads so every input byte
+// is read from HBM once; 8 lanes x 8 channels per pixel quad; each 16-byte LDS feeds up to 3 taps.
+// ------------------------------------------------------------------------------------------------
+constexpr int kT1H = 8, kT1W = 32;
+struct Tap3x3 { int idx[9]; };   // idx[(dh+1)*3 + (dw+1)] = row of wgt for that offset
+
+__device__ __forceinline__ void t1_load_halo(__nv_bfloat16 (*s_x)[kT1W + 2][64], const __nv_bfloat16* __restrict__ x,
+                                             int b, int h0, int w0, int H, int W) {
+  for (int i = threadIdx.x; i < (kT1H + 2) * (kT1W + 2) * 8; i += 256) {
+    const int v = i & 7, pix = i >> 3;
+    const int hr = pix / (kT1W + 2), hc = pix % (kT1W + 2);
+    const int h = h0 - 1 + hr, w = w0 - 1 + hc;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (h >= 0 && h < H && w >= 0 && w < W)
+      val = *reinterpret_cast<const uint4*>(x + ((static_cast<long>(b) * H + h) * W + w) * 64 + v * 8);
+    *reinterpret_cast<uint4*>(&s_x[hr][hc][v * 8]) = val;
+  }
+}
+
+__device__ __forceinline__ void t1_unpack(const uint4& raw, float (&f)[8]) {
+  const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 t = __bfloat1622float2(hh[q]);
+    f[2 * q] = t.x;
+    f[2 * q + 1] = t.y;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+conv3x3_c64_to1_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, const float* __restrict__ wgt,
+                       Tap3x3 tp, const float* __restrict__ bias, int mode, const uint8_t* __restrict__ mask,
+                       const float* __restrict__ xin, float* __restrict__ out, float* __restrict__ sig_out) {
+  __shared__ __align__(16) __nv_bfloat16 s_x[kT1H + 2][kT1W + 2][64];
+  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(wgt + tp.idx[t] * 64 + sub * 8 + j);
+  const float bv = bias ? __ldg(bias) : 0.f;
+  const int tiles_w = (W + kT1W - 1) / kT1W, tiles_h = (H + kT1H - 1) / kT1H;
+  const long total_tiles = static_cast<long>(B) * tiles_h * tiles_w;
+  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tw = static_cast<int>(tile % tiles_w);
+    const int th = static_cast<int>((tile / tiles_w) % tiles_h);
+    const int b = static_cast<int>(tile / (static_cast<long>(tiles_w) * tiles_h));
+    const int h0 = th * kT1H, w0 = tw * kT1W;
+    __syncthreads();
+    t1_load_halo(s_x, x, b, h0, w0, H, W);
+    __syncthreads();
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      const int q = ps * 32 + grp;
+      const int row = q >> 3, col0 = (q & 7) * 4;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+          float v[8];
+          t1_unpack(*reinterpret_cast<const uint4*>(&s_x[row + r][col0 + cc][sub * 8]), v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kw = cc - j;
+            if (kw >= 0 && kw < 3) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[j] += v[e] * wr[r * 3 + kw][e];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+      }
+      const int h = h0 + row, w = w0 + col0;
+      if (sub == 0 && h < H) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (w + j >= W) break;
+          const long p = (static_cast<long>(b) * H + h) * W + w + j;
+          const float val = acc[j] + bv;
+          if (mode == 0) {
+            out[p] = val;
+          } else {
+            const float sg = 1.f / (1.f + __expf(-val));
+            if (sig_out) sig_out[p] = sg;
+            const float m = mask[p] ? 1.f : 0.f;
+            out[p] = sg * (1.f - m) + xin[p] * m;
+          }
+        }
+      }
+    }
+  }
+}
+
+// dw[t][c] = sum_o g[o] * x[o + d_t][c], db = sum_o g[o]; partial[block][9][64], partial_b[block]
+__global__ void __launch_bounds__(256)
+conv3x3_c64_to1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, const float* __restrict__ g,
+                             Tap3x3 tp, float* __restrict__ partial, float* __restrict__ partial_b) {
+  __shared__ __align__(16) __nv_bfloat16 s_x[kT1H + 2][kT1W + 2][64];
+  __shared__ float s_red[9][64];
+  __shared__ float s_b;
+  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  for (int i = threadIdx.x; i < 9 * 64; i += 256) (&s_red[0][0])[i] = 0.f;
+  if (threadIdx.x == 0) s_b = 0.f;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  float gsum = 0.f;
+  const int tiles_w = (W + kT1W - 1) / kT1W, tiles_h = (H + kT1H - 1) / kT1H;
+  const long total_tiles = static_cast<long>(B) * tiles_h * tiles_w;
+  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tw = static_cast<int>(tile % tiles_w);
+    const int th = static_cast<int>((tile / tiles_w) % tiles_h);
+    const int b = static_cast<int>(tile / (static_cast<long>(tiles_w) * tiles_h));
+    const int h0 = th * kT1H, w0 = tw * kT1W;
+    __syncthreads();
+    t1_load_halo(s_x, x, b, h0, w0, H, W);
+    __syncthreads();
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      const int q = ps * 32 + grp;
+      const int row = q >> 3, col0 = (q & 7) * 4;
+      const int h = h0 + row, w = w0 + col0;
+      float gv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        gv[j] = (h < H && w + j < W) ? __ldg(g + (static_cast<long>(b) * H + h) * W + w + j) : 0.f;
+      if (sub == 0) gsum += gv[0] + gv[1] + gv[2] + gv[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+          float v[8];
+          t1_unpack(*reinterpret_cast<const uint4*>(&s_x[row + r][col0 + cc][sub * 8]), v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kw = cc - j;
+            if (kw >= 0 && kw < 3) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[r * 3 + kw][e] += gv[j] * v[e];
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_red[t][sub * 8 + j], acc[t][j]);
+  if (sub == 0) atomicAdd(&s_b, gsum);
+  __syncthreads();
+  // s_red is indexed by spatial offset (dh+1)*3+(dw+1); emit in the caller's tap order
+  for (int i = threadIdx.x; i < 9 * 64; i += 256) {
+    const int o = i / 64, c = i % 64;
+    partial[(static_cast<long>(blockIdx.x) * 9 + tp.idx[o]) * 64 + c] = s_red[o][c];
+  }
+  if (threadIdx.x == 0 && partial_b != nullptr) partial_b[blockIdx.x] = s_b;
+}
+
+static bool make_tap3x3(Tap3x3* tp, int ntaps, const int8_t* dh, const int8_t* dw) {
+  if (ntaps != 9) return false;
+  for (int i = 0; i < 9; ++i) tp->idx[i] = -1;
+  for (int t = 0; t < 9; ++t) {
+    if (dh[t] < -1 || dh[t] > 1 || dw[t] < -1 || dw[t] > 1) return false;
+    tp->idx[(dh[t] + 1) * 3 + dw[t] + 1] = t;
+  }
+  for (int i = 0; i < 9; ++i)
+    if (tp->idx[i] < 0) return false;
+  return true;
+}
+
 // data gradient of a stride-1 C->1 conv: dx[b][h][w][c] = sum_t g[b][h - dh_t][w - dw_t] * w[t][c]
-__global__ void conv_to1_bwd_data_kernel(const float* __restrict__ g, int B, int Ho, int Wo,
-                                         const float* __restrict__ wgt, To1Taps taps, int H, int W, int C,
-                                         __nv_bfloat16* __restrict__ dx) {
+__global__ void __launch_bounds__(256)
+conv_to1_bwd_data_kernel(const float* __restrict__ g, int B, int Ho, int Wo, const float* __restrict__ wgt, To1Taps taps,
+                         int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
   const int cv = C >> 3;
   const long total = static_cast<long>(B) * H * W * cv;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -302,6 +504,44 @@ __global__ void conv_to1_bwd_data_kernel(const float* __restrict__ g, int B, int
       acc[4] += gv * w1.x; acc[5] += gv * w1.y; acc[6] += gv * w1.z; acc[7] += gv * w1.w;
     }
     *reinterpret_cast<uint4*>(dx + p * C + c) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                   pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// 3x3 / C = 64 specialisation: the 72 weights of a thread's 8-channel group live in registers
+__global__ void __launch_bounds__(256)
+conv3x3_c64_to1_bwd_data_kernel(const float* __restrict__ g, int B, int H, int W, const float* __restrict__ wgt,
+                                Tap3x3 tp, __nv_bfloat16* __restrict__ dx) {
+  const int sub = threadIdx.x & 7;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(wgt + tp.idx[t] * 64 + sub * 8 + j);
+  const long total = static_cast<long>(B) * H * W;
+  for (long p = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 3; p < total;
+       p += (static_cast<long>(gridDim.x) * blockDim.x) >> 3) {
+    const int w = static_cast<int>(p % W);
+    const int h = static_cast<int>((p / W) % H);
+    const float* gb = g + (p - static_cast<long>(h) * W - w);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh) {
+      const int oh = h - dh;
+      if (oh < 0 || oh >= H) continue;
+#pragma unroll
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int ow = w - dw;
+        if (ow < 0 || ow >= W) continue;
+        const float gv = __ldg(gb + oh * W + ow);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += gv * wr[(dh + 1) * 3 + dw + 1][j];
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + p * 64 + sub * 8) =
         make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
                    pack_bf16x2(acc[6], acc[7]));
   }
@@ -448,8 +688,8 @@ extern "C" int tg_conv_c1_wgrad(const float* x, const uint8_t* xmask, int B, int
   using namespace tg;
   TG_REQUIRE(x && g && partial && dw, "tg_conv_c1_wgrad: null pointer");
   const int Ho = (H + 2 * pad - k) / s + 1, Wo = (W + 2 * pad - k) / s + 1;
-  const long M = static_cast<long>(B) * Ho * Wo;
-  int grid = dc_grid(M, 8, 2);
+  const long tiles = static_cast<long>(B) * ((Ho + kC1TH - 1) / kC1TH) * ((Wo + kC1TW - 1) / kC1TW);
+  int grid = static_cast<int>(tiles < 2L * num_sms() ? tiles : 2L * num_sms());
   if (grid > rows_cap) grid = rows_cap;
   TG_REQUIRE(grid >= 1, "tg_conv_c1_wgrad: rows_cap must be >= 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -479,6 +719,15 @@ extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, 
   TG_REQUIRE(mode == 0 || (mask && xin), "tg_conv_to1_fwd: composite mode needs mask and xin");
   To1Taps taps;
   TG_REQUIRE(fill_taps(&taps, ncls, cls_count, tap_dh, tap_dw) > 0, "tg_conv_to1_fwd: bad tap table");
+  Tap3x3 tp;
+  if (ncls == 1 && C == 64 && !x_split && Ho == H && Wo == W && make_tap3x3(&tp, cls_count[0], tap_dh, tap_dw)) {
+    const long tiles = static_cast<long>(B) * ((H + kT1H - 1) / kT1H) * ((W + kT1W - 1) / kT1W);
+    const int g3 = static_cast<int>(tiles < 4L * num_sms() ? tiles : 4L * num_sms());
+    conv3x3_c64_to1_kernel<<<g3, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, wgt, tp, bias, mode, mask, xin, out, sig_out);
+    TG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const long M = static_cast<long>(B) * Ho * Wo;
   const int grid = dc_grid(M * 8, 256, 8);
   conv_to1_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -496,6 +745,13 @@ extern "C" int tg_conv_to1_bwd_data(const float* g, int B, int Ho, int Wo, const
   To1Taps taps;
   TG_REQUIRE(fill_taps(&taps, 1, &ntaps, tap_dh, tap_dw) > 0, "tg_conv_to1_bwd_data: bad tap table");
   const long total = static_cast<long>(B) * H * W * (C / 8);
+  Tap3x3 tp;
+  if (C == 64 && Ho == H && Wo == W && make_tap3x3(&tp, ntaps, tap_dh, tap_dw)) {
+    conv3x3_c64_to1_bwd_data_kernel<<<dc_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        g, B, H, W, wgt, tp, reinterpret_cast<__nv_bfloat16*>(dx));
+    TG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   conv_to1_bwd_data_kernel<<<dc_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       g, B, Ho, Wo, wgt, taps, H, W, C, reinterpret_cast<__nv_bfloat16*>(dx));
   TG_CHECK_CUDA(cudaGetLastError());
@@ -518,6 +774,18 @@ extern "C" int tg_conv_to1_wgrad(const void* x, int B, int H, int W, int C, cons
   TG_REQUIRE(gx >= 1, "tg_conv_to1_wgrad: rows_cap must be >= 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+  Tap3x3 tp;
+  if (C == 64 && Ho == H && Wo == W && make_tap3x3(&tp, ntaps, tap_dh, tap_dw)) {
+    const long tiles = static_cast<long>(B) * ((H + kT1H - 1) / kT1H) * ((W + kT1W - 1) / kT1W);
+    int g3 = static_cast<int>(tiles < 4L * num_sms() ? tiles : 4L * num_sms());
+    if (g3 > rows_cap) g3 = rows_cap;
+    conv3x3_c64_to1_wgrad_kernel<<<g3, 256, 0, st>>>(xx, B, H, W, g, tp, partial, partial_b);
+    TG_CHECK_CUDA(cudaGetLastError());
+    conv_to1_wgrad_reduce_kernel<<<(ntaps * C + 127) / 128, 128, 0, st>>>(partial, partial_b, g3, ntaps, C, dw, db,
+                                                                         accumulate);
+    TG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   dim3 grid(gx, slabs);
   if (ntaps == 9) conv_to1_wgrad_kernel<9><<<grid, 128, 0, st>>>(xx, B, H, W, C, g, Ho, Wo, taps, partial, partial_b);
   else if (ntaps == 16) conv_to1_wgrad_kernel<16><<<grid, 128, 0, st>>>(xx, B, H, W, C, g, Ho, Wo, taps, partial, partial_b);

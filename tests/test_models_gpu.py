@@ -49,6 +49,11 @@ def grad_ok(got, ref32, refq, name="", scale=0.0):
     e32, floor, eq = rel_err(got, ref32, scale), rel_err(refq, ref32, scale), rel_err(got, refq, scale)
     l32, lfloor = rel_l2(got, ref32, scale), rel_l2(refq, ref32, scale)
     ok = e32 <= TOL or (e32 <= TOL + 4 * floor and l32 <= TOL + 4 * lfloor)
+    if scale > 0.0:
+        # conv bias feeding train-mode BatchNorm: its true gradient is ~0 (BN removes any constant shift; only
+        # the per-pixel mask ratio leaves a residue) and the reference's own value is rounding noise, so it is
+        # only required to stay small relative to the BN-bias gradient of the same layer
+        ok = ok or e32 <= 0.25
     return ok, (name, round(e32, 4), round(floor, 4), round(eq, 4), "L2", round(l32, 4), round(lfloor, 4))
 
 
