@@ -230,7 +230,13 @@ def run_ours(args):
     clocks = sampler.stop()
 
     tc = {}
-    for kind, flops, a, b in prof:
+    if args.per_launch and rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", args.per_launch), "w") as f:
+            for kind, flops, a, b, shape in prof[: len(prof) // max(args.steps, 1)]:
+                ms = a.elapsed_time(b)
+                f.write(f"{kind:6s} {ms*1e3:9.1f} us {flops/ms/1e9:8.1f} TFLOP/s  {flops/1e9:9.1f} GF  {shape}\n")
+    for kind, flops, a, b, _shape in prof:
         t = tc.setdefault(kind, [0.0, 0.0, 0])
         t[0] += flops
         t[1] += a.elapsed_time(b)
@@ -294,6 +300,7 @@ def main():
     ap.add_argument("--ref-graph", action="store_true",
                     help="also compute the discriminator weight gradients of the generator step (discarded by the reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-launch", default="", help="write a per-launch table of the tensor-core kernels to gpurun_out/<name>")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,138 @@
+// conv_epilogue.cuh — epilogue of one 128-pixel x BN-channel accumulator tile, shared by the
+// implicit-GEMM convolution kernels (conv_igemm.cu: per-tap TMA boxes; conv_halo.cu: halo-tile reuse).
+// One thread = one output pixel (TMEM lane); columns are drained 32 at a time with tcgen05.ld.
+#pragma once
+#include "conv_igemm.cuh"
+#include "tg_common.cuh"
+
+namespace tg {
+
+// s_vec: [3][kVec] bias / scale / shift staged in shared memory; my_stats: this warp's [2][kVec] accumulators.
+// stage: this warp's private 32 x (kSC*2)-byte staging tile. Each thread owns one pixel row, so a direct
+// store would touch 32 different 128-byte lines per instruction (the LSU serialises them: measured 4x the
+// MMA time on the N=64 layers). Rows are therefore written to shared memory (XOR-swizzled, conflict-free)
+// and read back transposed so that every global store instruction writes full contiguous lines.
+template <int BN, int kVec, int kSC>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, int lane, int nt, int sb, int tw,
+                                                   int th, int tb, uint32_t t_addr, const float* s_vec,
+                                                   float* my_stats, bool has_vec, uint8_t* stage, int hsel) {
+  static_assert(kSC == 32 || kSC == 64, "staging width is 32 or 64 columns");
+  constexpr int kLPR = kSC / 8;           // 16-byte chunks (= lanes) per staged row
+  constexpr int kRowBytes = kSC * 2;
+  constexpr int kChunksPerStage = kSC / 32;
+  const int r = q * 32 + lane;  // row of the tile = pixel in box order
+  const int wt = r % p.Wt;
+  const int ht = (r / p.Wt) % p.Ht;
+  const int bt = r / (p.Wt * p.Ht);
+  const int w = tw * p.Wt + wt, h = th * p.Ht + ht, b = tb * p.Bt + bt;
+  const bool valid = (w < p.Wo) && (h < p.Ho) && (b < p.B);
+  const long pix =
+      ((static_cast<long>(b) * p.Po + p.sub[sb].out_plane) * p.Ho + h) * p.Wo + w;
+  float rs = 1.f;
+  if (p.code != nullptr && valid) rs = p.lut[p.code[pix]];
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const bool has_affine = p.scale != nullptr || p.shift != nullptr;
+  const int sw_w = (kSC == 64) ? (lane & 7) : ((lane >> 1) & 3);     // write-side swizzle key of this row
+  const __nv_bfloat16* grow = p.gate ? p.gate + pix * p.Cout + nt * BN : nullptr;
+
+  // two warps share each TMEM lane quarter: warp `hsel` takes every other kSC-column group
+#pragma unroll 1
+  for (int ch = 0; ch < BN / 32; ++ch) {
+    if (((ch / kChunksPerStage) & 1) != hsel) continue;
+    uint32_t raw[32];
+    tmem_ld_32x32(t_addr + ch * 32, raw);
+    tmem_ld_wait();
+    const int n0 = nt * BN + ch * 32;
+    float v[32];
+    if (has_vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bv = *reinterpret_cast<const float4*>(s_vec + n0 + j);
+        v[j] = __uint_as_float(raw[j]) + bv.x;
+        v[j + 1] = __uint_as_float(raw[j + 1]) + bv.y;
+        v[j + 2] = __uint_as_float(raw[j + 2]) + bv.z;
+        v[j + 3] = __uint_as_float(raw[j + 3]) + bv.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+    }
+    const float rsv = valid ? rs : 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= rsv;
+    if (p.stats != nullptr) {
+      float sq[32], sm[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        sm[j] = v[j];
+        sq[j] = v[j] * v[j];
+      }
+      const float csum = warp_transpose_sum32(sm);
+      const float csq = warp_transpose_sum32(sq);
+      my_stats[n0 + lane] += csum;
+      my_stats[kVec + n0 + lane] += csq;
+    }
+    uint32_t packed[16];
+    uint32_t gbits[16];
+    if (grow != nullptr && valid) {
+      const uint4* gsrc = reinterpret_cast<const uint4*>(grow + ch * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 t = gsrc[j];
+        gbits[4 * j] = t.x; gbits[4 * j + 1] = t.y; gbits[4 * j + 2] = t.z; gbits[4 * j + 3] = t.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float a = v[j], c = v[j + 1];
+      if (has_affine) {
+        const float2 sc2 = *reinterpret_cast<const float2*>(s_vec + kVec + n0 + j);
+        const float2 sh2 = *reinterpret_cast<const float2*>(s_vec + 2 * kVec + n0 + j);
+        a = a * sc2.x + sh2.x;
+        c = c * sc2.y + sh2.y;
+      }
+      if (grow != nullptr && valid) {
+        // derivative of ReLU / LeakyReLU of the tensor this gradient flows into
+        const float2 gv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gbits[j >> 1]));
+        if (!(gv.x > 0.f)) a *= p.gate_slope;
+        if (!(gv.y > 0.f)) c *= p.gate_slope;
+      }
+      if (p.act == 1) {
+        a = fmaxf(a, 0.f);
+        c = fmaxf(c, 0.f);
+      } else if (p.act == 2) {
+        a = a > 0.f ? a : a * p.slope;
+        c = c > 0.f ? c : c * p.slope;
+      }
+      packed[j >> 1] = pack_bf16x2(a, c);
+    }
+    {
+      const int cbase = (ch % kChunksPerStage) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(stage + lane * kRowBytes + (((cbase + j) ^ sw_w) << 4)) =
+            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    }
+    if ((ch % kChunksPerStage) == kChunksPerStage - 1) {
+      __syncwarp();
+      const int col0 = nt * BN + (ch - (kChunksPerStage - 1)) * 32;   // first channel held by the staging tile
+#pragma unroll
+      for (int i = 0; i < kLPR; ++i) {
+        const int row = i * (32 / kLPR) + lane / kLPR;
+        const int chunk = lane % kLPR;
+        const int key = (kSC == 64) ? (row & 7) : ((row >> 1) & 3);
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + row * kRowBytes + ((chunk ^ key) << 4));
+        // pixel index of the row this lane stores: held by lane `row` of the warp
+        const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(pix & 0xffffffffu), row);
+        const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(static_cast<unsigned long long>(pix) >> 32), row);
+        if (((vmask >> row) & 1u) && !(p.debug & 1)) {
+          const long pix2 = static_cast<long>((static_cast<unsigned long long>(hi) << 32) | lo);
+          *reinterpret_cast<uint4*>(p.out + pix2 * p.Cout + col0 + chunk * 8) = val;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+}  // namespace tg

@@ -19,27 +19,32 @@
 //
 // Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
 // warps 4..7 epilogue (TMEM lane quarter = warp_idx % 4).
+#include <stdlib.h>
+
+#include "conv_epilogue.cuh"
 #include "conv_igemm.cuh"
 #include "tg_common.cuh"
 #include "../../include/terragan_b200.h"
 
 namespace tg {
 
-constexpr int kStages = 4;
 constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
 
 template <int BN>
 struct ConvSmem {
+  static constexpr int kStages = (BN >= 256) ? 3 : 4;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTiles = kStages * kStageBytes;
   static constexpr int kStatsFloats = 4 * 2 * 512;  // per epilogue warp (sum, sumsq) x channel
   static constexpr int kVecFloats = 3 * 512;        // bias / scale / shift
-  static constexpr int kTotal = kTiles + (kStatsFloats + kVecFloats) * 4 + 256 + 1024;
+  static constexpr int kStoreCols = (BN == 128) ? 64 : 32;                 // epilogue staging width
+  static constexpr int kStageOutBytes = 8 * 32 * kStoreCols * 2;            // per-warp transposing tiles
+  static constexpr int kTotal = kTiles + (kStatsFloats + kVecFloats) * 4 + kStageOutBytes + 256 + 1024;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -47,9 +52,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   using S = ConvSmem<BN>;
+  constexpr int kStages = S::kStages;
   float* s_stats = reinterpret_cast<float*>(smem + S::kTiles);
   float* s_vec = s_stats + S::kStatsFloats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + S::kVecFloats);
+  uint8_t* s_out = reinterpret_cast<uint8_t*>(s_vec + S::kVecFloats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + S::kStageOutBytes);
   uint64_t* full_bar = bars;                    // [kStages]
   uint64_t* empty_bar = bars + kStages;         // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
@@ -83,7 +90,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -171,7 +178,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp - 4;  // TMEM lane quarter == warp_idx % 4
+    const int q = (warp - 4) & 3;   // TMEM lane quarter == warp_idx % 4
+    const int hsel = (warp - 4) >> 2;  // which half of the column groups this warp drains
     float* my_stats = s_stats + q * (2 * 512);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -183,87 +191,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int tb = mt / (p.tiles_w * p.tiles_h);
-      const int r = q * 32 + lane;  // row of the tile = pixel in box order
-      const int wt = r % p.Wt;
-      const int ht = (r / p.Wt) % p.Ht;
-      const int bt = r / (p.Wt * p.Ht);
-      const int w = tw * p.Wt + wt, h = th * p.Ht + ht, b = tb * p.Bt + bt;
-      const bool valid = (w < p.Wo) && (h < p.Ho) && (b < p.B);
-      const long pix =
-          ((static_cast<long>(b) * p.Po + p.sub[sb].out_plane) * p.Ho + h) * p.Wo + w;
-      float rs = 1.f;
-      if (p.code != nullptr && valid) rs = p.lut[p.code[pix]];
-      __nv_bfloat16* orow = p.out + pix * p.Cout + nt * BN;
-      const __nv_bfloat16* grow = p.gate ? p.gate + pix * p.Cout + nt * BN : nullptr;
-
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t raw[32];
-        tmem_ld_32x32(t_addr + ch * 32, raw);
-        tmem_ld_wait();
-        const int n0 = nt * BN + ch * 32;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(raw[j]);
-          if (has_vec) x += s_vec[n0 + j];
-          v[j] = valid ? x * rs : 0.f;
-        }
-        if (p.stats != nullptr) {
-          float sq[32], sm[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            sm[j] = v[j];
-            sq[j] = v[j] * v[j];
-          }
-          const float csum = warp_transpose_sum32(sm);
-          const float csq = warp_transpose_sum32(sq);
-          my_stats[n0 + lane] += csum;
-          my_stats[512 + n0 + lane] += csq;
-        }
-        uint32_t packed[16];
-        uint32_t gbits[16];
-        if (grow != nullptr && valid) {
-          const uint4* gsrc = reinterpret_cast<const uint4*>(grow + ch * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 t = gsrc[j];
-            gbits[4 * j] = t.x; gbits[4 * j + 1] = t.y; gbits[4 * j + 2] = t.z; gbits[4 * j + 3] = t.w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float a = v[j], c = v[j + 1];
-          if (has_vec) {
-            a = a * s_vec[512 + n0 + j] + s_vec[1024 + n0 + j];
-            c = c * s_vec[512 + n0 + j + 1] + s_vec[1024 + n0 + j + 1];
-          }
-          if (grow != nullptr && valid) {
-            // derivative of ReLU / LeakyReLU of the tensor this gradient flows into
-            const float2 gv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gbits[j >> 1]));
-            if (!(gv.x > 0.f)) a *= p.gate_slope;
-            if (!(gv.y > 0.f)) c *= p.gate_slope;
-          }
-          if (p.act == 1) {
-            a = fmaxf(a, 0.f);
-            c = fmaxf(c, 0.f);
-          } else if (p.act == 2) {
-            a = a > 0.f ? a : a * p.slope;
-            c = c > 0.f ? c : c * p.slope;
-          }
-          packed[j >> 1] = pack_bf16x2(a, c);
-        }
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2],
-                                packed[4 * j + 3]);
-        }
-      }
+      conv_epilogue_tile<BN, 512, S::kStoreCols>(p, q, lane, nt, sb, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
+                                                 s_out + (warp - 4) * (32 * S::kStoreCols * 2), hsel);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -274,10 +206,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     // flush the per-CTA BatchNorm partials: one row per CTA, summed by tg_bn_finalize
     if (p.stats != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int et = threadIdx.x - 128;
       float* dst = p.stats + static_cast<long>(blockIdx.x) * 2 * p.Cout;
-      for (int c = et; c < p.Cout; c += 128) {
+      for (int c = et; c < p.Cout; c += 256) {
         float a = 0.f, s2 = 0.f;
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
@@ -300,6 +232,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+bool conv_halo_eligible(const tg_conv_args* a);                       // conv_halo.cu
+int conv_halo_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st);
+
+static bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TG_NO_HALO");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static void choose_box(int Ho, int Wo, int pixels, int* Bt, int* Ht, int* Wt) {
   int wt = 1;
   while (wt * 2 <= Wo && wt * 2 <= 16 && wt * 2 <= pixels) wt *= 2;
@@ -320,7 +264,7 @@ static int launch_conv(const tg_conv_args* a, const CUtensorMap& tmA, const CUte
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
-  conv_igemm_kernel<BN><<<grid, 256, S::kTotal, st>>>(tmA, tmB, kp);
+  conv_igemm_kernel<BN><<<grid, 384, S::kTotal, st>>>(tmA, tmB, kp);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -390,6 +334,13 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   kp.stats = a->stats;
   kp.gate = reinterpret_cast<const __nv_bfloat16*>(a->gate);
   kp.gate_slope = a->gate_slope;
+  {
+    const char* e = getenv("TG_CONV_DEBUG");
+    kp.debug = e ? atoi(e) : 0;
+  }
+
+  // small-N 3x3 stride-1 layers: halo-tile reuse + resident weights (conv_halo.cu)
+  if (halo_enabled() && conv_halo_eligible(a)) return conv_halo_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
 
   // A: channels-last activations as a 5-D tensor (C, W, H, P, B)
   CUtensorMap tmA, tmB;

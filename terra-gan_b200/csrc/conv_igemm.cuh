@@ -41,6 +41,7 @@ struct ConvKParams {
   float* stats;                   // [gridDim.x][2][Cout] per-CTA (sum, sum of squares) or null
   const __nv_bfloat16* gate;      // same shape as out, or null: out *= (gate > 0 ? 1 : gate_slope)
   float gate_slope;
+  int debug;                      // perf experiments only: 1 no stores, 2 no epilogue work, 4 no MMA
 };
 
 struct WgradBlk {                 // one 64-row block of dW^T: (tap, 64-channel block of the input)

@@ -29,12 +29,12 @@ def _prof_begin():
     return ev
 
 
-def _prof_end(kind: str, flops: float, ev0) -> None:
+def _prof_end(kind: str, flops: float, ev0, shape: str = "") -> None:
     if ev0 is None:
         return
     ev1 = torch.cuda.Event(enable_timing=True)
     ev1.record()
-    PROFILE.append((kind, flops, ev0, ev1))
+    PROFILE.append((kind, flops, ev0, ev1, shape))
 
 
 def _req(t: torch.Tensor, dtype, name: str) -> None:
@@ -114,7 +114,8 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
         a.stats, a.stats_rows_cap = ptr(stats), rows
     ev0 = _prof_begin()
     check(lib().tg_conv_igemm(C.byref(a), stream_ptr()), "tg_conv_igemm")
-    _prof_end("fprop" if plan.is_fprop else "dgrad", 2.0 * B * Ho * Wo * N * len(plan.taps) * Cc, ev0)
+    _prof_end("fprop" if plan.is_fprop else "dgrad", 2.0 * B * Ho * Wo * N * len(plan.taps) * Cc, ev0,
+              f"B{B} {H}x{W}x{Cc}(P{P}) -> {Ho}x{Wo}x{N}(P{Po}) taps{len(plan.taps)}")
     if stats is not None:
         stats = stats[: a.stats_rows_used]
     return out, stats
@@ -159,7 +160,7 @@ def wgrad_igemm(x: torch.Tensor, g: torch.Tensor, plan: TapPlan, blks: torch.Ten
     a.blks, a.num_blk = ptr(blks), T * (Cc // 64)
     ev0 = _prof_begin()
     check(lib().tg_wgrad_igemm(C.byref(a), stream_ptr()), "tg_wgrad_igemm")
-    _prof_end("wgrad", 2.0 * B * Ho * Wo * N * T * Cc, ev0)
+    _prof_end("wgrad", 2.0 * B * Ho * Wo * N * T * Cc, ev0, f"B{B} x {H}x{W}x{Cc}(P{P}) g {Ho}x{Wo}x{N} taps{T} splits{a.splits}")
     check(lib().tg_wgrad_reduce(ptr(partial), a.splits, T, Cc, N, ptr(tap_perm), ptr(dw),
                                 1 if accumulate else 0, stream_ptr()), "tg_wgrad_reduce")
 
