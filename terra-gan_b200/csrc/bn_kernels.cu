@@ -117,38 +117,51 @@ __global__ void bn_eval_coeff_kernel(int C, const float* __restrict__ gamma, con
   shift[c] = (beta ? beta[c] : 0.f) - running_mean[c] * sc;
 }
 
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long M, int C, int H, int W,
-                                const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                                float slope, const uint8_t* __restrict__ code,
-                                __nv_bfloat16* __restrict__ y_nhwc, __nv_bfloat16* __restrict__ y_split,
-                                int mask_split) {
-  const int cv = C >> 3;
-  const long total = M * cv;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long p = i / cv;
-    const int c = static_cast<int>(i % cv) << 3;
-    float v[8], sc[8], sh[8];
-    load8(z + p * C + c, v);
-    ldg8f(scale + c, sc);
-    ldg8f(shift + c, sh);
+// Channel-stationary: a thread owns one 8-channel vector (scale/shift live in registers) and strides
+// over pixels; 256 threads = (C/8) channel vectors x 256/(C/8) pixel lanes; two pixels in flight per
+// iteration; 32-bit pixel arithmetic.
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ z, unsigned M, int C, int H, int W,
+                const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope,
+                const uint8_t* __restrict__ code, __nv_bfloat16* __restrict__ y_nhwc,
+                __nv_bfloat16* __restrict__ y_split, int mask_split) {
+  const unsigned cv = C >> 3;
+  const unsigned lanes = blockDim.x / cv;
+  const unsigned c = (threadIdx.x % cv) << 3;
+  const unsigned lane = threadIdx.x / cv;
+  float sc[8], sh[8];
+  ldg8f(scale + c, sc);
+  ldg8f(shift + c, sh);
+  const unsigned stride = gridDim.x * lanes;
+  const unsigned HW = static_cast<unsigned>(H) * W;
+  for (unsigned p0 = blockIdx.x * lanes + lane; p0 < M; p0 += 2 * stride) {
+    const unsigned p1 = p0 + stride;
+    const bool two = p1 < M;
+    float v0[8], v1[8];
+    load8(z + static_cast<size_t>(p0) * C + c, v0);
+    if (two) load8(z + static_cast<size_t>(p1) * C + c, v1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = v[j] * sc[j] + sh[j];
-      if (act == 1) t = fmaxf(t, 0.f);
-      else if (act == 2) t = t > 0.f ? t : t * slope;
-      v[j] = t;
-    }
-    if (y_nhwc) store8(y_nhwc + p * C + c, v);
-    if (y_split) {
-      const int w = static_cast<int>(p % W);
-      const int h = static_cast<int>((p / W) % H);
-      const int b = static_cast<int>(p / (static_cast<long>(W) * H));
-      if (mask_split && code[p] == 0) {
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      float (&v)[8] = u ? v1 : v0;
+      const unsigned p = u ? p1 : p0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        float t = v[j] * sc[j] + sh[j];
+        if (act == 1) t = fmaxf(t, 0.f);
+        else if (act == 2) t = t > 0.f ? t : t * slope;
+        v[j] = t;
       }
-      store8(y_split + split_index(b, h, w, H, W) * C + c, v);
+      if (y_nhwc) store8(y_nhwc + static_cast<size_t>(p) * C + c, v);
+      if (y_split) {
+        const unsigned b = p / HW, rem = p - b * HW;
+        const unsigned h = rem / W, w = rem - h * W;
+        if (mask_split && code[p] == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        }
+        store8(y_split + static_cast<size_t>(split_index(b, h, w, H, W)) * C + c, v);
+      }
     }
   }
 }
@@ -196,19 +209,20 @@ __global__ void bn_bwd_reduce_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16
   ldg8f(scale + c, sc);
   ldg8f(shift + c, sh);
   const bool need_split = s0.split || (s1.ptr && s1.split);
-  if (my_lane < lanes) {
-    for (long p = static_cast<long>(blockIdx.x) * lanes + my_lane; p < M;
-         p += static_cast<long>(gridDim.x) * lanes) {
+  {
+    const unsigned Mu = static_cast<unsigned>(M);
+    const unsigned HW = static_cast<unsigned>(H) * W;
+    const unsigned stride = gridDim.x * lanes;
+    for (unsigned p = blockIdx.x * lanes + my_lane; p < Mu; p += stride) {
       long ps = 0;
       if (need_split) {
-        const int w = static_cast<int>(p % W);
-        const int h = static_cast<int>((p / W) % H);
-        const int b = static_cast<int>(p / (static_cast<long>(W) * H));
+        const unsigned b = p / HW, rem = p - b * HW;
+        const unsigned h = rem / W, w = rem - h * W;
         ps = split_index(b, h, w, H, W);
       }
       float g[8], zz[8];
       load_grad(s0, s1, p, ps, c, g);
-      load8(z + p * C + c, zz);
+      load8(z + static_cast<size_t>(p) * C + c, zz);
       const float r = code ? __ldg(lut + code[p]) : 1.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -220,9 +234,11 @@ __global__ void bn_bwd_reduce_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16
         acc[1][j] += gg * zz[j];
         acc[2][j] += r * gg;
         acc[3][j] += r * zz[j];
-        acc[4][j] += r;
       }
+      acc[4][0] += r;
     }
+#pragma unroll
+    for (int j = 1; j < 8; ++j) acc[4][j] = acc[4][0];
   }
   // reduce over pixel lanes through shared memory
   float* mine = red + (static_cast<long>(my_lane) * cv + my_cv) * 40;
@@ -281,35 +297,45 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, doubl
   if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + static_cast<float>(dbi);
 }
 
-// gz[p][c] = r[p] * scale[c] * (g' - c1[c] - zhat * c2[c])
-__global__ void bn_bwd_apply_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16* __restrict__ z, long M, int C,
-                                    int H, int W, const float* __restrict__ shift,
-                                    const float* __restrict__ coeff, int act, float slope,
-                                    const uint8_t* __restrict__ code, const float* __restrict__ lut,
-                                    __nv_bfloat16* __restrict__ gz) {
-  const int cv = C >> 3;
-  const long total = M * cv;
-  const bool need_split = s0.split || (s1.ptr && s1.split);
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long p = i / cv;
-    const int c = static_cast<int>(i % cv) << 3;
-    long ps = 0;
-    if (need_split) {
-      const int w = static_cast<int>(p % W);
-      const int h = static_cast<int>((p / W) % H);
-      const int b = static_cast<int>(p / (static_cast<long>(W) * H));
-      ps = split_index(b, h, w, H, W);
-    }
-    float g[8], zz[8], sc[8], sh[8], mu[8], is[8], c1[8], c2[8];
-    load_grad(s0, s1, p, ps, c, g);
-    load8(z + p * C + c, zz);
+// gz[p][c] = r[p] * scale[c] * (g' - c1[c] - zhat * c2[c]) = r[p] * (A[c]*g' + Bz[c]*z + Cc[c])
+// Channel-stationary like bn_apply_kernel: the five per-channel coefficients live in registers.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16* __restrict__ z, unsigned M, int C, int H, int W,
+                    const float* __restrict__ shift, const float* __restrict__ coeff, int act, float slope,
+                    const uint8_t* __restrict__ code, const float* __restrict__ lut,
+                    __nv_bfloat16* __restrict__ gz) {
+  const unsigned cv = C >> 3;
+  const unsigned lanes = blockDim.x / cv;
+  const unsigned c = (threadIdx.x % cv) << 3;
+  const unsigned lane = threadIdx.x / cv;
+  float sc[8], sh[8], bz[8], cc[8];
+  {
+    float mu[8], is[8], c1[8], c2[8];
     ldg8f(coeff + c, sc);
     ldg8f(shift + c, sh);
     ldg8f(coeff + C + c, mu);
     ldg8f(coeff + 2 * C + c, is);
     ldg8f(coeff + 3 * C + c, c1);
     ldg8f(coeff + 4 * C + c, c2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      bz[j] = -sc[j] * c2[j] * is[j];
+      cc[j] = sc[j] * (mu[j] * is[j] * c2[j] - c1[j]);
+    }
+  }
+  const bool need_split = s0.split || (s1.ptr && s1.split);
+  const unsigned stride = gridDim.x * lanes;
+  const unsigned HW = static_cast<unsigned>(H) * W;
+  for (unsigned p = blockIdx.x * lanes + lane; p < M; p += stride) {
+    long ps = 0;
+    if (need_split) {
+      const unsigned b = p / HW, rem = p - b * HW;
+      const unsigned h = rem / W, w = rem - h * W;
+      ps = split_index(b, h, w, H, W);
+    }
+    float g[8], zz[8];
+    load_grad(s0, s1, p, ps, c, g);
+    load8(z + static_cast<size_t>(p) * C + c, zz);
     const float r = code ? __ldg(lut + code[p]) : 1.f;
     float o[8];
 #pragma unroll
@@ -318,10 +344,9 @@ __global__ void bn_bwd_apply_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16*
       float gg = g[j];
       if (act == 1) gg = pre > 0.f ? gg : 0.f;
       else if (act == 2) gg = pre > 0.f ? gg : gg * slope;
-      const float zhat = (zz[j] - mu[j]) * is[j];
-      o[j] = r * sc[j] * (gg - c1[j] - zhat * c2[j]);
+      o[j] = r * (sc[j] * gg + bz[j] * zz[j] + cc[j]);
     }
-    store8(gz + p * C + c, o);
+    store8(gz + static_cast<size_t>(p) * C + c, o);
   }
 }
 
@@ -376,8 +401,9 @@ extern "C" int tg_bn_apply(const void* z, int B, int H, int W, int C, const floa
   TG_REQUIRE(!y_split || (H % 2 == 0 && W % 2 == 0), "tg_bn_apply: parity-split output needs even H, W");
   TG_REQUIRE(!(mask_split && y_split) || code, "tg_bn_apply: mask_split needs code");
   const long M = static_cast<long>(B) * H * W;
-  bn_apply_kernel<<<ew_grid(M * (C / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(z), M, C, H, W, scale, shift, act, slope, code,
+  TG_REQUIRE(C / 8 <= 256 && 256 % (C / 8) == 0 && M < (1L << 31), "tg_bn_apply: unsupported C=%d or too many pixels", C);
+  bn_apply_kernel<<<ew_grid(M * (C / 8), 512), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(z), static_cast<unsigned>(M), C, H, W, scale, shift, act, slope, code,
       reinterpret_cast<__nv_bfloat16*>(y_nhwc), reinterpret_cast<__nv_bfloat16*>(y_split), mask_split);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -426,14 +452,14 @@ extern "C" int tg_bn_bwd_apply(const tg_grad_src* g0, const tg_grad_src* g1, con
                                const uint8_t* code, const float* lut_dev, void* gz, void* stream) {
   using namespace tg;
   TG_REQUIRE(g0 && g0->ptr && z && shift && coeff && gz, "tg_bn_bwd_apply: null pointer");
-  TG_REQUIRE(C % 8 == 0, "tg_bn_bwd_apply: C must be a multiple of 8");
+  TG_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "tg_bn_bwd_apply: unsupported C=%d", C);
   TG_REQUIRE(!code || lut_dev, "tg_bn_bwd_apply: code needs a device LUT");
   const long M = static_cast<long>(B) * H * W;
   GradSrc s0 = to_src(*g0), s1;
   if (g1 && g1->ptr) s1 = to_src(*g1);
   else { s1.ptr = nullptr; s1.pix_stride = 0; s1.chan_off = 0; s1.split = 0; }
   bn_bwd_apply_kernel<<<ew_grid(M * (C / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      s0, s1, reinterpret_cast<const __nv_bfloat16*>(z), M, C, H, W, shift, coeff, act, slope, code, lut_dev,
+      s0, s1, reinterpret_cast<const __nv_bfloat16*>(z), static_cast<unsigned>(M), C, H, W, shift, coeff, act, slope, code, lut_dev,
       reinterpret_cast<__nv_bfloat16*>(gz));
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;

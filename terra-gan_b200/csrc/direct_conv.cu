@@ -466,6 +466,100 @@ conv3x3_c64_to1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, 
   if (threadIdx.x == 0 && partial_b != nullptr) partial_b[blockIdx.x] = s_b;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Data gradient of a 4x4 / stride-2 / pad-1 convolution with ONE input channel and 64 output channels
+// (Discriminator model[0], discriminator.py:17): out[b][h][w] = sum over the 2x2 taps of parity class
+// (h&1, w&1) of <g[b][(h>>1)+dh][(w>>1)+dw][:], W[tap][:]>. g is bf16 [B][Hg][Wg][64], optionally in
+// parity-split storage. Block = 8x32 tile of g pixels (16x64 outputs); the 10x34 halo tile of g is
+// staged in shared memory once; 8 lanes x 8 channels per g pixel produce its four outputs.
+// s_w[cls][pos][c]: weight of class cls at neighbourhood position pos = (dh+1)*3 + (dw+1), 0 if unused.
+// ------------------------------------------------------------------------------------------------
+constexpr int kS2H = 6;
+struct S2Taps { unsigned used[4]; int row[4][9]; };   // used[cls] bitmask over pos; row = weight row or -1
+
+__global__ void __launch_bounds__(256)
+conv_s2_c64_to1_kernel(const __nv_bfloat16* __restrict__ g, int g_split, int B, int Hg, int Wg,
+                       const float* __restrict__ wgt, S2Taps tp, float* __restrict__ out) {
+  __shared__ __align__(16) __nv_bfloat16 s_x[kS2H + 2][kT1W + 2][64];
+  __shared__ __align__(16) float s_w[4][9][64];
+  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  for (int i = threadIdx.x; i < 4 * 9 * 64; i += 256) {
+    const int c = i & 63, pos = (i >> 6) % 9, cls = i / (9 * 64);
+    const int r = tp.row[cls][pos];
+    s_w[cls][pos][c] = r >= 0 ? __ldg(wgt + r * 64 + c) : 0.f;
+  }
+  const int tiles_w = (Wg + kT1W - 1) / kT1W, tiles_h = (Hg + kS2H - 1) / kS2H;
+  const long total_tiles = static_cast<long>(B) * tiles_h * tiles_w;
+  const int H = 2 * Hg, W = 2 * Wg;
+  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tw = static_cast<int>(tile % tiles_w);
+    const int th = static_cast<int>((tile / tiles_w) % tiles_h);
+    const int b = static_cast<int>(tile / (static_cast<long>(tiles_w) * tiles_h));
+    const int h0 = th * kS2H, w0 = tw * kT1W;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (kS2H + 2) * (kT1W + 2) * 8; i += 256) {
+      const int v = i & 7, pix = i >> 3;
+      const int hr = pix / (kT1W + 2), hc = pix % (kT1W + 2);
+      const int h = h0 - 1 + hr, w = w0 - 1 + hc;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (h >= 0 && h < Hg && w >= 0 && w < Wg) {
+        const long gp = g_split ? dc_split_index(b, h, w, Hg, Wg) : (static_cast<long>(b) * Hg + h) * Wg + w;
+        val = *reinterpret_cast<const uint4*>(g + gp * 64 + v * 8);
+      }
+      *reinterpret_cast<uint4*>(&s_x[hr][hc][v * 8]) = val;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ps = 0; ps < (kS2H * kT1W) / 32; ++ps) {
+      const int q = ps * 32 + grp;
+      const int row = q / kT1W, col = q % kT1W;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int pos = 0; pos < 9; ++pos) {
+        float v[8];
+        t1_unpack(*reinterpret_cast<const uint4*>(&s_x[row + pos / 3][col + pos % 3][sub * 8]), v);
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls) {
+          if ((tp.used[cls] >> pos) & 1u) {
+            const float4 wa = *reinterpret_cast<const float4*>(&s_w[cls][pos][sub * 8]);
+            const float4 wb = *reinterpret_cast<const float4*>(&s_w[cls][pos][sub * 8 + 4]);
+            acc[cls] += v[0] * wa.x + v[1] * wa.y + v[2] * wa.z + v[3] * wa.w + v[4] * wb.x + v[5] * wb.y +
+                        v[6] * wb.z + v[7] * wb.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int cls = 0; cls < 4; ++cls) {
+        acc[cls] += __shfl_xor_sync(0xffffffffu, acc[cls], 4);
+        acc[cls] += __shfl_xor_sync(0xffffffffu, acc[cls], 2);
+        acc[cls] += __shfl_xor_sync(0xffffffffu, acc[cls], 1);
+      }
+      const int gh = h0 + row, gw = w0 + col;
+      if (sub == 0 && gh < Hg && gw < Wg) {
+        float* o = out + (static_cast<long>(b) * H + 2 * gh) * W + 2 * gw;
+        *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
+        *reinterpret_cast<float2*>(o + W) = make_float2(acc[2], acc[3]);
+      }
+    }
+  }
+}
+
+// class (P,Q) = 2*P+Q with taps inside the 3x3 neighbourhood -> S2Taps; false if the pattern does not fit
+static bool make_s2taps(S2Taps* tp, const int* cls_count, const int8_t* dh, const int8_t* dw) {
+  int t = 0;
+  for (int cls = 0; cls < 4; ++cls) {
+    tp->used[cls] = 0;
+    for (int i = 0; i < 9; ++i) tp->row[cls][i] = -1;
+    for (int i = 0; i < cls_count[cls]; ++i, ++t) {
+      if (dh[t] < -1 || dh[t] > 1 || dw[t] < -1 || dw[t] > 1) return false;
+      const int pos = (dh[t] + 1) * 3 + dw[t] + 1;
+      tp->used[cls] |= 1u << pos;
+      tp->row[cls][pos] = t;
+    }
+  }
+  return true;
+}
+
 static bool make_tap3x3(Tap3x3* tp, int ntaps, const int8_t* dh, const int8_t* dw) {
   if (ntaps != 9) return false;
   for (int i = 0; i < 9; ++i) tp->idx[i] = -1;
@@ -725,6 +819,16 @@ extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, 
     const int g3 = static_cast<int>(tiles < 4L * num_sms() ? tiles : 4L * num_sms());
     conv3x3_c64_to1_kernel<<<g3, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, wgt, tp, bias, mode, mask, xin, out, sig_out);
+    TG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  S2Taps s2;
+  if (ncls == 4 && C == 64 && mode == 0 && bias == nullptr && Ho == 2 * H && Wo == 2 * W &&
+      make_s2taps(&s2, cls_count, tap_dh, tap_dw)) {
+    const long tiles = static_cast<long>(B) * ((H + kS2H - 1) / kS2H) * ((W + kT1W - 1) / kT1W);
+    const int g3 = static_cast<int>(tiles < 4L * num_sms() ? tiles : 4L * num_sms());
+    conv_s2_c64_to1_kernel<<<g3, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), x_split, B, H, W, wgt, s2, out);
     TG_CHECK_CUDA(cudaGetLastError());
     return 0;
   }

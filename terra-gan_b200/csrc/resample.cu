@@ -47,40 +47,68 @@ __device__ __forceinline__ void bilinear_src(int o, int n, int& i0, int& i1, flo
 }
 
 // out[b][oh][ow][0:Cu] = bilinear_up2(up)[...] * mm ; out[...][Cu:Cu+Cs] = skip * mm
-__global__ void upsample_concat_kernel(const __nv_bfloat16* __restrict__ up, int B, int h, int w, int Cu,
-                                       const __nv_bfloat16* __restrict__ skip, int Cs,
-                                       const uint8_t* __restrict__ mm, __nv_bfloat16* __restrict__ out) {
-  const int H = 2 * h, W = 2 * w, C = Cu + Cs, cv = C >> 3;
-  const long total = static_cast<long>(B) * H * W * cv;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long p = i / cv;
-    const int c = static_cast<int>(i % cv) << 3;
-    float v[8];
-    if (mm != nullptr && mm[p] == 0) {
+// One thread = one 8-channel vector of a 2x2 output block: the four outputs of source pixel (i, j)
+// share its 3x3 neighbourhood (9 loads for 4 outputs instead of 16), index math is 32-bit and
+// amortised over the block. Exact PyTorch weights: 0.75/0.25 with edge clamping.
+__global__ void __launch_bounds__(256)
+upsample_concat_kernel(const __nv_bfloat16* __restrict__ up, int B, int h, int w, int Cu,
+                       const __nv_bfloat16* __restrict__ skip, int Cs, const uint8_t* __restrict__ mm,
+                       __nv_bfloat16* __restrict__ out) {
+  const int H = 2 * h, W = 2 * w, C = Cu + Cs;
+  const unsigned cv = C >> 3;
+  const unsigned total = static_cast<unsigned>(B) * h * w * cv;
+  const unsigned hw = static_cast<unsigned>(h) * w;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned blk = i / cv;
+    const int c = static_cast<int>(i - blk * cv) << 3;
+    const unsigned b = blk / hw, rem = blk - b * hw;
+    const int ii = static_cast<int>(rem / w);
+    const int jj = static_cast<int>(rem - ii * w);
+    const size_t obase = (static_cast<size_t>(b) * H + 2 * ii) * W + 2 * jj;   // pixel (2i, 2j)
+    const size_t opix[4] = {obase, obase + 1, obase + W, obase + W + 1};
+    bool on[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    } else if (c < Cu) {
-      const int ow = static_cast<int>(p % W);
-      const int oh = static_cast<int>((p / W) % H);
-      const int b = static_cast<int>(p / (static_cast<long>(W) * H));
-      int h0, h1, w0, w1;
-      float lh0, lh1, lw0, lw1;
-      bilinear_src(oh, h, h0, h1, lh0, lh1);
-      bilinear_src(ow, w, w0, w1, lw0, lw1);
-      const __nv_bfloat16* base = up + static_cast<long>(b) * h * w * Cu + c;
-      float a00[8], a01[8], a10[8], a11[8];
-      rs_load8(base + (static_cast<long>(h0) * w + w0) * Cu, a00);
-      rs_load8(base + (static_cast<long>(h0) * w + w1) * Cu, a01);
-      rs_load8(base + (static_cast<long>(h1) * w + w0) * Cu, a10);
-      rs_load8(base + (static_cast<long>(h1) * w + w1) * Cu, a11);
+    for (int q = 0; q < 4; ++q) on[q] = (mm == nullptr) || (mm[opix[q]] != 0);
+    float o[4][8];
+    if (c < Cu) {
+      if (on[0] || on[1] || on[2] || on[3]) {
+        const int im = ii > 0 ? ii - 1 : 0, ip = ii < h - 1 ? ii + 1 : h - 1;
+        const int jm = jj > 0 ? jj - 1 : 0, jp = jj < w - 1 ? jj + 1 : w - 1;
+        const __nv_bfloat16* base = up + static_cast<size_t>(b) * hw * Cu + c;
+        float t[3][3][8];
+        const int rr[3] = {im, ii, ip}, cc[3] = {jm, jj, jp};
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        v[j] = lh0 * (lw0 * a00[j] + lw1 * a01[j]) + lh1 * (lw0 * a10[j] + lw1 * a11[j]);
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) rs_load8(base + (static_cast<size_t>(rr[r]) * w + cc[q]) * Cu, t[r][q]);
+        // output row 2i uses rows (i-1, i) with (0.25, 0.75) [row 0: weight 1 on i], row 2i+1 uses (i, i+1)
+        // with (0.75, 0.25) [last row: weight 1 on i]; same along columns. Clamped neighbours make the edge
+        // cases fall out of the same formula: 0.25*x[i] + 0.75*x[i] = x[i].
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          // PyTorch evaluates lh0*(lw0*a00 + lw1*a01) + lh1*(lw0*a10 + lw1*a11) with (h0,h1) = (i-1,i) or (i,i+1)
+          const float r0a = 0.25f * t[0][0][e] + 0.75f * t[0][1][e], r0b = 0.75f * t[0][1][e] + 0.25f * t[0][2][e];
+          const float r1a = 0.25f * t[1][0][e] + 0.75f * t[1][1][e], r1b = 0.75f * t[1][1][e] + 0.25f * t[1][2][e];
+          const float r2a = 0.25f * t[2][0][e] + 0.75f * t[2][1][e], r2b = 0.75f * t[2][1][e] + 0.25f * t[2][2][e];
+          o[0][e] = 0.25f * r0a + 0.75f * r1a;
+          o[1][e] = 0.25f * r0b + 0.75f * r1b;
+          o[2][e] = 0.75f * r1a + 0.25f * r2a;
+          o[3][e] = 0.75f * r1b + 0.25f * r2b;
+        }
+      }
     } else {
-      rs_load8(skip + p * Cs + (c - Cu), v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (on[q]) rs_load8(skip + opix[q] * Cs + (c - Cu), o[q]);
     }
-    rs_store8(out + p * C + c, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!on[q]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[q][e] = 0.f;
+      }
+      rs_store8(out + opix[q] * C + c, o[q]);
+    }
   }
 }
 
@@ -88,15 +116,16 @@ __global__ void upsample_concat_kernel(const __nv_bfloat16* __restrict__ up, int
 // of weight * d_merged[b][oh][ow][c]   (d_merged already carries the merged-mask factor)
 __global__ void upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dm, int B, int h, int w, int Cu,
                                            int Ctot, __nv_bfloat16* __restrict__ dup) {
-  const int H = 2 * h, W = 2 * w, cv = Cu >> 3;
-  const long total = static_cast<long>(B) * h * w * cv;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long p = i / cv;
-    const int c = static_cast<int>(i % cv) << 3;
-    const int jj = static_cast<int>(p % w);
-    const int ii = static_cast<int>((p / w) % h);
-    const int b = static_cast<int>(p / (static_cast<long>(w) * h));
+  const int H = 2 * h, W = 2 * w;
+  const unsigned cv = Cu >> 3;
+  const unsigned total = static_cast<unsigned>(B) * h * w * cv;
+  const unsigned hw = static_cast<unsigned>(h) * w;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned p = i / cv;
+    const int c = static_cast<int>(i - p * cv) << 3;
+    const unsigned b = p / hw, rem = p - b * hw;
+    const int ii = static_cast<int>(rem / w);
+    const int jj = static_cast<int>(rem - ii * w);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -122,7 +151,7 @@ __global__ void upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dm,
         for (int j = 0; j < 8; ++j) acc[j] += wt * g[j];
       }
     }
-    rs_store8(dup + p * Cu + c, acc);
+    rs_store8(dup + static_cast<size_t>(p) * Cu + c, acc);
   }
 }
 
@@ -205,7 +234,8 @@ extern "C" int tg_upsample_concat(const void* up, int B, int h, int w, int Cu, c
   using namespace tg;
   TG_REQUIRE(up && out && Cu > 0 && Cu % 8 == 0 && Cs >= 0 && Cs % 8 == 0, "tg_upsample_concat: bad arguments");
   TG_REQUIRE(Cs == 0 || skip, "tg_upsample_concat: skip missing");
-  const long total = static_cast<long>(B) * 4 * h * w * ((Cu + Cs) / 8);
+  const long total = static_cast<long>(B) * h * w * ((Cu + Cs) / 8);     // one thread per 2x2 output block
+  TG_REQUIRE(total < (1L << 31), "tg_upsample_concat: tensor too large for 32-bit indexing");
   upsample_concat_kernel<<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(up), B, h, w, Cu, reinterpret_cast<const __nv_bfloat16*>(skip), Cs,
       merged_mask, reinterpret_cast<__nv_bfloat16*>(out));
