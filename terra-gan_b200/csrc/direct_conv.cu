@@ -613,12 +613,13 @@ conv3x3_c64_to1_bwd_data_kernel(const float* __restrict__ g, int B, int H, int W
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(wgt + tp.idx[t] * 64 + sub * 8 + j);
-  const long total = static_cast<long>(B) * H * W;
-  for (long p = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 3; p < total;
-       p += (static_cast<long>(gridDim.x) * blockDim.x) >> 3) {
-    const int w = static_cast<int>(p % W);
-    const int h = static_cast<int>((p / W) % H);
-    const float* gb = g + (p - static_cast<long>(h) * W - w);
+  const unsigned total = static_cast<unsigned>(B) * H * W;          // pixels; host checks < 2^31
+  const unsigned HW = static_cast<unsigned>(H) * W;
+  for (unsigned p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; p < total; p += (gridDim.x * blockDim.x) >> 3) {
+    const unsigned bimg = p / HW, rem = p - bimg * HW;
+    const int h = static_cast<int>(rem / W);
+    const int w = static_cast<int>(rem - h * W);
+    const float* gb = g + static_cast<size_t>(bimg) * HW;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -635,7 +636,7 @@ conv3x3_c64_to1_bwd_data_kernel(const float* __restrict__ g, int B, int H, int W
         for (int j = 0; j < 8; ++j) acc[j] += gv * wr[(dh + 1) * 3 + dw + 1][j];
       }
     }
-    *reinterpret_cast<uint4*>(dx + p * 64 + sub * 8) =
+    *reinterpret_cast<uint4*>(dx + static_cast<size_t>(p) * 64 + sub * 8) =
         make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
                    pack_bf16x2(acc[6], acc[7]));
   }

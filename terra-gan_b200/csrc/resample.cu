@@ -129,24 +129,29 @@ __global__ void upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dm,
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const __nv_bfloat16* base = dm + static_cast<long>(b) * H * W * Ctot + c;
-    for (int oh = 2 * ii - 1; oh <= 2 * ii + 2; ++oh) {
-      if (oh < 0 || oh >= H) continue;
-      int h0, h1;
-      float lh0, lh1;
-      bilinear_src(oh, h, h0, h1, lh0, lh1);
-      const float wh = (h0 == ii ? lh0 : 0.f) + (h1 == ii ? lh1 : 0.f);
-      if (wh == 0.f) continue;
-      for (int ow = 2 * jj - 1; ow <= 2 * jj + 2; ++ow) {
-        if (ow < 0 || ow >= W) continue;
-        int w0, w1;
-        float lw0, lw1;
-        bilinear_src(ow, w, w0, w1, lw0, lw1);
-        const float ww = (w0 == jj ? lw0 : 0.f) + (w1 == jj ? lw1 : 0.f);
-        if (ww == 0.f) continue;
+    const __nv_bfloat16* base = dm + static_cast<size_t>(b) * H * W * Ctot + c;
+    // transpose of PyTorch's bilinear x2: source pixel i feeds output rows 2i-1, 2i, 2i+1, 2i+2 with weights
+    // 0.25, 0.75, 0.75, 0.25; at the borders the clamped neighbour folds its weight onto the edge pixel.
+    float wh[4], ww[4];
+    wh[0] = ii > 0 ? 0.25f : 0.f;
+    wh[1] = ii > 0 ? 0.75f : 1.f;
+    wh[2] = ii < h - 1 ? 0.75f : 1.f;
+    wh[3] = ii < h - 1 ? 0.25f : 0.f;
+    ww[0] = jj > 0 ? 0.25f : 0.f;
+    ww[1] = jj > 0 ? 0.75f : 1.f;
+    ww[2] = jj < w - 1 ? 0.75f : 1.f;
+    ww[3] = jj < w - 1 ? 0.25f : 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int oh = 2 * ii - 1 + r;
+      if (wh[r] == 0.f) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ow = 2 * jj - 1 + q;
+        if (ww[q] == 0.f) continue;
         float g[8];
-        rs_load8(base + (static_cast<long>(oh) * W + ow) * Ctot, g);
-        const float wt = wh * ww;
+        rs_load8(base + (static_cast<size_t>(oh) * W + ow) * Ctot, g);
+        const float wt = wh[r] * ww[q];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += wt * g[j];
       }
