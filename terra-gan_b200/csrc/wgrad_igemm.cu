@@ -13,6 +13,8 @@
 // ever materialised. The pixel axis is split over CTAs (split-K); each share is written to an fp32
 // partial buffer and tg_wgrad_reduce sums the shares in a fixed order (deterministic) while
 // scattering into PyTorch's [Cout][Cin][kh][kw] gradient layout.
+#include <stdlib.h>
+
 #include "conv_igemm.cuh"
 #include "tg_common.cuh"
 #include "../../include/terragan_b200.h"
@@ -215,6 +217,20 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
   }
 }
 
+bool wgrad_halo_shape_ok(int Ho, int Wo, int num_taps, int N);       // wgrad_halo.cu
+int wgrad_halo_splits(int B, int Ho, int Wo, int C, int sms);
+bool wgrad_halo_eligible(const tg_wgrad_args* a);
+int wgrad_halo_launch(tg_wgrad_args* a, cudaStream_t st);
+
+static bool wgrad_halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TG_NO_HALO");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static void choose_kbox(int Ho, int Wo, int* Bt, int* Ht, int* Wt) {
   int wt = 1;
   while (wt * 2 <= Wo && wt * 2 <= 16) wt *= 2;
@@ -261,7 +277,11 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmG, const Wg
 
 extern "C" int64_t tg_wgrad_partial_floats(int B, int Ho, int Wo, int num_taps, int C, int N) {
   const int sms = tg::num_sms() > 0 ? tg::num_sms() : 148;
-  const int splits = tg::choose_splits(B, Ho, Wo, num_taps * (C / 64), N, sms);
+  int splits = tg::choose_splits(B, Ho, Wo, num_taps * (C / 64), N, sms);
+  if (tg::wgrad_halo_shape_ok(Ho, Wo, num_taps, N)) {
+    const int hs = tg::wgrad_halo_splits(B, Ho, Wo, C, sms);
+    if (hs > splits) splits = hs;
+  }
   return (int64_t)splits * num_taps * C * N;
 }
 
@@ -273,6 +293,7 @@ extern "C" int tg_wgrad_igemm(tg_wgrad_args* a, void* stream) {
   TG_REQUIRE(a->num_taps >= 1 && a->num_taps <= TG_MAX_TAPS, "tg_wgrad_igemm: bad num_taps");
   const int sms = num_sms();
   TG_REQUIRE(sms > 0, "tg_wgrad_igemm: no CUDA device");
+  if (wgrad_halo_enabled() && wgrad_halo_eligible(a)) return wgrad_halo_launch(a, reinterpret_cast<cudaStream_t>(stream));
   const int BN = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : 64;
   const int num_blk = a->num_taps * (a->C / 64);
 
