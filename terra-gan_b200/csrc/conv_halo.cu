@@ -24,7 +24,7 @@ namespace tg {
 constexpr int kHaloW = 8, kHaloH = 16;                       // output tile
 constexpr int kHaloRows = (kHaloW + 2) * (kHaloH + 2);       // 180 halo pixels
 constexpr int kHaloStageBytes = 23 * 1024;                   // 180 * 128 B rounded up to the swizzle period
-constexpr int kHaloStages = 3;
+constexpr int kHaloStages = 3;                               // upper bound; 2 when the weights are large
 constexpr int kHaloVec = 128;                                // max output channels of this kernel
 
 template <int BN>
@@ -33,21 +33,21 @@ struct HaloCfg {
 };
 
 struct HaloSmem {
-  static int total(int w_bytes, int kStoreCols = 64) {
-    return w_bytes + kHaloStages * kHaloStageBytes + (4 * 2 * kHaloVec + 3 * kHaloVec) * 4 + 8 * 32 * kStoreCols * 2 + 256 + 1024;
+  static int total(int w_bytes, int kStoreCols = 64, int stages = kHaloStages) {
+    return w_bytes + stages * kHaloStageBytes + (4 * 2 * kHaloVec + 3 * kHaloVec) * 4 + 8 * 32 * kStoreCols * 2 + 256 + 1024;
   }
 };
 
 template <int BN>
 __global__ void __launch_bounds__(384, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ ConvKParams p, int w_bytes) {
+                 const __grid_constant__ ConvKParams p, int w_bytes, int n_stages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* s_w = smem;                                       // [taps*cin_blocks] slabs of BN rows x 128 B
   uint8_t* s_a = smem + w_bytes;                             // kHaloStages halo tiles
-  float* s_stats = reinterpret_cast<float*>(s_a + kHaloStages * kHaloStageBytes);
+  float* s_stats = reinterpret_cast<float*>(s_a + n_stages * kHaloStageBytes);
   float* s_vec = s_stats + 4 * 2 * kHaloVec;
   constexpr int kSC = HaloCfg<BN>::kStoreCols;
   uint8_t* s_out = reinterpret_cast<uint8_t*>(s_vec + 3 * kHaloVec);   // 8 warps x 32 rows x kSC*2 B
@@ -118,7 +118,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[stage], kHaloRows * 128);
           tma_load_5d(s_a + stage * kHaloStageBytes, &tmA, &full_bar[stage], cb * 64, tw * kHaloW - 1,
                       th * kHaloH - 1, 0, tb);
-          if (++stage == kHaloStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -154,7 +154,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == kHaloStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -217,13 +217,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKParams& kp, int w_bytes, int grid,
                        cudaStream_t st) {
-  const int smem = HaloSmem::total(w_bytes, HaloCfg<BN>::kStoreCols);
+  const int stages = HaloSmem::total(w_bytes, HaloCfg<BN>::kStoreCols, 3) <= 227 * 1024 ? 3 : 2;
+  const int smem = HaloSmem::total(w_bytes, HaloCfg<BN>::kStoreCols, stages);
   static int attr_set = 0;
   if (attr_set < smem) {
     TG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = smem;
   }
-  conv_halo_kernel<BN><<<grid, 384, smem, st>>>(tmA, tmB, kp, w_bytes);
+  conv_halo_kernel<BN><<<grid, 384, smem, st>>>(tmA, tmB, kp, w_bytes, stages);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -237,7 +238,7 @@ bool conv_halo_eligible(const tg_conv_args* a) {
     if (a->tap_plane[t] != 0 || a->tap_dh[t] < -1 || a->tap_dh[t] > 1 || a->tap_dw[t] < -1 || a->tap_dw[t] > 1)
       return false;
   const long w_bytes = static_cast<long>(a->N) * a->Ktot * 2;
-  return HaloSmem::total(static_cast<int>(w_bytes)) <= 227 * 1024;
+  return HaloSmem::total(static_cast<int>(w_bytes), a->N == 128 ? 64 : 32, 2) <= 227 * 1024;
 }
 
 int conv_halo_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st) {

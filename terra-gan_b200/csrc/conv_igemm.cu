@@ -38,7 +38,7 @@ struct ConvSmem {
   static constexpr int kTiles = kStages * kStageBytes;
   static constexpr int kStatsFloats = 4 * 2 * 512;  // per epilogue warp (sum, sumsq) x channel
   static constexpr int kVecFloats = 3 * 512;        // bias / scale / shift
-  static constexpr int kStoreCols = (BN == 128) ? 64 : 32;                 // epilogue staging width
+  static constexpr int kStoreCols = (BN == 128 || BN == 192) ? 64 : 32;    // epilogue staging width
   static constexpr int kStageOutBytes = 8 * 32 * kStoreCols * 2;            // per-warp transposing tiles
   static constexpr int kTotal = kTiles + (kStatsFloats + kVecFloats) * 4 + kStageOutBytes + 256 + 1024;
 };
@@ -294,7 +294,7 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
                "tg_conv_igemm: sub %d weight slab out of range", s);
     TG_REQUIRE(sb.out_plane >= 0 && sb.out_plane < a->Po, "tg_conv_igemm: sub %d bad out_plane", s);
   }
-  const int BN = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : 64;
+  const int BN = (a->N % 256 == 0) ? 256 : (a->N == 192) ? 192 : (a->N % 128 == 0) ? 128 : 64;
 
   ConvKParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -367,6 +367,7 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   a->stats_rows_used = grid;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (BN == 256) return launch_conv<256>(a, tmA, tmB, kp, grid, st);
+  if (BN == 192) return launch_conv<192>(a, tmA, tmB, kp, grid, st);
   if (BN == 128) return launch_conv<128>(a, tmA, tmB, kp, grid, st);
   return launch_conv<64>(a, tmA, tmB, kp, grid, st);
 }
