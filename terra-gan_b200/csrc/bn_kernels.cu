@@ -213,44 +213,30 @@ __global__ void bn_bwd_reduce_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16
     const unsigned Mu = static_cast<unsigned>(M);
     const unsigned HW = static_cast<unsigned>(H) * W;
     const unsigned stride = gridDim.x * lanes;
-    for (unsigned p0 = blockIdx.x * lanes + my_lane; p0 < Mu; p0 += 2 * stride) {
-      const unsigned p1 = p0 + stride;
-      const bool two = p1 < Mu;
-      long ps0 = 0, ps1 = 0;
+    // one pixel per iteration: measured faster than 2- and 4-pixel unrolling (registers -> occupancy)
+    for (unsigned p = blockIdx.x * lanes + my_lane; p < Mu; p += stride) {
+      long ps = 0;
       if (need_split) {
-        unsigned b = p0 / HW, rem = p0 - b * HW;
-        unsigned h = rem / W, w = rem - h * W;
-        ps0 = split_index(b, h, w, H, W);
-        if (two) {
-          b = p1 / HW; rem = p1 - b * HW;
-          h = rem / W; w = rem - h * W;
-          ps1 = split_index(b, h, w, H, W);
-        }
+        const unsigned b = p / HW, rem = p - b * HW;
+        const unsigned h = rem / W, w = rem - h * W;
+        ps = split_index(b, h, w, H, W);
       }
-      float g0[8], z0[8], g1[8], z1[8];
-      load_grad(s0, s1, p0, ps0, c, g0);
-      load8(z + static_cast<size_t>(p0) * C + c, z0);
-      float r0 = code ? __ldg(lut + code[p0]) : 1.f, r1 = 0.f;
-      if (two) {
-        load_grad(s0, s1, p1, ps1, c, g1);
-        load8(z + static_cast<size_t>(p1) * C + c, z1);
-        r1 = code ? __ldg(lut + code[p1]) : 1.f;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g1[j] = z1[j] = 0.f;
-      }
+      float g[8], zz[8];
+      load_grad(s0, s1, p, ps, c, g);
+      load8(z + static_cast<size_t>(p) * C + c, zz);
+      const float r = code ? __ldg(lut + code[p]) : 1.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float pre0 = z0[j] * sc[j] + sh[j], pre1 = z1[j] * sc[j] + sh[j];
-        float ga = g0[j], gb = g1[j];
-        if (act == 1) { ga = pre0 > 0.f ? ga : 0.f; gb = pre1 > 0.f ? gb : 0.f; }
-        else if (act == 2) { ga = pre0 > 0.f ? ga : ga * slope; gb = pre1 > 0.f ? gb : gb * slope; }
-        acc[0][j] += ga + gb;
-        acc[1][j] += ga * z0[j] + gb * z1[j];
-        acc[2][j] += r0 * ga + r1 * gb;
-        acc[3][j] += r0 * z0[j] + r1 * z1[j];
+        const float pre = zz[j] * sc[j] + sh[j];
+        float gg = g[j];
+        if (act == 1) gg = pre > 0.f ? gg : 0.f;
+        else if (act == 2) gg = pre > 0.f ? gg : gg * slope;
+        acc[0][j] += gg;
+        acc[1][j] += gg * zz[j];
+        acc[2][j] += r * gg;
+        acc[3][j] += r * zz[j];
       }
-      acc[4][0] += r0 + r1;
+      acc[4][0] += r;
     }
 #pragma unroll
     for (int j = 1; j < 8; ++j) acc[4][j] = acc[4][0];

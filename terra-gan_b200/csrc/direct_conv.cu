@@ -615,30 +615,43 @@ conv3x3_c64_to1_bwd_data_kernel(const float* __restrict__ g, int B, int H, int W
     for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(wgt + tp.idx[t] * 64 + sub * 8 + j);
   const unsigned total = static_cast<unsigned>(B) * H * W;          // pixels; host checks < 2^31
   const unsigned HW = static_cast<unsigned>(H) * W;
-  for (unsigned p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; p < total; p += (gridDim.x * blockDim.x) >> 3) {
-    const unsigned bimg = p / HW, rem = p - bimg * HW;
-    const int h = static_cast<int>(rem / W);
-    const int w = static_cast<int>(rem - h * W);
-    const float* gb = g + static_cast<size_t>(bimg) * HW;
-    float acc[8];
+  const unsigned stride = (gridDim.x * blockDim.x) >> 3;
+  constexpr int U = 4;                                               // pixels in flight per thread
+  for (unsigned pbase = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; pbase < total; pbase += U * stride) {
+    float gv[U][9];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const unsigned p = pbase + u * stride;
+      const unsigned pc = p < total ? p : total - 1;
+      const unsigned bimg = pc / HW, rem = pc - bimg * HW;
+      const int h = static_cast<int>(rem / W);
+      const int w = static_cast<int>(rem - h * W);
+      const float* gb = g + static_cast<size_t>(bimg) * HW;
 #pragma unroll
-    for (int dh = -1; dh <= 1; ++dh) {
-      const int oh = h - dh;
-      if (oh < 0 || oh >= H) continue;
+      for (int dh = -1; dh <= 1; ++dh) {
 #pragma unroll
-      for (int dw = -1; dw <= 1; ++dw) {
-        const int ow = w - dw;
-        if (ow < 0 || ow >= W) continue;
-        const float gv = __ldg(gb + oh * W + ow);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += gv * wr[(dh + 1) * 3 + dw + 1][j];
+        for (int dw = -1; dw <= 1; ++dw) {
+          const int oh = h - dh, ow = w - dw;
+          const bool in = oh >= 0 && oh < H && ow >= 0 && ow < W;
+          gv[u][(dh + 1) * 3 + dw + 1] = in ? __ldg(gb + oh * W + ow) : 0.f;
+        }
       }
     }
-    *reinterpret_cast<uint4*>(dx + static_cast<size_t>(p) * 64 + sub * 8) =
-        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                   pack_bf16x2(acc[6], acc[7]));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned p = pbase + u * stride;
+      if (p >= total) break;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += gv[u][t] * wr[t][j];
+      *reinterpret_cast<uint4*>(dx + static_cast<size_t>(p) * 64 + sub * 8) =
+          make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                     pack_bf16x2(acc[6], acc[7]));
+    }
   }
 }
 
