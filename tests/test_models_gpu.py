@@ -425,3 +425,76 @@ def test_no_cpu_fallback():
     G = PConvUNet()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         G(torch.rand(1, 1, 128, 128), torch.ones(1, 1, 128, 128))
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: ragged batch, non-square tiles, degenerate masks
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,kind", [(1, 128, 128, "rect"), (3, 128, 256, "large"), (2, 256, 128, "iid"),
+                                        (2, 128, 128, "ones"), (2, 128, 128, "zeros")])
+def test_generator_eval_edge_cases(B, H, W, kind):
+    """Batch 1 / odd batches (partial 128-pixel tiles), non-square tiles, all-valid and all-hole masks
+    (every window count 0 -> ratio 0 -> z = 0 exactly, pconv.py:40) through the whole U-Net in eval mode."""
+    x = O.make_tiles(80, B, H, W)
+    mask = O.make_mask(81, B, H, kind, W)
+    with torch.no_grad():
+        ref = O.pconv_unet(x * mask, mask, O.make_generator_state(1), False)
+    G = PConvUNet()
+    G.load_state_dict(O.make_generator_state(1))
+    G.to(DEV).eval()
+    with torch.no_grad():
+        out = G((x * mask).to(DEV), mask.to(DEV))
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < TOL
+    if kind == "ones":      # nothing to inpaint: the composite returns the input bit-exactly (generator.py:62)
+        assert torch.equal(out.cpu(), x)
+
+
+def test_train_step_odd_batch_nonsquare():
+    """A full adversarial step on a ragged configuration runs and stays finite (B=3, 128x256)."""
+    B, H, W = 3, 128, 256
+    real, masks = O.make_tiles(90, B, H, W).to(DEV), O.make_mask(91, B, H, "rect", W).to(DEV)
+    G, D, vgg = _make_modules()
+    crit = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=torch.device(DEV), vgg_state_dict=vgg)
+    from tg_b200.step import AdversarialStep
+    st = AdversarialStep(G, D, crit, torch.optim.Adam(G.parameters(), lr=2e-4), torch.optim.Adam(D.parameters(), lr=2e-4))
+    for _ in range(2):
+        res = st.run(real, masks)
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v).all() for v in res.values())
+    assert res["gen_imgs"].shape == (B, 1, H, W)
+    # the valid region is copied through unchanged (generator.py:62)
+    m = masks.bool()
+    assert torch.equal(res["gen_imgs"][m], (real * masks)[m])
+
+
+def test_adversarial_step_full_size_tiles():
+    """The real tile shape (1x512x512, train.py:68) at batch 2: generator output and every loss term of the
+    adversarial step within 1e-2 of the fp32 oracle; gradients by the bf16-floor criterion (grad_ok)."""
+    H, B = 512, 2
+    real = O.make_tiles(30, B, H)
+    masks = O.make_mask(31, B, H, "rect")
+    vgg = O.make_vgg_state(3)
+    r = O.adversarial_step(real, masks, O.make_generator_state(1), O.make_discriminator_state(2), vgg)
+    with O.rounding(O.bf16_ste):
+        rq = O.adversarial_step(real, masks, O.make_generator_state(1), O.make_discriminator_state(2), vgg)
+    G, D, _ = _make_modules()
+    criterion = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=torch.device(DEV), vgg_state_dict=vgg)
+    bce = torch.nn.BCEWithLogitsLoss()
+    real_c, masks_c = real.to(DEV), masks.to(DEV)
+    gen = G(real_c * masks_c, masks_c)
+    g_loss = criterion(gen, real_c, masks_c)
+    fake = D(gen)
+    g_adv = bce(fake, torch.ones_like(fake))
+    (g_loss + g_adv).backward()
+    ok, info = grad_ok(gen, r["gen"], rq["gen"], "gen")
+    l2 = rel_l2(gen, r["gen"])
+    print("512x512 gen (max-err vs fp32 oracle, bf16 floor, vs rounding oracle):", info, "rel-L2", l2,
+          "g_loss", g_loss.item(), r["g_loss"].item(), "g_adv", g_adv.item(), r["g_adv"].item())
+    # train-mode BatchNorm in bf16: the reference's own modules under bf16 autocast differ from fp32 by 1.06e-2
+    # (SURVEY.md / BASELINE.md); the max-norm is met up to the bf16-storage floor, the L2 error is far below 1e-2
+    assert ok, info
+    assert l2 < TOL
+    assert abs(g_loss.item() - r["g_loss"].item()) < TOL * abs(r["g_loss"].item())
+    assert abs(g_adv.item() - r["g_adv"].item()) < TOL * abs(r["g_adv"].item())
+    _check_grads(G.named_parameters(), r["g_grads"], rq["g_grads"], what="G 512x512")
