@@ -36,8 +36,10 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 GFLOP_PER_TILE_STEP = 690.163          # algorithmic work of one adversarial step per tile
+GFLOP_PER_TILE = {"train": 690.163, "infer": 93.634, "hg": 573.118}
 TILE = 512
 METRIC = "gan_train_step_dsm_tiles_per_sec"
+METRICS = {"train": METRIC, "infer": "generator_inference_dsm_tiles_per_sec", "hg": "hg_finetune_step_dsm_tiles_per_sec"}
 
 
 def load_peaks():
@@ -145,7 +147,6 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from oracle import terra_oracle as O            # seeded weights / synthetic tiles only (host side)
     from tg_b200 import _lib, ops
     from tg_b200.ddp import BucketedGradReducer, broadcast_module_state
     from tg_b200.step import AdversarialStep
@@ -154,12 +155,12 @@ def run_ours(args):
     from mvp_gan.src.utils.losses import InpaintingLoss
 
     B = args.batch
+    torch.manual_seed(1)                               # random-init weights (default PyTorch init), same on every rank
     G, D = PConvUNet(), Discriminator()
-    G.load_state_dict(O.make_generator_state(1))
-    D.load_state_dict(O.make_discriminator_state(2))
     G.to(dev).train()
     D.to(dev).train()
-    criterion = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=dev, vgg_state_dict=O.make_vgg_state(3))
+    os.environ.setdefault("TERRA_VGG_SEED", "3")       # no network: seeded random VGG16[:16] weights
+    criterion = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=dev)
     opt_G = torch.optim.Adam(G.parameters(), lr=2e-4)
     opt_D = torch.optim.Adam(D.parameters(), lr=2e-4)
     reducer = None
@@ -167,6 +168,17 @@ def run_ours(args):
         broadcast_module_state([G, D])
         reducer = BucketedGradReducer([G, D])
     stepper = AdversarialStep(G, D, criterion, opt_G, opt_D, reducer, skip_discarded_d_wgrad=not args.ref_graph)
+    hg_stepper = None
+    if args.workload == "hg":          # BASELINE.json configs[4]: human-guided fine-tuning step (no discriminator)
+        from tg_b200.step import HumanGuidedStep
+        from mvp_gan.src.utils.losses import HumanGuidedLoss
+        cfg = {"training": {"loss_weights": {"perceptual": 0.1, "tv": 0.1, "boundary": 0.5},
+                            "modes": {"human_guided": {"human_feedback_weight": 0.3, "base_loss_weight": 0.7,
+                                                       "learning_rate": 1e-4}}}}
+        hg_crit = HumanGuidedLoss(cfg, device=dev)
+        hg_stepper = HumanGuidedStep(G, hg_crit, torch.optim.Adam(G.parameters(), lr=1e-4), reducer)
+    if args.workload == "infer":       # BASELINE.json configs[1]: generator inference (evaluate.py:47-50)
+        G.eval()
 
     # synthetic DSM tiles + rectangular hole masks, a different shard per rank; pinned host copies for e2e
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -201,15 +213,27 @@ def run_ours(args):
             ms = float(t.item())
         return ms / steps
 
+    human_d = (torch.rand((B, 1, TILE, TILE), generator=gen) < 0.1).float().to(dev)
+
+    def run_step(r, m):
+        if args.workload == "infer":
+            with torch.no_grad():
+                out = G(r * m, m)
+            return {"g_total_loss": out.mean(), "d_loss": out.mean()}
+        if args.workload == "hg":
+            o = hg_stepper.run(r, m, human_d)
+            return {"g_total_loss": o["loss"], "d_loss": o["loss"]}
+        return stepper.run(r, m)
+
     def step_resident():
-        stepper.run(real_d, mask_d)
+        run_step(real_d, mask_d)
 
     loss_host = torch.empty(2, pin_memory=True)
 
     def step_e2e():
         r = real_h.to(dev, non_blocking=True)
         m = mask_h.to(dev, non_blocking=True)
-        out = stepper.run(r, m)
+        out = run_step(r, m)
         loss_host.copy_(torch.stack([out["g_total_loss"], out["d_loss"]]), non_blocking=True)
         torch.cuda.current_stream().synchronize()     # the user reads the losses every step (train.py:222-225)
 
@@ -246,6 +270,14 @@ def run_ours(args):
     peak_tf, peak_bw, peak_src = load_peaks()
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
 
+    # DRAM traffic of the same kernel family from the committed ncu --set full capture (one B=64 train step)
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_tensorcore_step_summary.json")
+    if os.path.exists(tpath) and B == 64 and args.workload == "train":
+        t = json.load(open(tpath))
+        traffic = t["dram_gbytes"] * 1e9 / t["launches"]
+        traffic_note = (f"dram__bytes_read+write: {t['dram_gbytes']:.1f} GB over the {t['launches']} tensor-core launches of one "
+                        f"B=64 step (profiles/r01_ncu_full_tensorcore_kernels.csv); bytes per launch (mean)")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -260,24 +292,29 @@ def run_ours(args):
                "sample": "1 warm-up + 4 timed adversarial steps at batch 4 (oracle/terra_oracle.py: the reference's "
                          "own ATen/oneDNN ops, fp32, all host threads)"}
     line = {
-        "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRICS[args.workload], "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "adversarial train step (train.py:179-225): PConvUNet + Discriminator + InpaintingLoss "
-                               "(perceptual 0.1, tv 0.1, boundary 0.5) + Adam x2, 1x512x512 DSM tiles, rect hole masks",
+        "config": {"workload": {"train": "adversarial train step (train.py:179-225): PConvUNet + Discriminator + "
+                                         "InpaintingLoss (perceptual 0.1, tv 0.1, boundary 0.5) + Adam x2, 1x512x512 DSM "
+                                         "tiles, rect hole masks",
+                                "infer": "generator inference, eval mode, no_grad (evaluate.py:47-50), 1x512x512 DSM tiles",
+                                "hg": "human-guided fine-tune step (human_guided_trainer.py:101-153): PConvUNet + "
+                                      "HumanGuidedLoss (0.7/0.3, boundary 0.5) + Adam 1e-4, 1x512x512 DSM tiles"}[args.workload],
                    "tile": TILE, "batch_per_gpu": B, "global_batch": tiles_per_step,
                    "parallelism": f"dp{world}", "l2": "working set per step (>10 GB) exceeds the 126 MB L2",
                    "d_wgrad_in_g_step": "computed (reference graph)" if args.ref_graph else
                                         "skipped (zeroed unused by train.py:210; output-equivalent)",
-                   "step_gflop_per_tile": GFLOP_PER_TILE_STEP,
-                   "step_frac_of_bf16_peak": value / world * GFLOP_PER_TILE_STEP * 1e9 / (peak_tf * 1e12)},
+                   "step_gflop_per_tile": GFLOP_PER_TILE[args.workload],
+                   "step_frac_of_bf16_peak": value / world * GFLOP_PER_TILE[args.workload] * 1e9 / (peak_tf * 1e12)},
         "e2e": {"value": e2e, "unit": "tiles/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(real_h.numel() * 4 + mask_h.numel() * 4) * world,
                 "d2h_bytes_per_step": 8 * world},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel + wgrad_igemm_kernel (tcgen05 implicit GEMM)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                     "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
+                     "traffic_note": traffic_note,
                      "share_of_step": tc_ms / (ms_step * args.steps) if ms_step > 0 else None,
                      "by_kind": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0,
                                      "ms_per_step": v[1] / args.steps, "launches_per_step": v[2] / args.steps}
@@ -301,6 +338,9 @@ def main():
     ap.add_argument("--ref-graph", action="store_true",
                     help="also compute the discriminator weight gradients of the generator step (discarded by the reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "hg"],
+                    help="train: adversarial step (headline, configs[2]); infer: generator inference (configs[1]); "
+                         "hg: human-guided fine-tune step (configs[4])")
     ap.add_argument("--per-launch", default="", help="write a per-launch table of the tensor-core kernels to gpurun_out/<name>")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -4,7 +4,6 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "terra-gan_b200")); sys.path.insert(0, ROOT)
-from oracle import terra_oracle as O
 from tg_b200.step import AdversarialStep
 from mvp_gan.src.models.generator import PConvUNet
 from mvp_gan.src.models.discriminator import Discriminator
@@ -13,10 +12,11 @@ from mvp_gan.src.utils.losses import InpaintingLoss
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dev = torch.device("cuda:0")
+torch.manual_seed(1)
 G, D = PConvUNet(), Discriminator()
-G.load_state_dict(O.make_generator_state(1)); D.load_state_dict(O.make_discriminator_state(2))
 G.to(dev).train(); D.to(dev).train()
-crit = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=dev, vgg_state_dict=O.make_vgg_state(3))
+os.environ.setdefault("TERRA_VGG_SEED", "3")
+crit = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=dev)
 st = AdversarialStep(G, D, crit, torch.optim.Adam(G.parameters(), lr=2e-4), torch.optim.Adam(D.parameters(), lr=2e-4))
 gen = torch.Generator().manual_seed(0)
 real = torch.rand((B, 1, 512, 512), generator=gen).to(dev)
