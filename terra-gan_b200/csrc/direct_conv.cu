@@ -11,6 +11,7 @@
 //   final conv + sigmoid + `out*(1-mask) + x*mask`          mvp_gan/src/models/generator.py:56-62
 // and the autograd backward of each.
 #include "tg_common.cuh"
+#include "thin_mma.cuh"
 #include "../../include/terragan_b200.h"
 
 namespace tg {
@@ -25,7 +26,7 @@ __device__ __forceinline__ long dc_split_index(int b, int h, int w, int H, int W
 constexpr int kC1TW = 32, kC1TH = 4;
 
 template <int K, int S>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 conv_c1_fwd_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmask, int B, int H, int W, int pad,
                    const float* __restrict__ wgt /*[64][K*K]*/, const float* __restrict__ bias, int Ho, int Wo,
                    const uint8_t* __restrict__ code, const float* __restrict__ lut, int act, float slope,
@@ -34,6 +35,7 @@ conv_c1_fwd_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmas
   __shared__ float s_w[K * K][64];
   __shared__ float s_in[IH][IW + 1];
   __shared__ float s_stats[4][2][64];
+  __shared__ uint4 s_stage[4][32 * 8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 64 * K * K; i += 128) s_w[i % (K * K)][i / (K * K)] = wgt[i];
   for (int i = tid; i < 4 * 2 * 64; i += 128) (&s_stats[0][0][0])[i] = 0.f;
@@ -100,23 +102,37 @@ conv_c1_fwd_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmas
         s_stats[warp][1][half * 32 + lane] += q2;
       }
     }
-    if (valid) {
-      const long opix = out_split ? dc_split_index(b, ho, wo, Ho, Wo) : pix;
-      uint4* dst = reinterpret_cast<uint4*>(out + opix * 64);
+    // A thread owns one pixel row (128 B): storing it directly would touch 32 different lines per
+    // instruction. Rows go through a per-warp XOR-swizzled staging tile and are written back 4 rows
+    // (512 contiguous bytes in the plain layout) per instruction.
+    uint4* st = &s_stage[warp][0];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v[8];
+    for (int j = 0; j < 8; ++j) {
+      float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float t = acc[8 * j + q];
-          if (act == 1) t = fmaxf(t, 0.f);
-          else if (act == 2) t = t > 0.f ? t : t * slope;
-          v[q] = t;
+      for (int q = 0; q < 8; ++q) {
+        float t = acc[8 * j + q];
+        if (act == 1) t = fmaxf(t, 0.f);
+        else if (act == 2) t = t > 0.f ? t : t * slope;
+        v[q] = t;
+      }
+      st[lane * 8 + (j ^ (lane & 7))] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                   pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+    __syncwarp();
+    if (ho < Ho) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3), chunk = lane & 7;
+        const int wr = tw * kC1TW + row;            // tx == lane: row r of the warp is pixel (ho, tw*32 + r)
+        if (wr < Wo) {
+          const long opix = out_split ? dc_split_index(b, ho, wr, Ho, Wo)
+                                      : (static_cast<long>(b) * Ho + ho) * Wo + wr;
+          reinterpret_cast<uint4*>(out + opix * 64)[chunk] = st[row * 8 + (chunk ^ (row & 7))];
         }
-        dst[j] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                            pack_bf16x2(v[6], v[7]));
       }
     }
+    __syncwarp();
   }
   if (stats != nullptr) {
     __syncthreads();
@@ -133,7 +149,7 @@ conv_c1_fwd_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmas
 // partial[block][64][K*K (+1 for bias)]
 // ------------------------------------------------------------------------------------------------
 template <int K, int S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmask, int B, int H, int W, int pad,
                      const __nv_bfloat16* __restrict__ g /*[B][Ho][Wo][64]*/, int Ho, int Wo, int g_split,
                      float* __restrict__ partial) {
@@ -156,6 +172,19 @@ conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xm
     const int th = static_cast<int>((tile / tiles_w) % tiles_h);
     const int b = static_cast<int>(tile / (static_cast<long>(tiles_w) * tiles_h));
     const int ih0 = th * kC1TH * S - pad, iw0 = tw * kC1TW * S - pad;
+    // gradient rows of this warp's 16 pixels, fetched in batches of 4 one batch ahead of their use
+    // (one dependent 128-byte load per pixel left the kernel latency-bound at ~0.4 TB/s)
+    auto load_g = [&](int q) -> __nv_bfloat162 {
+      const int pt = warp * 16 + q;
+      const int ho = th * kC1TH + pt / kC1TW, wo = tw * kC1TW + pt % kC1TW;
+      if (ho >= Ho || wo >= Wo) return __floats2bfloat162_rn(0.f, 0.f);   // contributes nothing
+      const long p = (static_cast<long>(b) * Ho + ho) * Wo + wo;
+      const long gp = g_split ? dc_split_index(b, ho, wo, Ho, Wo) : p;
+      return *reinterpret_cast<const __nv_bfloat162*>(g + gp * 64 + 2 * lane);
+    };
+    __nv_bfloat162 gn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gn[j] = load_g(j);
     __syncthreads();
     for (int i = tid; i < IH * IW; i += 256) {
       const int r = i / IW, c = i % IW;
@@ -170,23 +199,29 @@ conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xm
     }
     __syncthreads();
 #pragma unroll 1
-    for (int q = 0; q < 16; ++q) {
-      const int pt = warp * 16 + q;               // pixel of the tile handled by this warp
-      const int tx = pt % kC1TW, ty = pt / kC1TW;
-      const int ho = th * kC1TH + ty, wo = tw * kC1TW + tx;
-      if (ho >= Ho || wo >= Wo) continue;         // warp-uniform
-      const long p = (static_cast<long>(b) * Ho + ho) * Wo + wo;
-      const long gp = g_split ? dc_split_index(b, ho, wo, Ho, Wo) : p;
-      const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g + gp * 64 + 2 * lane));
-      acc[T][0] += gf.x;
-      acc[T][1] += gf.y;
+    for (int qb = 0; qb < 4; ++qb) {
+      __nv_bfloat162 gc[4];
 #pragma unroll
-      for (int kh = 0; kh < K; ++kh) {
+      for (int j = 0; j < 4; ++j) gc[j] = gn[j];
+      if (qb < 3) {
 #pragma unroll
-        for (int kw = 0; kw < K; ++kw) {
-          const float xv = s_in[ty * S + kh][tx * S + kw];
-          acc[kh * K + kw][0] += xv * gf.x;
-          acc[kh * K + kw][1] += xv * gf.y;
+        for (int j = 0; j < 4; ++j) gn[j] = load_g(qb * 4 + 4 + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pt = warp * 16 + qb * 4 + j;
+        const int tx = pt % kC1TW, ty = pt / kC1TW;
+        const float2 gf = __bfloat1622float2(gc[j]);
+        acc[T][0] += gf.x;
+        acc[T][1] += gf.y;
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+#pragma unroll
+          for (int kw = 0; kw < K; ++kw) {
+            const float xv = s_in[ty * S + kh][tx * S + kw];
+            acc[kh * K + kw][0] += xv * gf.x;
+            acc[kh * K + kw][1] += xv * gf.y;
+          }
         }
       }
     }
@@ -781,6 +816,21 @@ extern "C" int tg_conv_c1_fwd(const float* x, const uint8_t* xmask, int B, int H
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (thin_mma_enabled() && (k == 3 || k == 4 || k == 7) && static_cast<long>(B) * Ho * Wo < (1L << 31) &&
+      (act != 2 || (slope >= 0.f && slope <= 1.f))) {
+    RowGemmParams rp{};
+    rp.src = x; rp.src_mask = xmask; rp.B = B; rp.H = H; rp.W = W; rp.Ho = Ho; rp.Wo = Wo;
+    rp.S = s; rp.pad = pad; rp.flip = 0;
+    rp.wgt = wgt; rp.w_sn = k * k; rp.w_st = 1;
+    for (int t = 0; t < k * k; ++t) rp.perm[t] = static_cast<int8_t>(t);
+    rp.bias = bias; rp.code = code; rp.lut = lut_dev; rp.act = act; rp.slope = slope;
+    rp.out = o; rp.out_split = out_split; rp.stats = stats;
+    rp.total = static_cast<unsigned>(static_cast<long>(B) * Ho * Wo);
+    int used = 0;
+    TG_REQUIRE(rowgemm_dispatch(k, rp, stats ? stats_rows_cap : 0, &used, st) == 0, "tg_conv_c1_fwd: launch failed");
+    if (stats) *stats_rows_used = used;
+    return 0;
+  }
   bool handled = false;
   TG_C1_DISPATCH(7, 2, (conv_c1_fwd_kernel<K, S><<<grid, 128, 0, st>>>(x, xmask, B, H, W, pad, wgt, bias, Ho, Wo, code, lut_dev, act, slope, o, out_split, stats)))
   TG_C1_DISPATCH(4, 2, (conv_c1_fwd_kernel<K, S><<<grid, 128, 0, st>>>(x, xmask, B, H, W, pad, wgt, bias, Ho, Wo, code, lut_dev, act, slope, o, out_split, stats)))
@@ -864,6 +914,20 @@ extern "C" int tg_conv_to1_bwd_data(const float* g, int B, int Ho, int Wo, const
   TG_REQUIRE(fill_taps(&taps, 1, &ntaps, tap_dh, tap_dw) > 0, "tg_conv_to1_bwd_data: bad tap table");
   const long total = static_cast<long>(B) * H * W * (C / 8);
   Tap3x3 tp;
+  if (thin_mma_enabled() && C == 64 && Ho == H && Wo == W && make_tap3x3(&tp, ntaps, tap_dh, tap_dw) &&
+      static_cast<long>(B) * H * W < (1L << 31)) {
+    // dx[p][c] = sum_pos g[p - d_pos] * w[tap(pos)][c]: a "flipped" 3x3 1 -> 64 convolution of g
+    RowGemmParams rp{};
+    rp.src = g; rp.B = B; rp.H = H; rp.W = W; rp.Ho = H; rp.Wo = W;
+    rp.S = 1; rp.pad = 1; rp.flip = 1;
+    rp.wgt = wgt; rp.w_sn = 1; rp.w_st = 64;
+    for (int t = 0; t < 9; ++t) rp.perm[t] = static_cast<int8_t>(tp.idx[t]);
+    rp.out = reinterpret_cast<__nv_bfloat16*>(dx);
+    rp.total = static_cast<unsigned>(static_cast<long>(B) * H * W);
+    TG_REQUIRE(rowgemm_dispatch(3, rp, 0, nullptr, reinterpret_cast<cudaStream_t>(stream)) == 0,
+               "tg_conv_to1_bwd_data: launch failed");
+    return 0;
+  }
   if (C == 64 && Ho == H && Wo == W && make_tap3x3(&tp, ntaps, tap_dh, tap_dw)) {
     conv3x3_c64_to1_bwd_data_kernel<<<dc_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         g, B, H, W, wgt, tp, reinterpret_cast<__nv_bfloat16*>(dx));

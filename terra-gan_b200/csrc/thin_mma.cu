@@ -1,0 +1,385 @@
+// thin_mma.cu — the 1 <-> 64 channel convolutions of the path on the tensor cores.
+//
+// A k x k convolution with ONE input channel and 64 output channels (PConv enc1 7x7/s2, Discriminator
+// model[0] 4x4/s2, VGG conv0 3x3 with its three identical input channels folded — reference pconv.py:27-43,
+// discriminator.py:17, losses.py:79-89) and the data gradient of the 64 -> 1 `final` convolution
+// (generator.py:56) are GEMMs with a tiny reduction dimension: [pixels] x [k*k] x [64]. On the CUDA cores they
+// cost k*k*64 FMAs per pixel and ran at 1/4 of what the 128-byte-per-pixel output write allows
+// (profiles/r01_*). Here every thread builds one im2col row of its pixel directly in shared memory in the
+// canonical SWIZZLE_128B K-major layout, and one elected thread issues K/16 tcgen05.mma (M=128 pixels, N=64);
+// the kernel is then bound by the bf16 output store (128 B per pixel).
+//
+// fp32 fidelity: the single-channel source and the weights are fp32 in the reference. Each is split into
+// bf16 hi + lo parts and the GEMM sums src_hi*w_hi + src_lo*w_hi + src_hi*w_lo (3*k*k reduction
+// elements, fp32 accumulate) — the dropped lo*lo term is ~2^-18 relative.
+#include "thin_mma.cuh"
+#include <cstdlib>
+#include <cstring>
+#include "tg_common.cuh"
+#include "../../include/terragan_b200.h"
+
+namespace tg {
+
+template <int K>
+struct RowGemmCfg {
+  static constexpr int T = K * K;
+  static constexpr int KE = 3 * T + 2;                   // src_hi*w_hi, src_lo*w_hi, src_hi*w_lo, 1*bias_hi, 1*bias_lo
+  static constexpr int KP = (KE + 15) / 16 * 16;         // reduction length issued to the tensor core
+  static constexpr int NKB = (KP + 63) / 64;             // 64-element (128-byte) swizzle blocks
+  static constexpr int NBUF = NKB == 1 ? 2 : 1;          // A tile + accumulator double-buffered when A is small
+  static constexpr int kABytes = NKB * 16384, kBBytes = NKB * 8192;
+  // NBUF == 2: the bf16 output tile is staged in the A buffer its MMA has just finished reading
+  static constexpr int kStageBytes = NBUF == 2 ? 0 : 4 * 4096;
+  static constexpr int kSmem = NBUF * kABytes + kBBytes + kStageBytes + 4 * 2 * 64 * 4 + 64 + 1024;
+};
+
+__device__ __forceinline__ uint32_t split_hi_lo(float v) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v, 0.f);                 // packed convert: not on the XU pipe
+  const float hf = __uint_as_float(static_cast<uint32_t>(__bfloat16_as_ushort(h.x)) << 16);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v - hf, 0.f);
+  return static_cast<uint32_t>(__bfloat16_as_ushort(h.x)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l.x)) << 16);
+}
+
+// Per CTA (128 threads, thread = pixel row = TMEM lane), software-pipelined over its tiles:
+//   build A(i) from the prefetched source values -> MMA(i) issued -> prefetch source of tile i+1 ->
+//   epilogue of tile i-1 (NBUF = 2) or i (NBUF = 1) while the loads / the MMA are in flight.
+// The bias rides in the GEMM (two extra reduction elements 1 x bias_hi, 1 x bias_lo).
+template <int K, bool MASKED>
+__global__ void __launch_bounds__(128)
+rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant__ CUtensorMap tm_out) {
+  using Cfg = RowGemmCfg<K>;
+  constexpr int T = Cfg::T, KP = Cfg::KP, NBUF = Cfg::NBUF;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_a = smem;
+  uint8_t* s_b = s_a + NBUF * Cfg::kABytes;
+  uint8_t* s_stage = s_b + Cfg::kBBytes;                    // only when NBUF == 1
+  float* s_stats = reinterpret_cast<float*>(s_stage + Cfg::kStageBytes);   // [4 warps][2][64]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_stats + 4 * 2 * 64);      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup: B operand (weights hi/hi/lo, bias hi/lo), barriers, TMEM ----
+  for (int i = tid; i < 64 * KP; i += 128) {
+    const int n = i / KP, e = i % KP;
+    unsigned short bits = 0;
+    if (e < 3 * T) {
+      const int part = e / T, t = e % T;
+      const uint32_t hl = split_hi_lo(__ldg(p.wgt + n * p.w_sn + p.perm[t] * p.w_st));
+      bits = static_cast<unsigned short>(part == 2 ? (hl >> 16) : (hl & 0xffffu));
+    } else if (e < 3 * T + 2 && p.bias != nullptr) {
+      const uint32_t hl = split_hi_lo(__ldg(p.bias + n));
+      bits = static_cast<unsigned short>(e == 3 * T ? (hl & 0xffffu) : (hl >> 16));
+    }
+    const int kb = e >> 6, ec = e & 63;
+    uint8_t* dst = s_b + kb * 8192 + (n >> 3) * 1024 + (n & 7) * 128 + (((ec >> 3) ^ (n & 7)) << 4) + (ec & 7) * 2;
+    *reinterpret_cast<unsigned short*>(dst) = bits;
+  }
+  for (int i = tid; i < 4 * 2 * 64; i += 128) s_stats[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_barrier_init();
+    if (!p.out_split) tma_prefetch_desc(&tm_out);
+  }
+  if (warp == 0) tmem_alloc<64 * NBUF>(tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t a_addr = smem_u32(s_a), b_addr = smem_u32(s_b);
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+  float* my_stats = s_stats + warp * 2 * 64;
+  const unsigned HoWo = static_cast<unsigned>(p.Ho) * p.Wo;
+  const unsigned tiles = (p.total + 127u) / 128u;
+
+  // raw source values of this thread's pixel of a tile
+  // (nothing may consume the loaded registers here: the loads stay in flight across the epilogue)
+  auto load_src = [&](unsigned tile, float (&v)[T], uint8_t (&mk)[MASKED ? T : 1]) {
+    const unsigned P = tile * 128u + tid;
+    const bool valid = P < p.total;
+    const unsigned Pc = valid ? P : p.total - 1;
+    const unsigned b = Pc / HoWo, rem = Pc - b * HoWo;
+    const int ho = static_cast<int>(rem / p.Wo), wo = static_cast<int>(rem - static_cast<unsigned>(ho) * p.Wo);
+    const int hb = p.flip ? ho * p.S + p.pad : ho * p.S - p.pad;
+    const int wb = p.flip ? wo * p.S + p.pad : wo * p.S - p.pad;
+    const float* sb = p.src + static_cast<size_t>(b) * p.H * p.W;
+    const uint8_t* mb = MASKED ? p.src_mask + static_cast<size_t>(b) * p.H * p.W : nullptr;
+#pragma unroll
+    for (int kh = 0; kh < K; ++kh) {
+      const int h = p.flip ? hb - kh : hb + kh;
+#pragma unroll
+      for (int kw = 0; kw < K; ++kw) {
+        const int w = p.flip ? wb - kw : wb + kw;
+        const bool in = valid && h >= 0 && h < p.H && w >= 0 && w < p.W && !(p.debug & 2);
+        const int off = in ? h * p.W + w : 0;
+        // out-of-image taps read element 0 of the image and are zeroed through the mask byte / `inb` bit below
+        v[kh * K + kw] = __ldg(sb + off);
+        if (MASKED) mk[kh * K + kw] = in ? __ldg(mb + off) : static_cast<uint8_t>(0);
+      }
+    }
+  };
+  // which taps of this thread's pixel fall inside the image (bit t), recomputed at build time: pure ALU
+  auto inside_bits = [&](unsigned tile) -> unsigned long long {
+    const unsigned P = tile * 128u + tid;
+    if (P >= p.total || (p.debug & 2)) return 0ull;
+    const unsigned b = P / HoWo, rem = P - b * HoWo;
+    const int ho = static_cast<int>(rem / p.Wo), wo = static_cast<int>(rem - static_cast<unsigned>(ho) * p.Wo);
+    const int hb = p.flip ? ho * p.S + p.pad : ho * p.S - p.pad;
+    const int wb = p.flip ? wo * p.S + p.pad : wo * p.S - p.pad;
+    unsigned hbits = 0, wbits = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int h = p.flip ? hb - k : hb + k, w = p.flip ? wb - k : wb + k;
+      hbits |= (h >= 0 && h < p.H) ? (1u << k) : 0u;
+      wbits |= (w >= 0 && w < p.W) ? (1u << k) : 0u;
+    }
+    unsigned long long bits = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if ((hbits >> k) & 1u) bits |= static_cast<unsigned long long>(wbits) << (k * K);
+    return bits;
+  };
+
+  // L2 prefetch of the source rows of a tile a few iterations ahead: its first touch is a DRAM read that queues
+  // behind this kernel's own write stream (measured: 2x the kernel time when left on the critical path)
+  auto prefetch_src = [&](unsigned tile) {
+    const unsigned P = tile * 128u + tid;
+    if (P >= p.total) return;
+    const unsigned b = P / HoWo, rem = P - b * HoWo;
+    const int ho = static_cast<int>(rem / p.Wo), wo = static_cast<int>(rem - static_cast<unsigned>(ho) * p.Wo);
+    const int hb = p.flip ? ho * p.S + p.pad : ho * p.S - p.pad;
+    const int w = min(max(wo * p.S, 0), p.W - 1);
+    const size_t img = static_cast<size_t>(b) * p.H * p.W;
+#pragma unroll
+    for (int kh = 0; kh < K; ++kh) {
+      const int h = p.flip ? hb - kh : hb + kh;
+      if (h >= 0 && h < p.H) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src + img + h * p.W + w));
+        if (p.src_mask != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src_mask + img + h * p.W + w));
+      }
+    }
+  };
+
+  auto build_a = [&](uint8_t* a_tile, const float (&v)[T], const uint8_t (&mk)[MASKED ? T : 1], unsigned long long inb,
+                     bool valid) {
+    uint32_t hl[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const bool keep = MASKED ? (mk[t] != 0) : (((inb >> t) & 1ull) != 0);
+      hl[t] = split_hi_lo(keep ? v[t] : 0.f);
+    }
+    const uint32_t one = valid ? 0x3f80u : 0u;             // bf16 1.0: switches the bias on for real pixels
+    uint8_t* rowp = a_tile + (tid >> 3) * 1024 + (tid & 7) * 128;
+#pragma unroll
+    for (int j = 0; j < KP / 8; ++j) {
+      uint32_t wd[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t two[2];
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+          const int e = j * 8 + q * 2 + z;       // compile-time
+          uint32_t x16 = 0;
+          if (e < T) x16 = hl[e] & 0xffffu;
+          else if (e < 2 * T) x16 = hl[e - T] >> 16;
+          else if (e < 3 * T) x16 = hl[e - 2 * T] & 0xffffu;
+          else if (e < 3 * T + 2) x16 = one;
+          two[z] = x16;
+        }
+        wd[q] = two[0] | (two[1] << 16);
+      }
+      *reinterpret_cast<uint4*>(rowp + (j >> 3) * 16384 + ((((j & 7) ^ (tid & 7))) << 4)) =
+          make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+  };
+
+  // thread = pixel row = TMEM lane: ratio, stats, activation, bf16; the warp's 32 x 128 B sub-tile is staged in
+  // SWIZZLE_128B order and leaves through one TMA tensor store (plain layout) or 4-rows-per-instruction stores
+  auto epilogue = [&](unsigned tile, uint32_t t_acc, uint8_t* stage_tile) {
+    const unsigned P = tile * 128u + tid;
+    const bool valid = P < p.total;
+    uint4* st = reinterpret_cast<uint4*>(stage_tile) + warp * 256;
+    float rs = 1.f;
+    if (p.code != nullptr && valid) rs = __ldg(p.lut + p.code[P]);
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t raw[32];
+      tmem_ld_32x32(t_acc + (static_cast<uint32_t>(warp * 32) << 16) + ch * 32, raw);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (p.code != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= rs;
+      }
+      if (p.stats != nullptr) {
+        float sm[32], sq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          sm[j] = v[j];
+          sq[j] = v[j] * v[j];
+        }
+        const float csum = warp_transpose_sum32(sm);
+        const float csq = warp_transpose_sum32(sq);
+        my_stats[ch * 32 + lane] += csum;
+        my_stats[64 + ch * 32 + lane] += csq;
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);   // slope in [0, 1)
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st[lane * 8 + ((ch * 4 + j) ^ (lane & 7))] =
+            make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+    }
+    if (!p.out_split) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && !(p.debug & 1)) {
+        tma_store_2d(&tm_out, st, 0, static_cast<int>(tile * 128u + warp * 32));   // rows >= total are clipped
+        bulk_commit_group();
+      }
+    } else {
+      const unsigned Pc = valid ? P : p.total - 1;
+      const unsigned b = Pc / HoWo, rem = Pc - b * HoWo;
+      const unsigned ho = rem / p.Wo, wo = rem - ho * p.Wo;
+      const unsigned oidx = ((b * 4u + 2u * (ho & 1) + (wo & 1)) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1);
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3), chunk = lane & 7;
+        const unsigned ridx = __shfl_sync(0xffffffffu, oidx, row);
+        if ((vmask >> row) & 1u)
+          reinterpret_cast<uint4*>(p.out + static_cast<size_t>(ridx) * 64)[chunk] = st[row * 8 + (chunk ^ (row & 7))];
+      }
+      __syncwarp();
+    }
+  };
+
+  float v[T];
+  uint8_t mk[MASKED ? T : 1];
+  for (int d = 1; d < 4; ++d)
+    if (blockIdx.x + d * gridDim.x < tiles) prefetch_src(blockIdx.x + d * gridDim.x);
+  if (blockIdx.x < tiles) load_src(blockIdx.x, v, mk);
+  unsigned prev_tile = 0;
+  int it = 0;
+  for (unsigned tile = blockIdx.x;; tile += gridDim.x, ++it) {
+    const bool have = tile < tiles;          // CTA-uniform
+    const int buf = it % NBUF;
+    if (NBUF == 2) {
+      // this warp's rows of A[buf] were the staging area of tile it-2: its TMA store must have read them
+      if (lane == 0) bulk_wait_read_all();
+      __syncwarp();
+    }
+    if (have) build_a(s_a + buf * Cfg::kABytes, v, mk, MASKED ? 0ull : inside_bits(tile), tile * 128u + tid < p.total);
+    fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
+    tc_fence_before();            // earlier tcgen05.ld of this accumulator are complete before it is overwritten
+    __syncthreads();
+    if (have && tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < KP / 16; ++ks) {
+        const uint32_t off_a = buf * Cfg::kABytes + (ks >> 2) * 16384 + (ks & 3) * 32;
+        const uint32_t off_b = (ks >> 2) * 8192 + (ks & 3) * 32;
+        umma_bf16(tmem + buf * 64, make_smem_desc(a_addr + off_a, 16, 1024), make_smem_desc(b_addr + off_b, 16, 1024),
+                  idesc, ks ? 1u : 0u);
+      }
+      umma_commit(&mbar[buf]);
+    }
+    if (have && tile + gridDim.x < tiles) load_src(tile + gridDim.x, v, mk);
+    if (tile + 4 * gridDim.x < tiles && !(p.debug & 4)) prefetch_src(tile + 4 * gridDim.x);
+    if (NBUF == 1) {
+      if (have) {
+        mbar_wait(&mbar[0], it & 1);
+        tc_fence_after();
+        if (lane == 0) bulk_wait_read_all();     // previous tile's store has left the staging area
+        __syncwarp();
+        epilogue(tile, tmem, s_stage);
+      }
+    } else {
+      if (it > 0) {
+        const int pb = (it - 1) % NBUF;
+        mbar_wait(&mbar[pb], ((it - 1) / NBUF) & 1);
+        tc_fence_after();
+        epilogue(prev_tile, tmem + pb * 64, s_a + pb * Cfg::kABytes);
+      }
+      prev_tile = tile;
+    }
+    if (!have) break;
+  }
+
+  if (lane == 0) bulk_wait_read_all();
+  tc_fence_before();
+  __syncthreads();
+  if (p.stats != nullptr) {
+    const int c = tid & 63, which = tid >> 6;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += s_stats[q * 128 + which * 64 + c];
+    p.stats[(static_cast<size_t>(blockIdx.x) * 2 + which) * 64 + c] = s;
+  }
+  if (warp == 0) tmem_dealloc<64 * NBUF>(tmem);
+}
+
+template <int K, bool MASKED>
+static int rowgemm_launch(const RowGemmParams& p, int grid_cap, int* grid_used, cudaStream_t st) {
+  using Cfg = RowGemmCfg<K>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TG_CHECK_CUDA(cudaFuncSetAttribute(rowgemm64_kernel<K, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr_set = true;
+  }
+  CUtensorMap tm_out;
+  memset(&tm_out, 0, sizeof(tm_out));
+  if (!p.out_split) {
+    const uint64_t dims[2] = {64, p.total};
+    const uint64_t str[1] = {128};
+    const uint32_t box[2] = {64, 32};
+    if (make_tmap_bf16(&tm_out, p.out, 2, dims, str, box) != 0) return -3;
+  }
+  int per_sm = (220 * 1024) / Cfg::kSmem;
+  if (per_sm > 5) per_sm = 5;
+  const long tiles = (static_cast<long>(p.total) + 127) / 128;
+  long grid = static_cast<long>(num_sms()) * per_sm;
+  if (grid > tiles) grid = tiles;
+  if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
+  if (grid < 1) grid = 1;
+  if (grid_used) *grid_used = static_cast<int>(grid);
+  RowGemmParams q = p;
+  {
+    const char* e = getenv("TG_THIN_DEBUG");
+    q.debug = e ? atoi(e) : 0;
+  }
+  rowgemm64_kernel<K, MASKED><<<static_cast<int>(grid), 128, Cfg::kSmem, st>>>(q, tm_out);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+bool thin_mma_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TG_NO_THIN_MMA");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// entry used by direct_conv.cu
+int rowgemm_dispatch(int k, const RowGemmParams& p, int grid_cap, int* grid_used, cudaStream_t st) {
+  const bool m = p.src_mask != nullptr;
+  if (k == 3) return m ? rowgemm_launch<3, true>(p, grid_cap, grid_used, st) : rowgemm_launch<3, false>(p, grid_cap, grid_used, st);
+  if (k == 4) return m ? rowgemm_launch<4, true>(p, grid_cap, grid_used, st) : rowgemm_launch<4, false>(p, grid_cap, grid_used, st);
+  if (k == 7) return m ? rowgemm_launch<7, true>(p, grid_cap, grid_used, st) : rowgemm_launch<7, false>(p, grid_cap, grid_used, st);
+  return -1;
+}
+
+}  // namespace tg
