@@ -852,6 +852,24 @@ extern "C" int tg_conv_c1_wgrad(const float* x, const uint8_t* xmask, int B, int
   TG_REQUIRE(grid >= 1, "tg_conv_c1_wgrad: rows_cap must be >= 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* gg = reinterpret_cast<const __nv_bfloat16*>(g);
+  if (thin_mma_enabled() && (k == 3 || k == 4 || k == 7) && static_cast<long>(B) * Ho * Wo < (1L << 31) &&
+      (!g_split || (Ho % 2 == 0 && Wo % 2 == 0))) {
+    const int T = k * k;
+    TapWgradParams tp{};
+    tp.src = x; tp.src_mask = xmask; tp.B = B; tp.H = H; tp.W = W; tp.Ho = Ho; tp.Wo = Wo;
+    tp.S = s; tp.pad = pad; tp.flip = 0; tp.y_split = g_split;
+    tp.total = static_cast<unsigned>(static_cast<long>(B) * Ho * Wo);
+    tp.partial = partial; tp.partial_c = nullptr; tp.center = -1;
+    const int cap = static_cast<int>(static_cast<long>(rows_cap) * (T + 1) / (2 * T + 1));   // same buffer, 2T+1 rows per CTA
+    TG_REQUIRE(cap >= 1, "tg_conv_c1_wgrad: rows_cap too small");
+    int used = 0;
+    TG_REQUIRE(tapwgrad_dispatch(k, tp, g, cap, &used, st) == 0, "tg_conv_c1_wgrad: launch failed");
+    int8_t perm[49];
+    for (int t = 0; t < T; ++t) perm[t] = static_cast<int8_t>(t);
+    TG_REQUIRE(tapwgrad_reduce(k, partial, nullptr, used, dw, T, 1, perm, db, 1, accumulate, st) == 0,
+               "tg_conv_c1_wgrad: reduce failed");
+    return 0;
+  }
   bool handled = false;
   TG_C1_DISPATCH(7, 2, (conv_c1_wgrad_kernel<K, S><<<grid, 256, 0, st>>>(x, xmask, B, H, W, pad, gg, Ho, Wo, g_split, partial)))
   TG_C1_DISPATCH(4, 2, (conv_c1_wgrad_kernel<K, S><<<grid, 256, 0, st>>>(x, xmask, B, H, W, pad, gg, Ho, Wo, g_split, partial)))
@@ -957,6 +975,22 @@ extern "C" int tg_conv_to1_wgrad(const void* x, int B, int H, int W, int C, cons
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
   Tap3x3 tp;
+  if (thin_mma_enabled() && C == 64 && Ho == H && Wo == W && make_tap3x3(&tp, ntaps, tap_dh, tap_dw) &&
+      static_cast<long>(B) * H * W < (1L << 31) && rows_cap * 9 / 19 >= 1) {
+    // dw[pos][c] = sum_n g[n - d_pos] * x[n][c]: the "flipped" 3x3 taps of g against the activation tile
+    TapWgradParams wp{};
+    wp.src = g; wp.B = B; wp.H = H; wp.W = W; wp.Ho = H; wp.Wo = W;
+    wp.S = 1; wp.pad = 1; wp.flip = 1; wp.y_split = 0;
+    wp.total = static_cast<unsigned>(static_cast<long>(B) * H * W);
+    wp.partial = partial; wp.partial_c = partial_b; wp.center = 4;
+    int used = 0;
+    TG_REQUIRE(tapwgrad_dispatch(3, wp, x, rows_cap * 9 / 19, &used, st) == 0, "tg_conv_to1_wgrad: launch failed");
+    int8_t perm[9];
+    for (int t = 0; t < 9; ++t) perm[t] = static_cast<int8_t>(tp.idx[t]);
+    TG_REQUIRE(tapwgrad_reduce(3, partial, partial_b, used, dw, 9, 1, perm, db, partial_b ? 2 : 0, accumulate, st) == 0,
+               "tg_conv_to1_wgrad: reduce failed");
+    return 0;
+  }
   if (C == 64 && Ho == H && Wo == W && make_tap3x3(&tp, ntaps, tap_dh, tap_dw)) {
     const long tiles = static_cast<long>(B) * ((H + kT1H - 1) / kT1H) * ((W + kT1W - 1) / kT1W);
     int g3 = static_cast<int>(tiles < 4L * num_sms() ? tiles : 4L * num_sms());

@@ -364,6 +364,288 @@ static int rowgemm_launch(const RowGemmParams& p, int grid_cap, int* grid_used, 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient:  D[row][c] += sum over the 128 pixels of a tile of A[row][pixel] * Y[pixel][c]
+//   A (thread-built, K-major over pixels): rows t / T+t = bf16 hi / lo part of the tap-t source value of each
+//   pixel, row 2T = 1 (bias gradient); Y tile [128 pixels][64] arrives by TMA and is the MN-major B operand.
+// One accumulator (128 lanes x 64 columns) lives in TMEM for the whole kernel and is read once at the end.
+// warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator, warps 4-7 and 8-11: two groups of A builders
+// taking alternate tiles (one tile's source-load latency per iteration is otherwise exposed); warps 4-7 read out.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTwStages = 3;
+constexpr int kTwSmem = kTwStages * (32768 + 16384) + 256 + 1024;
+
+template <int K, bool MASKED>
+__global__ void __launch_bounds__(384, 1)
+tapwgrad_kernel(const __grid_constant__ TapWgradParams p, const __grid_constant__ CUtensorMap tm_y) {
+  constexpr int T = K * K, NR = 2 * T + 1;
+  static_assert(NR <= 128, "tap rows must fit the 128 accumulator lanes");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_a = smem;                                   // [stage][2 k-blocks][128 rows][128 B]
+  uint8_t* s_y = s_a + kTwStages * 32768;                // [stage][128 pixels][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_y + kTwStages * 16384);
+  uint64_t* full_y = bars;
+  uint64_t* full_a = bars + kTwStages;
+  uint64_t* empty = bars + 2 * kTwStages;
+  uint64_t* done = bars + 3 * kTwStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kTwStages + 1);
+  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < kTwStages * 32768 / 16; i += 384) reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    for (int i = 0; i < kTwStages; ++i) {
+      mbar_init(&full_y[i], 1);
+      mbar_init(&full_a[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_y);
+  }
+  if (warp == 2) tmem_alloc<64>(tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const unsigned tiles = (p.total + 127u) / 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_y[stage], 16384);
+        tma_load_2d(s_y + stage * 16384, &tm_y, &full_y[stage], 0, static_cast<int>(tile * 128u));   // tail rows: zero fill
+        if (++stage == kTwStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);     // A K-major, B (= Y) MN-major
+      const uint32_t a_addr = smem_u32(s_a), y_addr = smem_u32(s_y);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&full_y[stage], phase);
+        mbar_wait(&full_a[stage], phase);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t da = make_smem_desc(a_addr + stage * 32768 + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc(y_addr + stage * 16384 + ks * 2048, 16384, 1024);
+          umma_bf16(tmem, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+        }
+        first = false;
+        umma_commit(&empty[stage]);
+        if (++stage == kTwStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(done);
+    }
+  } else if (warp >= 4) {
+    const int j = (tid - 128) & 127;             // pixel of the tile (= TMEM lane at read-out for group 0)
+    const int grp = (tid - 128) >> 7;            // builder group: tiles i = grp, grp + 2, ...
+    const unsigned HoWo = static_cast<unsigned>(p.Ho) * p.Wo;
+    struct Geo { int hb, wb; size_t img; bool valid; };
+    auto geo = [&](unsigned tile) -> Geo {
+      const unsigned P = tile * 128u + j;
+      Geo g;
+      g.valid = P < p.total;
+      const unsigned Pc = g.valid ? P : p.total - 1;
+      const unsigned b = Pc / HoWo, rem = Pc - b * HoWo;
+      int ho, wo;
+      if (p.y_split) {
+        const unsigned plane_sz = HoWo >> 2, w2n = static_cast<unsigned>(p.Wo) >> 1;
+        const unsigned plane = rem / plane_sz, r2 = rem - plane * plane_sz;
+        const unsigned h2 = r2 / w2n, w2 = r2 - h2 * w2n;
+        ho = static_cast<int>(2 * h2 + (plane >> 1));
+        wo = static_cast<int>(2 * w2 + (plane & 1));
+      } else {
+        ho = static_cast<int>(rem / p.Wo);
+        wo = static_cast<int>(rem - static_cast<unsigned>(ho) * p.Wo);
+      }
+      g.hb = p.flip ? ho * p.S + p.pad : ho * p.S - p.pad;
+      g.wb = p.flip ? wo * p.S + p.pad : wo * p.S - p.pad;
+      g.img = static_cast<size_t>(b) * p.H * p.W;
+      return g;
+    };
+    // loads only; nothing consumes the registers before the next build (they stay in flight)
+    auto load_src = [&](const Geo& g, float (&v)[T], uint8_t (&mk)[MASKED ? T : 1]) {
+#pragma unroll
+      for (int kh = 0; kh < K; ++kh) {
+        const int h = p.flip ? g.hb - kh : g.hb + kh;
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          const int w = p.flip ? g.wb - kw : g.wb + kw;
+          const bool in = g.valid && h >= 0 && h < p.H && w >= 0 && w < p.W;
+          const int off = in ? h * p.W + w : 0;
+          v[kh * K + kw] = __ldg(p.src + g.img + off);
+          if (MASKED) mk[kh * K + kw] = in ? __ldg(p.src_mask + g.img + off) : static_cast<uint8_t>(0);
+        }
+      }
+    };
+    auto inside_bits = [&](const Geo& g) -> unsigned long long {
+      if (!g.valid) return 0ull;
+      unsigned hbits = 0, wbits = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int h = p.flip ? g.hb - k : g.hb + k, w = p.flip ? g.wb - k : g.wb + k;
+        hbits |= (h >= 0 && h < p.H) ? (1u << k) : 0u;
+        wbits |= (w >= 0 && w < p.W) ? (1u << k) : 0u;
+      }
+      unsigned long long bits = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if ((hbits >> k) & 1u) bits |= static_cast<unsigned long long>(wbits) << (k * K);
+      return bits;
+    };
+
+    float v[T];
+    uint8_t mk[MASKED ? T : 1];
+    float csum = 0.f;
+    const unsigned my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    Geo g = geo(blockIdx.x + grp * gridDim.x);
+    if (static_cast<unsigned>(grp) < my_tiles) load_src(g, v, mk);
+    // element (row m, pixel j): k-block j>>6, 16-byte chunk (j&63)>>3 swizzled by the row, 2-byte slot j&7
+    const uint32_t col_off = (j >> 6) * 16384 + (j & 7) * 2;
+    const uint32_t chunk = (j & 63) >> 3;
+    for (unsigned i = grp; i < my_tiles; i += 2) {
+      const int stage = static_cast<int>(i % kTwStages);
+      const uint32_t phase = (i / kTwStages) & 1u;
+      const unsigned long long inb = MASKED ? 0ull : inside_bits(g);
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* a_st = s_a + stage * 32768 + col_off;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const bool keep = MASKED ? (mk[t] != 0) : (((inb >> t) & 1ull) != 0);
+        const float x = keep ? v[t] : 0.f;
+        if (t == p.center) csum += x;
+        const uint32_t hl = split_hi_lo(x);
+        const int m0 = t, m1 = T + t;
+        *reinterpret_cast<unsigned short*>(a_st + (m0 >> 3) * 1024 + (m0 & 7) * 128 + ((chunk ^ (m0 & 7)) << 4)) =
+            static_cast<unsigned short>(hl & 0xffffu);
+        *reinterpret_cast<unsigned short*>(a_st + (m1 >> 3) * 1024 + (m1 & 7) * 128 + ((chunk ^ (m1 & 7)) << 4)) =
+            static_cast<unsigned short>(hl >> 16);
+      }
+      {
+        constexpr int m2 = 2 * T;
+        *reinterpret_cast<unsigned short*>(a_st + (m2 >> 3) * 1024 + (m2 & 7) * 128 + ((chunk ^ (m2 & 7)) << 4)) =
+            g.valid ? static_cast<unsigned short>(0x3f80) : static_cast<unsigned short>(0);
+      }
+      fence_proxy_async();
+      mbar_arrive(&full_a[stage]);
+      if (i + 2 < my_tiles) {
+        g = geo(blockIdx.x + (i + 2) * gridDim.x);
+        load_src(g, v, mk);
+      }
+    }
+    if (p.partial_c != nullptr) {
+      const float ws = warp_sum(csum);
+      if (lane == 0) s_red[warp - 4] = ws;
+    }
+    if (grp == 0) {
+    // ---- read-out: lane j of the accumulator = row j ----
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float* dst = p.partial + (static_cast<size_t>(blockIdx.x) * NR + j) * 64;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tmem + (static_cast<uint32_t>((warp - 4) * 32) << 16) + ch * 32, raw);
+      tmem_ld_wait();
+      if (j < NR) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          reinterpret_cast<float4*>(dst + ch * 32)[q] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
+                                                                   __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
+      }
+    }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0 && p.partial_c != nullptr) p.partial_c[blockIdx.x] = s_red[0] + s_red[1] + s_red[2] + s_red[3] + s_red[4] + s_red[5] + s_red[6] + s_red[7];
+  if (warp == 2) tmem_dealloc<64>(tmem);
+}
+
+__global__ void tapwgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_c, int rows, int T,
+                                       float* __restrict__ out_w, int w_sn, int w_st, RowGemmParams perm_holder,
+                                       float* __restrict__ out_b, int bias_mode, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int NR = 2 * T + 1;
+  if (i < 64 * T) {
+    const int t = i / 64, c = i % 64;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) {
+      const float* pr = partial + static_cast<size_t>(r) * NR * 64;
+      s += static_cast<double>(pr[t * 64 + c]) + static_cast<double>(pr[(T + t) * 64 + c]);
+    }
+    float* d = out_w + c * w_sn + perm_holder.perm[t] * w_st;
+    *d = (accumulate ? *d : 0.f) + static_cast<float>(s);
+  } else if (i < 64 * T + 64 && bias_mode == 1 && out_b != nullptr) {
+    const int c = i - 64 * T;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += partial[(static_cast<size_t>(r) * NR + 2 * T) * 64 + c];
+    out_b[c] = (accumulate ? out_b[c] : 0.f) + static_cast<float>(s);
+  } else if (i == 64 * T + 64 && bias_mode == 2 && out_b != nullptr && partial_c != nullptr) {
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += partial_c[r];
+    out_b[0] = (accumulate ? out_b[0] : 0.f) + static_cast<float>(s);
+  }
+}
+
+template <int K, bool MASKED>
+static int tapwgrad_launch(const TapWgradParams& p, const void* y, int grid_cap, int* grid_used, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TG_CHECK_CUDA(cudaFuncSetAttribute(tapwgrad_kernel<K, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTwSmem));
+    attr_set = true;
+  }
+  CUtensorMap tm_y;
+  const uint64_t dims[2] = {64, p.total};
+  const uint64_t str[1] = {128};
+  const uint32_t box[2] = {64, 128};
+  if (make_tmap_bf16(&tm_y, y, 2, dims, str, box) != 0) return -3;
+  const long tiles = (static_cast<long>(p.total) + 127) / 128;
+  long grid = num_sms();
+  if (grid > tiles) grid = tiles;
+  if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
+  if (grid < 1) grid = 1;
+  if (grid_used) *grid_used = static_cast<int>(grid);
+  tapwgrad_kernel<K, MASKED><<<static_cast<int>(grid), 384, kTwSmem, st>>>(p, tm_y);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int tapwgrad_dispatch(int k, const TapWgradParams& p, const void* y, int grid_cap, int* grid_used, cudaStream_t st) {
+  const bool m = p.src_mask != nullptr;
+  if (k == 3) return m ? tapwgrad_launch<3, true>(p, y, grid_cap, grid_used, st) : tapwgrad_launch<3, false>(p, y, grid_cap, grid_used, st);
+  if (k == 4) return m ? tapwgrad_launch<4, true>(p, y, grid_cap, grid_used, st) : tapwgrad_launch<4, false>(p, y, grid_cap, grid_used, st);
+  if (k == 7) return m ? tapwgrad_launch<7, true>(p, y, grid_cap, grid_used, st) : tapwgrad_launch<7, false>(p, y, grid_cap, grid_used, st);
+  return -1;
+}
+
+int tapwgrad_reduce(int k, const float* partial, const float* partial_c, int rows, float* out_w, int w_sn, int w_st,
+                    const int8_t* perm, float* out_b, int bias_mode, int accumulate, cudaStream_t st) {
+  RowGemmParams holder{};
+  for (int t = 0; t < k * k; ++t) holder.perm[t] = perm[t];
+  const int n = 64 * k * k + 65;
+  tapwgrad_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, partial_c, rows, k * k, out_w, w_sn, w_st, holder, out_b,
+                                                          bias_mode, accumulate);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 bool thin_mma_enabled() {
   static int on = -1;
   if (on < 0) {

@@ -27,6 +27,25 @@ struct RowGemmParams {
   int debug;                // timing experiments only (env TG_THIN_DEBUG): 1 = skip the output store, 2 = skip the source loads
 };
 
+// Weight gradient of the same thin convolutions:  D[tap][c] = sum over pixels of src_tap(pixel) * Y[pixel][c].
+struct TapWgradParams {
+  const float* src;         // fp32 [B][H][W]: the single-channel operand (image x, or the gradient g of a 64->1 conv)
+  const uint8_t* src_mask;  // optional u8 [B][H][W]
+  int B, H, W, Ho, Wo;      // Y pixel grid is [B][Ho][Wo]
+  int S, pad, flip;         // same tap geometry as RowGemmParams
+  int y_split;              // Y is stored parity-split ([B][4][Ho/2][Wo/2][64])
+  unsigned total;           // B*Ho*Wo
+  float* partial;           // [grid][2*k*k + 1][64]: rows t = hi part, k*k + t = lo part, 2*k*k = sum of Y (bias gradient)
+  float* partial_c;         // optional [grid]: sum over pixels of the source value of tap `center`
+  int center;
+};
+// Launches the accumulation kernel; *grid_used partial rows are written (<= grid_cap).
+int tapwgrad_dispatch(int k, const TapWgradParams& p, const void* y, int grid_cap, int* grid_used, cudaStream_t st);
+// out_w[c * w_sn + perm[t] * w_st] (+)= sum_r partial[r][t][c] + partial[r][T+t][c];
+// bias_mode 1: out_b[c] (+)= sum_r partial[r][2T][c];  bias_mode 2: out_b[0] (+)= sum_r partial_c[r]
+int tapwgrad_reduce(int k, const float* partial, const float* partial_c, int rows, float* out_w, int w_sn, int w_st,
+                    const int8_t* perm, float* out_b, int bias_mode, int accumulate, cudaStream_t st);
+
 // k in {3, 4, 7}. grid_cap > 0 bounds the grid (= number of per-CTA stats rows); returns 0, or -1 if k is unsupported.
 int rowgemm_dispatch(int k, const RowGemmParams& p, int grid_cap, int* grid_used, cudaStream_t st);
 bool thin_mma_enabled();   // env TG_NO_THIN_MMA=1 selects the CUDA-core kernels (A/B timing only)
