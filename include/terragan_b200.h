@@ -220,7 +220,10 @@ int tg_conv_c1_wgrad_rows(void);
 int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, int C, const float* wgt, int ncls,
                     const int* cls_count, const int8_t* tap_dh, const int8_t* tap_dw, const float* bias,
                     int Ho, int Wo, int mode, const uint8_t* mask, const float* xin, float* out,
-                    float* sig_out, void* stream);
+                    float* sig_out, float* scratch, size_t scratch_floats, void* stream);
+/* Floats of device scratch with which tg_conv_to1_fwd runs its C = 64 cases on the tensor cores (per-pixel tap
+ * dot products, then the shifted sum); with scratch == NULL or too small it runs the CUDA-core kernels. */
+size_t tg_conv_to1_fwd_scratch_floats(int B, int H, int W, int C, int ntaps);
 /* dx[B][H][W][C] (bf16) = sum_t g[b][h - dh_t][w - dw_t] * wgt[t][c];  g fp32 [B][Ho][Wo]. */
 int tg_conv_to1_bwd_data(const float* g, int B, int Ho, int Wo, const float* wgt, int ntaps,
                          const int8_t* tap_dh, const int8_t* tap_dw, int H, int W, int C, void* dx,

@@ -11,8 +11,8 @@
 //   final conv + sigmoid + `out*(1-mask) + x*mask`          mvp_gan/src/models/generator.py:56-62
 // and the autograd backward of each.
 #include "tg_common.cuh"
-#include "thin_mma.cuh"
 #include "../../include/terragan_b200.h"
+#include "thin_mma.cuh"
 
 namespace tg {
 
@@ -262,12 +262,6 @@ __global__ void conv_c1_wgrad_reduce_kernel(const float* __restrict__ partial, i
 // out = sig * (1 - mask) + xin * mask.
 // 8 lanes per output pixel (8 channels each, 16-byte loads), 4 pixels per warp.
 // ------------------------------------------------------------------------------------------------
-struct To1Taps {
-  int ncls;
-  int count[4];
-  int begin[4];
-  int8_t dh[TG_MAX_TAPS], dw[TG_MAX_TAPS];
-};
 
 __global__ void __launch_bounds__(256)
 conv_to1_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_split, int B, int H, int W, int C,
@@ -887,7 +881,7 @@ extern "C" int tg_conv_c1_wgrad_rows(void) { return tg::num_sms() * 2; }
 extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, int C, const float* wgt, int ncls,
                                const int* cls_count, const int8_t* tap_dh, const int8_t* tap_dw, const float* bias, int Ho,
                                int Wo, int mode, const uint8_t* mask, const float* xin, float* out, float* sig_out,
-                               void* stream) {
+                               float* scratch, size_t scratch_floats, void* stream) {
   using namespace tg;
   TG_REQUIRE(x && wgt && out && cls_count && tap_dh && tap_dw, "tg_conv_to1_fwd: null pointer");
   TG_REQUIRE(C % 64 == 0, "tg_conv_to1_fwd: C=%d must be a multiple of 64", C);
@@ -895,6 +889,14 @@ extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, 
   TG_REQUIRE(mode == 0 || (mask && xin), "tg_conv_to1_fwd: composite mode needs mask and xin");
   To1Taps taps;
   TG_REQUIRE(fill_taps(&taps, ncls, cls_count, tap_dh, tap_dw) > 0, "tg_conv_to1_fwd: bad tap table");
+  if (thin_mma_enabled() && C == 64 && scratch != nullptr) {
+    int ntaps = 0;
+    for (int i = 0; i < ncls; ++i) ntaps += cls_count[i];
+    const int rc = to1_fwd_mma(x, x_split, B, H, W, wgt, taps, ntaps, bias, Ho, Wo, mode, mask, xin, out, sig_out, scratch,
+                               scratch_floats, reinterpret_cast<cudaStream_t>(stream));
+    if (rc == 0) return 0;
+    TG_REQUIRE(rc == -1, "tg_conv_to1_fwd: tensor-core path failed (%d)", rc);     // -1: shape not covered, fall through
+  }
   Tap3x3 tp;
   if (ncls == 1 && C == 64 && !x_split && Ho == H && Wo == W && make_tap3x3(&tp, cls_count[0], tap_dh, tap_dw)) {
     const long tiles = static_cast<long>(B) * ((H + kT1H - 1) / kT1H) * ((W + kT1W - 1) / kT1W);
@@ -921,6 +923,11 @@ extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, 
       sig_out);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" size_t tg_conv_to1_fwd_scratch_floats(int B, int H, int W, int C, int ntaps) {
+  if (C != 64 || ntaps < 1 || ntaps > 32) return 0;
+  return static_cast<size_t>(ntaps) * B * H * W;
 }
 
 extern "C" int tg_conv_to1_bwd_data(const float* g, int B, int Ho, int Wo, const float* wgt, int ntaps,

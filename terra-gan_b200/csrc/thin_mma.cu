@@ -646,6 +646,202 @@ int tapwgrad_reduce(int k, const float* partial, const float* partial_c, int row
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// 64 -> 1 gather convolution, step 1:  T[t][pixel] = sum_c w[t][c] * x[pixel][c]   (t < ntaps <= 32)
+//   A = the tap weight vectors as rows 0..ntaps-1 of a 128-row K-major tile (hi and lo bf16 parts in two tiles,
+//   accumulated into the same rows), B = 256 activation pixels x 64 channels per TMA box (storage order, so any
+//   layout of x works), D = 128 lanes x 256 columns in TMEM, double-buffered. Only lanes < ntaps carry data:
+//   the instruction costs the same 128 clocks either way and the kernel stays HBM-bound on reading x.
+// warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator, warps 4 and 8 (TMEM lane quarter 0): read-out.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTdStages = 4;
+constexpr int kTdN = 256;
+constexpr int kTdSmem = 2 * 16384 + kTdStages * kTdN * 128 + 256 + 1024;
+
+__global__ void __launch_bounds__(384, 1)
+tapdot_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ wgt /*[ntaps][64]*/, int ntaps,
+              unsigned total, float* __restrict__ T) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_w = smem;                                    // [hi | lo][128 rows][128 B]
+  uint8_t* s_x = s_w + 2 * 16384;                         // [stage][256 pixels][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + kTdStages * kTdN * 128);
+  uint64_t* full = bars;                                  // [kTdStages]
+  uint64_t* empty = bars + kTdStages;                     // [kTdStages]
+  uint64_t* tfull = bars + 2 * kTdStages;                 // [2]
+  uint64_t* tempty = bars + 2 * kTdStages + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTdStages + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < 2 * 16384 / 16; i += 384) reinterpret_cast<uint4*>(s_w)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  for (int i = tid; i < ntaps * 64; i += 384) {
+    const int m = i >> 6, c = i & 63;
+    const uint32_t hl = split_hi_lo(__ldg(wgt + i));
+    uint8_t* dst = s_w + (m >> 3) * 1024 + (m & 7) * 128 + (((c >> 3) ^ (m & 7)) << 4) + (c & 7) * 2;
+    *reinterpret_cast<unsigned short*>(dst) = static_cast<unsigned short>(hl & 0xffffu);
+    *reinterpret_cast<unsigned short*>(dst + 16384) = static_cast<unsigned short>(hl >> 16);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kTdStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 1);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const unsigned tiles = (total + kTdN - 1) / kTdN;
+  const unsigned my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (unsigned i = 0; i < my_tiles; ++i) {
+        const int stage = static_cast<int>(i % kTdStages);
+        mbar_wait(&empty[stage], ((i / kTdStages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&full[stage], kTdN * 128);
+        tma_load_2d(s_x + stage * kTdN * 128, &tm_x, &full[stage], 0,
+                    static_cast<int>((blockIdx.x + i * gridDim.x) * kTdN));      // tail rows: zero fill
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, kTdN, false, false);
+      const uint32_t w_addr = smem_u32(s_w), x_addr = smem_u32(s_x);
+      for (unsigned i = 0; i < my_tiles; ++i) {
+        const int stage = static_cast<int>(i % kTdStages);
+        const int acc = static_cast<int>(i & 1u);
+        mbar_wait(&tempty[acc], ((i >> 1) & 1u) ^ 1u);
+        mbar_wait(&full[stage], (i / kTdStages) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = make_smem_desc(w_addr + part * 16384 + ks * 32, 16, 1024);
+            const uint64_t db = make_smem_desc(x_addr + stage * kTdN * 128 + ks * 32, 16, 1024);
+            umma_bf16(tmem + acc * kTdN, da, db, idesc, (part | ks) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp == 4 || warp == 8) {
+    // lane t of TMEM quarter 0 = tap t; warp 4 drains accumulator 0, warp 8 accumulator 1
+    const int acc = warp == 4 ? 0 : 1;
+    for (unsigned i = acc; i < my_tiles; i += 2) {
+      mbar_wait(&tfull[acc], (i >> 1) & 1u);
+      tc_fence_after();
+      const unsigned p0 = (blockIdx.x + i * gridDim.x) * kTdN;
+      float* trow = T + static_cast<size_t>(lane) * total + p0;
+#pragma unroll 2
+      for (int ch = 0; ch < kTdN / 32; ++ch) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem + acc * kTdN + ch * 32, raw);
+        tmem_ld_wait();
+        if (lane < ntaps) {
+          if (p0 + ch * 32 + 32 <= total) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(trow + ch * 32)[q] =
+                  make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                              __uint_as_float(raw[4 * q + 3]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (p0 + ch * 32 + q < total) trow[ch * 32 + q] = __uint_as_float(raw[q]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// step 2: out[b][oh][ow] = bias + sum over the taps t of the pixel's class of T[t][storage index of base + d_t]
+__global__ void __launch_bounds__(256)
+tapsum_kernel(const float* __restrict__ T, unsigned total_in, int x_split, int B, int H, int W, To1Taps taps,
+              const float* __restrict__ bias, int Ho, int Wo, int mode, const uint8_t* __restrict__ mask,
+              const float* __restrict__ xin, float* __restrict__ out, float* __restrict__ sig_out) {
+  const unsigned M = static_cast<unsigned>(B) * Ho * Wo;
+  const float bv = bias ? __ldg(bias) : 0.f;
+  const unsigned HW = static_cast<unsigned>(H) * W, HoWo = static_cast<unsigned>(Ho) * Wo;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < M; p += gridDim.x * blockDim.x) {
+    const unsigned b = p / HoWo, rem = p - b * HoWo;
+    const int oh = static_cast<int>(rem / Wo), ow = static_cast<int>(rem - static_cast<unsigned>(oh) * Wo);
+    int cls = 0, bh = oh, bw = ow;
+    if (taps.ncls == 4) {
+      cls = 2 * (oh & 1) + (ow & 1);
+      bh = oh >> 1;
+      bw = ow >> 1;
+    }
+    float acc = 0.f;
+    for (int t = taps.begin[cls]; t < taps.begin[cls] + taps.count[cls]; ++t) {
+      const int h = bh + taps.dh[t], w = bw + taps.dw[t];
+      if (h < 0 || h >= H || w < 0 || w >= W) continue;
+      const unsigned sidx = x_split
+          ? ((b * 4u + 2u * (h & 1) + (w & 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)
+          : b * HW + static_cast<unsigned>(h) * W + w;
+      acc += __ldg(T + static_cast<size_t>(t) * total_in + sidx);
+    }
+    const float v = acc + bv;
+    if (mode == 0) {
+      out[p] = v;
+    } else {
+      const float sg = 1.f / (1.f + __expf(-v));
+      if (sig_out) sig_out[p] = sg;
+      const float m = mask[p] ? 1.f : 0.f;
+      out[p] = sg * (1.f - m) + xin[p] * m;
+    }
+  }
+}
+
+int to1_fwd_mma(const void* x, int x_split, int B, int H, int W, const float* wgt, const To1Taps& taps, int ntaps,
+                const float* bias, int Ho, int Wo, int mode, const uint8_t* mask, const float* xin, float* out,
+                float* sig_out, float* scratch, size_t scratch_floats, cudaStream_t st) {
+  const long total = static_cast<long>(B) * H * W;
+  if (ntaps < 1 || ntaps > 32 || total >= (1L << 31) || static_cast<long>(B) * Ho * Wo >= (1L << 31)) return -1;
+  if (scratch == nullptr || scratch_floats < static_cast<size_t>(ntaps) * total) return -1;
+  if (x_split && (H % 2 || W % 2)) return -1;
+  if (total % 4 != 0) return -1;                       // 16-byte stores into the rows of T
+  static bool attr_set = false;
+  if (!attr_set) {
+    TG_CHECK_CUDA(cudaFuncSetAttribute(tapdot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
+    attr_set = true;
+  }
+  CUtensorMap tm_x;
+  const uint64_t dims[2] = {64, static_cast<uint64_t>(total)};
+  const uint64_t str[1] = {128};
+  const uint32_t box[2] = {64, kTdN};
+  if (make_tmap_bf16(&tm_x, x, 2, dims, str, box) != 0) return -3;
+  const long tiles = (total + kTdN - 1) / kTdN;
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  tapdot_kernel<<<grid, 384, kTdSmem, st>>>(tm_x, wgt, ntaps, static_cast<unsigned>(total), scratch);
+  TG_CHECK_CUDA(cudaGetLastError());
+  const long M = static_cast<long>(B) * Ho * Wo;
+  long g2 = (M + 255) / 256;
+  if (g2 > 16L * num_sms()) g2 = 16L * num_sms();
+  tapsum_kernel<<<static_cast<int>(g2), 256, 0, st>>>(scratch, static_cast<unsigned>(total), x_split, B, H, W, taps, bias,
+                                                     Ho, Wo, mode, mask, xin, out, sig_out);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 bool thin_mma_enabled() {
   static int on = -1;
   if (on < 0) {

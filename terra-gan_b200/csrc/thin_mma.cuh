@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "../../include/terragan_b200.h"
 
 namespace tg {
 
@@ -45,6 +46,20 @@ int tapwgrad_dispatch(int k, const TapWgradParams& p, const void* y, int grid_ca
 // bias_mode 1: out_b[c] (+)= sum_r partial[r][2T][c];  bias_mode 2: out_b[0] (+)= sum_r partial_c[r]
 int tapwgrad_reduce(int k, const float* partial, const float* partial_c, int rows, float* out_w, int w_sn, int w_st,
                     const int8_t* perm, float* out_b, int bias_mode, int accumulate, cudaStream_t st);
+
+// Tap table of a C -> 1 "gather" convolution (direct_conv.cu): classes of taps selected by output parity.
+struct To1Taps {
+  int ncls;
+  int count[4];
+  int begin[4];
+  int8_t dh[TG_MAX_TAPS], dw[TG_MAX_TAPS];
+};
+// 64 -> 1 gather convolution in two steps: per-pixel tap dot products T[t][pixel] = <x[pixel][:], w[t][:]> on the
+// tensor cores (x bf16 [pixels][64] in storage order), then the shifted sum + bias / sigmoid-composite epilogue.
+// scratch: >= ntaps * B*H*W floats. Returns 0, or -1 when the shape is not covered (caller falls back).
+int to1_fwd_mma(const void* x, int x_split, int B, int H, int W, const float* wgt, const To1Taps& taps, int ntaps,
+                const float* bias, int Ho, int Wo, int mode, const uint8_t* mask, const float* xin, float* out,
+                float* sig_out, float* scratch, size_t scratch_floats, cudaStream_t st);
 
 // k in {3, 4, 7}. grid_cap > 0 bounds the grid (= number of per-CTA stats rows); returns 0, or -1 if k is unsupported.
 int rowgemm_dispatch(int k, const RowGemmParams& p, int grid_cap, int* grid_used, cudaStream_t st);
