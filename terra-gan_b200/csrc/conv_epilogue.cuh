@@ -4,6 +4,7 @@
 #pragma once
 #include "conv_igemm.cuh"
 #include "tg_common.cuh"
+#include <type_traits>
 
 namespace tg {
 
@@ -12,39 +13,86 @@ namespace tg {
 // store would touch 32 different 128-byte lines per instruction (the LSU serialises them: measured 4x the
 // MMA time on the N=64 layers). Rows are therefore written to shared memory (XOR-swizzled, conflict-free)
 // and read back transposed so that every global store instruction writes full contiguous lines.
-template <int BN, int kVec, int kSC>
+// MODE: compile-time feature set of the launch so that the per-tile instruction stream only holds what the layer
+// uses (a warp's epilogue is one dependent chain; with every variant predicated at run time it was ~500
+// instructions per 32x32 chunk and capped the N=64 layers). Bits: 1 ratio/mask code, 2 BN statistics,
+// 4 activation-derivative gate, 8 affine (eval-mode BN), 16 per-channel vectors present (bias / scale / shift).
+// MODE < 0: everything decided at run time.
+constexpr int kEpiCode = 1, kEpiStats = 2, kEpiGate = 4, kEpiAffine = 8, kEpiVec = 16;
+__host__ __device__ inline int conv_epilogue_mode(const void* code, const void* stats, const void* gate, const void* scale,
+                                                  const void* shift, const void* bias) {
+  const int m = (code ? kEpiCode : 0) | (stats ? kEpiStats : 0) | (gate ? kEpiGate : 0) |
+                ((scale || shift) ? kEpiAffine : 0) | ((bias || scale || shift) ? kEpiVec : 0);
+  switch (m) {
+    case 0: case kEpiCode: case kEpiGate: case kEpiVec: case kEpiVec | kEpiStats: case kEpiVec | kEpiCode | kEpiStats:
+    case kEpiVec | kEpiAffine: case kEpiVec | kEpiCode | kEpiAffine:
+      return m;
+    default:
+      return -1;
+  }
+}
+// calls f(std::integral_constant<int, MODE>) for the specialised modes, MODE = -1 otherwise
+template <typename F>
+__device__ __forceinline__ void conv_epilogue_dispatch(int mode, F f) {
+  switch (mode) {
+    case 0: f(std::integral_constant<int, 0>{}); break;
+    case kEpiCode: f(std::integral_constant<int, kEpiCode>{}); break;
+    case kEpiGate: f(std::integral_constant<int, kEpiGate>{}); break;
+    case kEpiVec: f(std::integral_constant<int, kEpiVec>{}); break;
+    case kEpiVec | kEpiStats: f(std::integral_constant<int, kEpiVec | kEpiStats>{}); break;
+    case kEpiVec | kEpiCode | kEpiStats: f(std::integral_constant<int, kEpiVec | kEpiCode | kEpiStats>{}); break;
+    case kEpiVec | kEpiAffine: f(std::integral_constant<int, kEpiVec | kEpiAffine>{}); break;
+    case kEpiVec | kEpiCode | kEpiAffine: f(std::integral_constant<int, kEpiVec | kEpiCode | kEpiAffine>{}); break;
+    default: f(std::integral_constant<int, -1>{}); break;
+  }
+}
+
+template <int BN, int kVec, int kSC, int MODE>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, int lane, int nt, int sb, int tw,
                                                    int th, int tb, uint32_t t_addr, const float* s_vec,
-                                                   float* my_stats, bool has_vec, uint8_t* stage, int hsel) {
+                                                   float* my_stats, bool has_vec, uint8_t* stage, int hsel,
+                                                   int wt, int ht, int bt) {
   static_assert(kSC == 32 || kSC == 64, "staging width is 32 or 64 columns");
   constexpr int kLPR = kSC / 8;           // 16-byte chunks (= lanes) per staged row
   constexpr int kRowBytes = kSC * 2;
   constexpr int kChunksPerStage = kSC / 32;
-  const int r = q * 32 + lane;  // row of the tile = pixel in box order
-  const int wt = r % p.Wt;
-  const int ht = (r / p.Wt) % p.Ht;
-  const int bt = r / (p.Wt * p.Ht);
+  // (wt, ht, bt): position of this thread's row (TMEM lane q*32 + lane) inside the pixel box. They depend on the
+  // thread only, so the callers compute them once per kernel: the three runtime integer divisions sat at the head
+  // of every tile's dependent chain (the epilogue is latency-bound per warp, not throughput-bound).
+  __builtin_assume(__isShared(s_vec));
+  __builtin_assume(__isShared(my_stats));
+  __builtin_assume(__isShared(stage));
+  constexpr bool kGen = MODE < 0;
+  const bool f_code = kGen ? (p.code != nullptr) : ((MODE & kEpiCode) != 0);
+  const bool f_stats = kGen ? (p.stats != nullptr) : ((MODE & kEpiStats) != 0);
+  const bool f_gate = kGen ? (p.gate != nullptr) : ((MODE & kEpiGate) != 0);
+  const bool f_vec = kGen ? has_vec : ((MODE & kEpiVec) != 0);
   const int w = tw * p.Wt + wt, h = th * p.Ht + ht, b = tb * p.Bt + bt;
   const bool valid = (w < p.Wo) && (h < p.Ho) && (b < p.B);
   const long pix =
       ((static_cast<long>(b) * p.Po + p.sub[sb].out_plane) * p.Ho + h) * p.Wo + w;
   float rs = 1.f;
-  if (p.code != nullptr && valid) rs = p.lut[p.code[pix]];
+  if (f_code && valid) rs = p.lut[p.code[pix]];
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  const bool has_affine = p.scale != nullptr || p.shift != nullptr;
+  const bool has_affine = kGen ? (p.scale != nullptr || p.shift != nullptr) : ((MODE & kEpiAffine) != 0);
   const int sw_w = (kSC == 64) ? (lane & 7) : ((lane >> 1) & 3);     // write-side swizzle key of this row
-  const __nv_bfloat16* grow = p.gate ? p.gate + pix * p.Cout + nt * BN : nullptr;
+  const __nv_bfloat16* grow = f_gate ? p.gate + pix * p.Cout + nt * BN : nullptr;
 
   // two warps share each TMEM lane quarter: warp `hsel` takes every other kSC-column group
 #pragma unroll 1
   for (int ch = 0; ch < BN / 32; ++ch) {
     if (((ch / kChunksPerStage) & 1) != hsel) continue;
     uint32_t raw[32];
-    tmem_ld_32x32(t_addr + ch * 32, raw);
-    tmem_ld_wait();
+    if (!(p.debug & 8)) {
+      tmem_ld_32x32(t_addr + ch * 32, raw);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) raw[j] = 0x3f800000u + lane;
+    }
     const int n0 = nt * BN + ch * 32;
     float v[32];
-    if (has_vec) {
+    if (f_vec) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 bv = *reinterpret_cast<const float4*>(s_vec + n0 + j);
@@ -57,10 +105,13 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
     }
-    const float rsv = valid ? rs : 0.f;
+    // rows outside the image must contribute 0 to the statistics; elsewhere they are simply not stored
+    if (f_code || f_stats) {
+      const float rsv = valid ? rs : 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= rsv;
-    if (p.stats != nullptr) {
+      for (int j = 0; j < 32; ++j) v[j] *= rsv;
+    }
+    if (f_stats) {
       float sq[32], sm[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -74,7 +125,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
     }
     uint32_t packed[16];
     uint32_t gbits[16];
-    if (grow != nullptr && valid) {
+    if (f_gate && valid) {
       const uint4* gsrc = reinterpret_cast<const uint4*>(grow + ch * 32);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -91,7 +142,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
         a = a * sc2.x + sh2.x;
         c = c * sc2.y + sh2.y;
       }
-      if (grow != nullptr && valid) {
+      if (f_gate && valid) {
         // derivative of ReLU / LeakyReLU of the tensor this gradient flows into
         const float2 gv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gbits[j >> 1]));
         if (!(gv.x > 0.f)) a *= p.gate_slope;
@@ -113,7 +164,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
         *reinterpret_cast<uint4*>(stage + lane * kRowBytes + (((cbase + j) ^ sw_w) << 4)) =
             make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
     }
-    if ((ch % kChunksPerStage) == kChunksPerStage - 1) {
+    if ((ch % kChunksPerStage) == kChunksPerStage - 1 && !(p.debug & 32)) {
       __syncwarp();
       const int col0 = nt * BN + (ch - (kChunksPerStage - 1)) * 32;   // first channel held by the staging tile
 #pragma unroll

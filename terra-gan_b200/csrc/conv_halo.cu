@@ -127,14 +127,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop so that addresses and descriptors stay warp-uniform (uniform registers);
+    // only the tcgen05 instructions themselves are issued by one elected lane. Under `if (lane == 0)` the
+    // compiler wraps every MMA in an ELECT / R2UR.BROADCAST loop (~10 extra instructions per MMA).
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
       mbar_wait(w_bar, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t w_addr = smem_u32(s_w);
+      // Descriptor words are fixed per operand; the loop below only adds byte offsets (>> 4) to the lo words:
+      // tap (dh, dw) starts at halo row (dh+1)*10 + (dw+1), 8-pixel atoms are 10 halo rows (1280 B) apart.
+      const uint64_t da0 = make_smem_desc(smem_u32(s_a), 16, (kHaloW + 2) * 128);
+      const uint64_t db0 = make_smem_desc(smem_u32(s_w), 16, 1024);
+      const uint32_t a_hi = static_cast<uint32_t>(da0 >> 32), b_hi = static_cast<uint32_t>(db0 >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(da0), b_lo0 = static_cast<uint32_t>(db0);
+      uint32_t tap_off[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_off[t] = static_cast<uint32_t>((p.tap_dh[t] + 1) * (kHaloW + 2) + (p.tap_dw[t] + 1)) * 8u;
+      const uint32_t slab16 = static_cast<uint32_t>(kSlabBytes >> 4);
+      const uint32_t tap_step = static_cast<uint32_t>(p.cin_blocks) * slab16;
+      const bool skip_mma = (p.debug & 4) != 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -142,24 +156,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int cb = 0; cb < p.cin_blocks; ++cb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(s_a + stage * kHaloStageBytes);
-          for (int t = 0; t < taps; ++t) {
-            // A rows = output pixels (ht, wt): halo pixel (ht + dh + 1, wt + dw + 1); 8-pixel atoms
-            // (one tile row) are (kHaloW + 2) halo rows = 1280 B apart
-            const int row0 = (p.tap_dh[t] + 1) * (kHaloW + 2) + (p.tap_dw[t] + 1);
-            const uint64_t da = make_smem_desc(a_addr + row0 * 128, 16, (kHaloW + 2) * 128);
-            const uint64_t db = make_smem_desc(w_addr + (t * p.cin_blocks + cb) * kSlabBytes, 16, 1024);
-            if (p.debug & 4) continue;
+          const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * (kHaloStageBytes >> 4);
+          uint32_t b_lo = b_lo0 + static_cast<uint32_t>(cb) * slab16;
+          if (!skip_mma && elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0);
+            for (int t = 0; t < 9; ++t) {
+              const uint32_t al = a_lo + tap_off[t];
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_lh(d_tmem, al + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (t | k) ? 1u : static_cast<uint32_t>(cb != 0));
+              b_lo += tap_step;
+            }
           }
-          umma_commit(&empty_bar[stage]);
+          if (elect_one()) umma_commit(&empty_bar[stage]);
           if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (elect_one()) umma_commit(&tfull_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -171,26 +186,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = (warp - 4) & 3;
     const int hsel = (warp - 4) >> 2;
     float* my_stats = s_stats + q * (2 * kHaloVec);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int tw = tile % p.tiles_w;
-      const int th = (tile / p.tiles_w) % p.tiles_h;
-      const int tb = tile / (p.tiles_w * p.tiles_h);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      if (!(p.debug & 2))
-        conv_epilogue_tile<BN, kHaloVec, kSC>(p, q, lane, 0, 0, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
-                                              s_out + (warp - 4) * (32 * kSC * 2), hsel);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
+    const int row = q * 32 + lane;                     // row of the tile = pixel in box order (8 wide, 16 high)
+    const int e_wt = row % kHaloW, e_ht = row / kHaloW, e_bt = 0;
+    const int epi_mode = conv_epilogue_mode(p.code, p.stats, p.gate, p.scale, p.shift, p.bias);
+    conv_epilogue_dispatch(epi_mode, [&](auto mode_tag) {
+      constexpr int kMode = decltype(mode_tag)::value;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tw = tile % p.tiles_w;
+        const int th = (tile / p.tiles_w) % p.tiles_h;
+        const int tb = tile / (p.tiles_w * p.tiles_h);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+        if (!(p.debug & 2))
+          conv_epilogue_tile<BN, kHaloVec, kSC, kMode>(p, q, lane, 0, 0, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
+                                                       s_out + (warp - 4) * (32 * kSC * 2), hsel, e_wt, e_ht, e_bt);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
-    }
+    });
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int et = threadIdx.x - 128;

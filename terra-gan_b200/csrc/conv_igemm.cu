@@ -139,8 +139,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp runs the loop (warp-uniform descriptors in uniform registers); one elected lane issues
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+      const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);     // A and B: K-major, 8-row atoms 1024 B apart
+      const uint32_t d_lo0 = static_cast<uint32_t>(d0), d_hi = static_cast<uint32_t>(d0 >> 32);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -154,22 +157,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * S::kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
-          const uint64_t da = make_smem_desc(a_addr, 16, 1024);
-          const uint64_t db = make_smem_desc(b_addr, 16, 1024);
+          // descriptor lo word = base + stage offset (>> 4); +2 per 16 bf16 (32 B) along K inside the swizzle row
+          const uint32_t a_lo = d_lo0 + static_cast<uint32_t>(stage) * (S::kStageBytes >> 4);
+          const uint32_t b_lo = a_lo + (kABytes >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 16 bf16 (32 B) along K inside the 128 B swizzle row: +2 in (addr >> 4) units
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lh(d_tmem, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -181,29 +183,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = (warp - 4) & 3;   // TMEM lane quarter == warp_idx % 4
     const int hsel = (warp - 4) >> 2;  // which half of the column groups this warp drains
     float* my_stats = s_stats + q * (2 * 512);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      const int rest = tile / p.n_tiles;
-      const int mt = rest % m_tiles;
-      const int sb = rest / m_tiles;
-      const int tw = mt % p.tiles_w;
-      const int th = (mt / p.tiles_w) % p.tiles_h;
-      const int tb = mt / (p.tiles_w * p.tiles_h);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      conv_epilogue_tile<BN, 512, S::kStoreCols>(p, q, lane, nt, sb, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
-                                                 s_out + (warp - 4) * (32 * S::kStoreCols * 2), hsel);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
+    const int row = q * 32 + lane;                     // row of the tile = pixel in box order
+    const int e_wt = row % p.Wt, e_ht = (row / p.Wt) % p.Ht, e_bt = row / (p.Wt * p.Ht);
+    const int epi_mode = conv_epilogue_mode(p.code, p.stats, p.gate, p.scale, p.shift, p.bias);
+    conv_epilogue_dispatch(epi_mode, [&](auto mode_tag) {
+      constexpr int kMode = decltype(mode_tag)::value;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int rest = tile / p.n_tiles;
+        const int mt = rest % m_tiles;
+        const int sb = rest / m_tiles;
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int tb = mt / (p.tiles_w * p.tiles_h);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+        conv_epilogue_tile<BN, 512, S::kStoreCols, kMode>(p, q, lane, nt, sb, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
+                                                          s_out + (warp - 4) * (32 * S::kStoreCols * 2), hsel, e_wt, e_ht,
+                                                          e_bt);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
-    }
+    });
     // flush the per-CTA BatchNorm partials: one row per CTA, summed by tg_bn_finalize
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -172,6 +172,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the two shared-memory descriptors given as (lo, hi) 32-bit words. The issuing thread is a single
+// dependent instruction stream: rebuilding 64-bit descriptors per MMA costs more clocks than an N <= 128 MMA
+// takes (measured with tools/probe/mma_rate.cu: 78 clk/MMA with per-MMA descriptor arithmetic, 55 / 64 / 128 clk
+// for N = 64 / 128 / 256 with precomputed words). Kernels therefore precompute the hi words and add byte offsets
+// (>> 4) to the lo word, whose low 14 bits hold the start address.
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(

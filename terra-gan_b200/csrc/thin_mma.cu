@@ -427,9 +427,11 @@ tapwgrad_kernel(const __grid_constant__ TapWgradParams p, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp (warp-uniform addressing); one elected lane issues
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);     // A K-major, B (= Y) MN-major
-      const uint32_t a_addr = smem_u32(s_a), y_addr = smem_u32(s_y);
+      const uint64_t da0 = make_smem_desc(smem_u32(s_a), 16, 1024), dy0 = make_smem_desc(smem_u32(s_y), 16384, 1024);
+      const uint32_t a_lo0 = static_cast<uint32_t>(da0), a_hi = static_cast<uint32_t>(da0 >> 32);
+      const uint32_t y_lo0 = static_cast<uint32_t>(dy0), y_hi = static_cast<uint32_t>(dy0 >> 32);
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
@@ -437,20 +439,22 @@ tapwgrad_kernel(const __grid_constant__ TapWgradParams p, const __grid_constant_
         mbar_wait(&full_y[stage], phase);
         mbar_wait(&full_a[stage], phase);
         tc_fence_after();
+        const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * (32768 >> 4);
+        const uint32_t y_lo = y_lo0 + static_cast<uint32_t>(stage) * (16384 >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t da = make_smem_desc(a_addr + stage * 32768 + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc(y_addr + stage * 16384 + ks * 2048, 16384, 1024);
-          umma_bf16(tmem, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16_lh(tmem, a_lo + (ks >> 2) * (16384 >> 4) + (ks & 3) * 2, a_hi, y_lo + ks * 128, y_hi, idesc,
+                         ks ? 1u : (first ? 0u : 1u));
+          umma_commit(&empty[stage]);
         }
         first = false;
-        umma_commit(&empty[stage]);
         if (++stage == kTwStages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(done);
+      if (elect_one()) umma_commit(done);
     }
   } else if (warp >= 4) {
     const int j = (tid - 128) & 127;             // pixel of the tile (= TMEM lane at read-out for group 0)
@@ -714,26 +718,28 @@ tapdot_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp (warp-uniform addressing); one elected lane issues
       constexpr uint32_t idesc = make_idesc_bf16(128, kTdN, false, false);
-      const uint32_t w_addr = smem_u32(s_w), x_addr = smem_u32(s_x);
+      const uint64_t dw0 = make_smem_desc(smem_u32(s_w), 16, 1024), dx0 = make_smem_desc(smem_u32(s_x), 16, 1024);
+      const uint32_t w_lo0 = static_cast<uint32_t>(dw0), x_lo0 = static_cast<uint32_t>(dx0), d_hi = static_cast<uint32_t>(dw0 >> 32);
       for (unsigned i = 0; i < my_tiles; ++i) {
         const int stage = static_cast<int>(i % kTdStages);
         const int acc = static_cast<int>(i & 1u);
         mbar_wait(&tempty[acc], ((i >> 1) & 1u) ^ 1u);
         mbar_wait(&full[stage], (i / kTdStages) & 1u);
         tc_fence_after();
+        const uint32_t x_lo = x_lo0 + static_cast<uint32_t>(stage) * (kTdN * 128 >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {
+          for (int part = 0; part < 2; ++part) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t da = make_smem_desc(w_addr + part * 16384 + ks * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(x_addr + stage * kTdN * 128 + ks * 32, 16, 1024);
-            umma_bf16(tmem + acc * kTdN, da, db, idesc, (part | ks) ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16_lh(tmem + acc * kTdN, w_lo0 + part * (16384 >> 4) + ks * 2, d_hi, x_lo + ks * 2, d_hi, idesc,
+                           (part | ks) ? 1u : 0u);
           }
+          umma_commit(&empty[stage]);
+          umma_commit(&tfull[acc]);
         }
-        umma_commit(&empty[stage]);
-        umma_commit(&tfull[acc]);
       }
     }
   } else if (warp == 4 || warp == 8) {

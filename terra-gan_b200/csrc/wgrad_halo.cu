@@ -87,8 +87,24 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, warp-uniform addressing; one elected lane issues the tcgen05 instructions
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, true);
+      // Per tap pair j: A starts at halo row row0[2j] (+ 2*10 rows per 16-pixel step) with the second tap LBO =
+      // (row0[2j+1] - row0[2j]) rows further. All descriptor words are formed once; the loop adds offsets >> 4.
+      const uint32_t smem0 = smem_u32(smem);
+      uint32_t a_off[5], a_hi[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int r0 = p.row0[2 * j], r1 = p.row0[2 * j + 1];
+        const uint64_t d = make_smem_desc(smem0, (r1 - r0) * 128, 1280);
+        a_hi[j] = static_cast<uint32_t>(d >> 32);
+        // lo word = start | LBO << 16: keep the LBO part here, the start address is added per stage
+        a_off[j] = (static_cast<uint32_t>(d) - ((smem0 & 0x3FFFF) >> 4)) + static_cast<uint32_t>(r0) * 8u;
+      }
+      const uint64_t dg = make_smem_desc(smem0, 1024, 1024);
+      const uint32_t g_hi = static_cast<uint32_t>(dg >> 32);
+      const uint32_t x_lo0 = (smem0 & 0x3FFFF) >> 4;
+      const uint32_t g_rel = (static_cast<uint32_t>(dg) - x_lo0) + (kWhXBytes >> 4);
       int stage = 0;
       uint32_t phase = 0, uphase = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
@@ -99,25 +115,25 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t x_addr = smem_u32(smem + stage * kWhStageBytes);
-          const uint32_t g_addr = x_addr + kWhXBytes;
+          const uint32_t x_lo = x_lo0 + static_cast<uint32_t>(stage) * (kWhStageBytes >> 4);
+          const uint32_t g_lo = x_lo + g_rel;
+          const uint32_t accum = static_cast<uint32_t>(kb > kb_begin);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {        // 16 pixels = two rows of the 8x8 box per MMA
-            const uint64_t db = make_smem_desc(g_addr + k * 2048, 1024, 1024);
+            for (int k = 0; k < 4; ++k) {        // 16 pixels = two rows of the 8x8 box per MMA
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {      // tap pairs (2j, 2j+1)
-              const int r0 = p.row0[2 * j], r1 = p.row0[2 * j + 1];
-              const uint64_t da = make_smem_desc(x_addr + (r0 + 2 * k * 10) * 128, (r1 - r0) * 128, 1280);
-              umma_bf16(tmem_base + j * 64, da, db, idesc, (kb > kb_begin) || (k > 0));
+              for (int j = 0; j < 5; ++j)        // tap pairs (2j, 2j+1)
+                umma_bf16_lh(tmem_base + j * 64, x_lo + a_off[j] + k * 160, a_hi[j], g_lo + k * 128, g_hi, idesc,
+                             k ? 1u : accum);
             }
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
           if (++stage == kWhStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(tfull_bar);
+        if (elect_one()) umma_commit(tfull_bar);
         uphase ^= 1;
       }
     }

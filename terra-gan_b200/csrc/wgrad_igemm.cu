@@ -115,8 +115,10 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, warp-uniform addressing; one elected lane issues the tcgen05 instructions
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, true, true);
+      const uint64_t d0 = make_smem_desc(smem_u32(smem), kBoxBytes, 1024);   // both operands MN-major, same strides
+      const uint32_t d_lo0 = static_cast<uint32_t>(d0), d_hi = static_cast<uint32_t>(d0 >> 32);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -131,22 +133,21 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * S::kStageBytes);
-          const uint32_t b_addr = a_addr + S::kABytes;
+          // 16 pixels (= 16 rows of 128 B = two 8-row swizzle atoms) per MMA: +2048 B = +128 in the lo word
+          const uint32_t a_lo = d_lo0 + static_cast<uint32_t>(stage) * (S::kStageBytes >> 4);
+          const uint32_t b_lo = a_lo + (S::kABytes >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // 16 pixels (= 16 rows of 128 B = two 8-row swizzle atoms) per MMA
-            const uint64_t da = make_smem_desc(a_addr + k * 2048, kBoxBytes, 1024);
-            const uint64_t db = make_smem_desc(b_addr + k * 2048, kBoxBytes, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb_begin) || (k > 0));
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lh(d_tmem, a_lo + k * 128, d_hi, b_lo + k * 128, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb > kb_begin));
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
           if (++stage == kWStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (elect_one()) umma_commit(&tfull_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
