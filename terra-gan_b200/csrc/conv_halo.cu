@@ -29,7 +29,7 @@ constexpr int kHaloVec = 128;                                // max output chann
 
 template <int BN>
 struct HaloCfg {
-  static constexpr int kStoreCols = (BN == 128) ? 64 : 32;
+  static constexpr int kStoreCols = 32;      // 32-column staging also for N = 128: the 64 -> 128 layer then fits with resident weights
 };
 
 struct HaloSmem {
@@ -259,7 +259,7 @@ bool conv_halo_eligible(const tg_conv_args* a) {
     if (a->tap_plane[t] != 0 || a->tap_dh[t] < -1 || a->tap_dh[t] > 1 || a->tap_dw[t] < -1 || a->tap_dw[t] > 1)
       return false;
   const long w_bytes = static_cast<long>(a->N) * a->Ktot * 2;
-  return HaloSmem::total(static_cast<int>(w_bytes), a->N == 128 ? 64 : 32, 2) <= 227 * 1024;
+  return HaloSmem::total(static_cast<int>(w_bytes), 32, 2) <= 227 * 1024;
 }
 
 int conv_halo_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st) {

@@ -243,11 +243,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 bool conv_halo_eligible(const tg_conv_args* a);                       // conv_halo.cu
 int conv_halo_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st);
+bool conv_halo_stream_eligible(const tg_conv_args* a);                // conv_halo_stream.cu
+int conv_halo_stream_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st);
 
 static bool halo_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TG_NO_HALO");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static bool halo_stream_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TG_NO_HALO_STREAM");
     v = (e != nullptr && e[0] == '1') ? 0 : 1;
   }
   return v == 1;
@@ -350,6 +361,8 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
 
   // small-N 3x3 stride-1 layers: halo-tile reuse + resident weights (conv_halo.cu)
   if (halo_enabled() && conv_halo_eligible(a)) return conv_halo_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
+  if (halo_enabled() != 0 && halo_stream_enabled() && conv_halo_stream_eligible(a))
+    return conv_halo_stream_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
 
   // A: channels-last activations as a 5-D tensor (C, W, H, P, B)
   CUtensorMap tmA, tmB;
