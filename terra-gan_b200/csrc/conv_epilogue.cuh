@@ -47,11 +47,37 @@ __device__ __forceinline__ void conv_epilogue_dispatch(int mode, F f) {
   }
 }
 
+// Per-tile inputs of the epilogue that come from global memory (ratio / mask code, gate row). They only depend on
+// the tile coordinates, so the callers fetch them BEFORE waiting for the accumulator: the loads then overlap the
+// MMAs of the tile instead of sitting on the epilogue's dependent chain.
+struct EpiPrefetch {
+  float rs;
+  uint4 g[4];
+};
+template <int BN, int MODE>
+__device__ __forceinline__ void conv_epilogue_prefetch(const ConvKParams& p, int nt, int sb, int tw, int th, int tb, int hsel,
+                                                       int wt, int ht, int bt, EpiPrefetch& pre) {
+  constexpr bool kGen = MODE < 0;
+  const bool f_code = kGen ? (p.code != nullptr) : ((MODE & kEpiCode) != 0);
+  const bool f_gate = kGen ? (p.gate != nullptr) : ((MODE & kEpiGate) != 0);
+  const int w = tw * p.Wt + wt, h = th * p.Ht + ht, b = tb * p.Bt + bt;
+  const bool valid = (w < p.Wo) && (h < p.Ho) && (b < p.B);
+  const long pix = ((static_cast<long>(b) * p.Po + p.sub[sb].out_plane) * p.Ho + h) * p.Wo + w;
+  pre.rs = 1.f;
+  if (f_code && valid) pre.rs = p.lut[p.code[pix]];
+  if (BN == 64 && f_gate && valid) {
+    const uint4* gsrc = reinterpret_cast<const uint4*>(p.gate + pix * p.Cout + nt * BN + hsel * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pre.g[j] = gsrc[j];
+  }
+}
+
 template <int BN, int kVec, int kSC, int MODE>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, int lane, int nt, int sb, int tw,
                                                    int th, int tb, uint32_t t_addr, const float* s_vec,
                                                    float* my_stats, bool has_vec, uint8_t* stage, int hsel,
-                                                   int wt, int ht, int bt) {
+                                                   int wt, int ht, int bt, float* racc = nullptr,
+                                                   const EpiPrefetch* pre = nullptr) {
   static_assert(kSC == 32 || kSC == 64, "staging width is 32 or 64 columns");
   constexpr int kLPR = kSC / 8;           // 16-byte chunks (= lanes) per staged row
   constexpr int kRowBytes = kSC * 2;
@@ -72,7 +98,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
   const long pix =
       ((static_cast<long>(b) * p.Po + p.sub[sb].out_plane) * p.Ho + h) * p.Wo + w;
   float rs = 1.f;
-  if (f_code && valid) rs = p.lut[p.code[pix]];
+  if (f_code && valid) rs = pre ? pre->rs : p.lut[p.code[pix]];
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   const bool has_affine = kGen ? (p.scale != nullptr || p.shift != nullptr) : ((MODE & kEpiAffine) != 0);
   const int sw_w = (kSC == 64) ? (lane & 7) : ((lane >> 1) & 3);     // write-side swizzle key of this row
@@ -112,16 +138,26 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
       for (int j = 0; j < 32; ++j) v[j] *= rsv;
     }
     if (f_stats) {
-      float sq[32], sm[32];
+      if (BN == 64 && racc != nullptr) {
+        // one chunk per warp: per-thread running sums over all tiles (64 registers, independent FMAs); the caller
+        // reduces them across lanes once at the end of the kernel instead of 62 dependent shuffles per tile
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        sm[j] = v[j];
-        sq[j] = v[j] * v[j];
+        for (int j = 0; j < 32; ++j) {
+          racc[j] += v[j];
+          racc[32 + j] = fmaf(v[j], v[j], racc[32 + j]);
+        }
+      } else {
+        float sq[32], sm[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          sm[j] = v[j];
+          sq[j] = v[j] * v[j];
+        }
+        const float csum = warp_transpose_sum32(sm);
+        const float csq = warp_transpose_sum32(sq);
+        my_stats[n0 + lane] += csum;
+        my_stats[kVec + n0 + lane] += csq;
       }
-      const float csum = warp_transpose_sum32(sm);
-      const float csq = warp_transpose_sum32(sq);
-      my_stats[n0 + lane] += csum;
-      my_stats[kVec + n0 + lane] += csq;
     }
     uint32_t packed[16];
     uint32_t gbits[16];
@@ -129,7 +165,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
       const uint4* gsrc = reinterpret_cast<const uint4*>(grow + ch * 32);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 t = gsrc[j];
+        const uint4 t = (BN == 64 && pre) ? pre->g[j] : gsrc[j];
         gbits[4 * j] = t.x; gbits[4 * j + 1] = t.y; gbits[4 * j + 2] = t.z; gbits[4 * j + 3] = t.w;
       }
     }

@@ -189,6 +189,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;                     // row of the tile = pixel in box order (8 wide, 16 high)
     const int e_wt = row % kHaloW, e_ht = row / kHaloW, e_bt = 0;
     const int epi_mode = conv_epilogue_mode(p.code, p.stats, p.gate, p.scale, p.shift, p.bias);
+    float racc[BN == 64 ? 64 : 1];
+#pragma unroll
+    for (int j = 0; j < (BN == 64 ? 64 : 1); ++j) racc[j] = 0.f;
     conv_epilogue_dispatch(epi_mode, [&](auto mode_tag) {
       constexpr int kMode = decltype(mode_tag)::value;
       int acc = 0;
@@ -197,12 +200,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int tw = tile % p.tiles_w;
         const int th = (tile / p.tiles_w) % p.tiles_h;
         const int tb = tile / (p.tiles_w * p.tiles_h);
+        EpiPrefetch pre;
+        conv_epilogue_prefetch<BN, kMode>(p, 0, 0, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
         if (!(p.debug & 2))
           conv_epilogue_tile<BN, kHaloVec, kSC, kMode>(p, q, lane, 0, 0, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
-                                                       s_out + (warp - 4) * (32 * kSC * 2), hsel, e_wt, e_ht, e_bt);
+                                                       s_out + (warp - 4) * (32 * kSC * 2), hsel, e_wt, e_ht, e_bt,
+                                                       BN == 64 ? racc : nullptr, &pre);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -212,6 +218,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     });
+    if (BN == 64 && p.stats != nullptr) {
+      // flush the per-thread running sums: this warp owns columns hsel*32 .. +31 of its lane quarter's rows
+      float sm[32], sq[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        sm[j] = racc[j];
+        sq[j] = racc[(BN == 64 ? 32 : 0) + j];
+      }
+      const float csum = warp_transpose_sum32(sm);
+      const float csq = warp_transpose_sum32(sq);
+      my_stats[hsel * 32 + lane] += csum;
+      my_stats[kHaloVec + hsel * 32 + lane] += csq;
+    }
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int et = threadIdx.x - 128;

@@ -180,28 +180,49 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int row = q * 32 + lane;
     const int e_wt = row % kHsW, e_ht = row / kHsW, e_bt = 0;
     const int epi_mode = conv_epilogue_mode(p.code, p.stats, p.gate, p.scale, p.shift, p.bias);
+    float racc[BN == 64 ? 64 : 1];
+#pragma unroll
+    for (int j = 0; j < (BN == 64 ? 64 : 1); ++j) racc[j] = 0.f;
     conv_epilogue_dispatch(epi_mode, [&](auto mode_tag) {
       constexpr int kMode = decltype(mode_tag)::value;
       uint32_t ucount = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++ucount) {
         const int nt = (2 * u + 1 < total_tiles) ? 2 : 1;
         const int set = ucount & 1u;
+        const int tile0 = 2 * u, tile1 = 2 * u + (nt - 1);
+        const int tw0 = tile0 % p.tiles_w, th0 = (tile0 / p.tiles_w) % p.tiles_h, tb0 = tile0 / (p.tiles_w * p.tiles_h);
+        const int tw1 = tile1 % p.tiles_w, th1 = (tile1 / p.tiles_w) % p.tiles_h, tb1 = tile1 / (p.tiles_w * p.tiles_h);
+        EpiPrefetch pre0, pre1;
+        conv_epilogue_prefetch<BN, kMode>(p, 0, 0, tw0, th0, tb0, hsel, e_wt, e_ht, e_bt, pre0);
+        conv_epilogue_prefetch<BN, kMode>(p, 0, 0, tw1, th1, tb1, hsel, e_wt, e_ht, e_bt, pre1);
         mbar_wait(&tfull[set], (ucount >> 1) & 1u);
         tc_fence_after();
-        for (int mt = 0; mt < nt; ++mt) {
-          const int tile = 2 * u + mt;
-          const int tw = tile % p.tiles_w;
-          const int th = (tile / p.tiles_w) % p.tiles_h;
-          const int tb = tile / (p.tiles_w * p.tiles_h);
-          const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * 2 * BN + mt * BN;
-          conv_epilogue_tile<BN, kHsVec, kSC, kMode>(p, q, lane, 0, 0, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
-                                                     s_out + (warp - 4) * (32 * kSC * 2), hsel, e_wt, e_ht, e_bt);
-        }
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * 2 * BN;
+        conv_epilogue_tile<BN, kHsVec, kSC, kMode>(p, q, lane, 0, 0, tw0, th0, tb0, t_addr, s_vec, my_stats, has_vec,
+                                                   s_out + (warp - 4) * (32 * kSC * 2), hsel, e_wt, e_ht, e_bt,
+                                                   BN == 64 ? racc : nullptr, &pre0);
+        if (nt == 2)
+          conv_epilogue_tile<BN, kHsVec, kSC, kMode>(p, q, lane, 0, 0, tw1, th1, tb1, t_addr + BN, s_vec, my_stats, has_vec,
+                                                     s_out + (warp - 4) * (32 * kSC * 2), hsel, e_wt, e_ht, e_bt,
+                                                     BN == 64 ? racc : nullptr, &pre1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[set]);
       }
     });
+    if (BN == 64 && p.stats != nullptr) {
+      // flush the per-thread running sums: this warp owns columns hsel*32 .. +31 of its lane quarter's rows
+      float sm[32], sq[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        sm[j] = racc[j];
+        sq[j] = racc[(BN == 64 ? 32 : 0) + j];
+      }
+      const float csum = warp_transpose_sum32(sm);
+      const float csq = warp_transpose_sum32(sq);
+      my_stats[hsel * 32 + lane] += csum;
+      my_stats[kHsVec + hsel * 32 + lane] += csq;
+    }
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int et = threadIdx.x - 128;

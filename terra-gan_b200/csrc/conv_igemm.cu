@@ -198,12 +198,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tw = mt % p.tiles_w;
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tb = mt / (p.tiles_w * p.tiles_h);
+        EpiPrefetch pre;
+        conv_epilogue_prefetch<BN, kMode>(p, nt, sb, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
         conv_epilogue_tile<BN, 512, S::kStoreCols, kMode>(p, q, lane, nt, sb, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
                                                           s_out + (warp - 4) * (32 * S::kStoreCols * 2), hsel, e_wt, e_ht,
-                                                          e_bt);
+                                                          e_bt, nullptr, &pre);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
