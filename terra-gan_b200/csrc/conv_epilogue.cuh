@@ -54,9 +54,9 @@ struct EpiPrefetch {
   float rs;
   uint4 g[4];
 };
-template <int BN, int MODE>
-__device__ __forceinline__ void conv_epilogue_prefetch(const ConvKParams& p, int nt, int sb, int tw, int th, int tb, int hsel,
-                                                       int wt, int ht, int bt, EpiPrefetch& pre) {
+template <int BN, int MODE, bool kBox8 = false>
+__device__ __forceinline__ void conv_epilogue_prefetch(const ConvKParams& p, int q, int lane, int nt, int sb, int tw, int th,
+                                                       int tb, int hsel, int wt, int ht, int bt, EpiPrefetch& pre) {
   constexpr bool kGen = MODE < 0;
   const bool f_code = kGen ? (p.code != nullptr) : ((MODE & kEpiCode) != 0);
   const bool f_gate = kGen ? (p.gate != nullptr) : ((MODE & kEpiGate) != 0);
@@ -65,14 +65,22 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const ConvKParams& p, int
   const long pix = ((static_cast<long>(b) * p.Po + p.sub[sb].out_plane) * p.Ho + h) * p.Wo + w;
   pre.rs = 1.f;
   if (f_code && valid) pre.rs = p.lut[p.code[pix]];
-  if (BN == 64 && f_gate && valid) {
-    const uint4* gsrc = reinterpret_cast<const uint4*>(p.gate + pix * p.Cout + nt * BN + hsel * 32);
+  if (kBox8 && BN == 64 && f_gate) {
+    // N = 64 halo kernels (8 x 16 pixel boxes, always inside the image): fetch the gate in the layout of the
+    // transposed output store -- lane = (row i*8 + lane/4, 16-byte chunk lane%4) -- so that every load instruction
+    // reads 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes
+    const long tile_pix = ((static_cast<long>(tb) * p.Po + p.sub[sb].out_plane) * p.Ho + th * p.Ht) * p.Wo + tw * p.Wt;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) pre.g[j] = gsrc[j];
+    for (int i = 0; i < 4; ++i) {
+      const int rr = q * 32 + i * 8 + (lane >> 2);
+      const long px = tile_pix + static_cast<long>(rr >> 3) * p.Wo + (rr & 7);
+      const uint4* src = reinterpret_cast<const uint4*>(p.gate + px * p.Cout + nt * BN + hsel * 32 + (lane & 3) * 8);
+      pre.g[i] = (p.debug & 16) ? make_uint4(0x3f803f80u, 0x3f803f80u, 0xbf80bf80u, 0x3f803f80u) : *src;
+    }
   }
 }
 
-template <int BN, int kVec, int kSC, int MODE>
+template <int BN, int kVec, int kSC, int MODE, bool kBox8 = false>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, int lane, int nt, int sb, int tw,
                                                    int th, int tb, uint32_t t_addr, const float* s_vec,
                                                    float* my_stats, bool has_vec, uint8_t* stage, int hsel,
@@ -103,6 +111,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
   const bool has_affine = kGen ? (p.scale != nullptr || p.shift != nullptr) : ((MODE & kEpiAffine) != 0);
   const int sw_w = (kSC == 64) ? (lane & 7) : ((lane >> 1) & 3);     // write-side swizzle key of this row
   const __nv_bfloat16* grow = f_gate ? p.gate + pix * p.Cout + nt * BN : nullptr;
+  const bool relu_gate = f_gate && p.gate_slope == 0.f && p.act == 0;
+  const bool gate_t = kBox8 && BN == 64 && kSC == 32 && f_gate && pre != nullptr;   // gate prefetched in store layout
 
   // two warps share each TMEM lane quarter: warp `hsel` takes every other kSC-column group
 #pragma unroll 1
@@ -161,11 +171,11 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
     }
     uint32_t packed[16];
     uint32_t gbits[16];
-    if (f_gate && valid) {
+    if (f_gate && valid && !gate_t) {
       const uint4* gsrc = reinterpret_cast<const uint4*>(grow + ch * 32);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 t = (BN == 64 && pre) ? pre->g[j] : gsrc[j];
+        const uint4 t = (p.debug & 16) ? make_uint4(0x3f803f80u, 0x3f803f80u, 0xbf80bf80u, 0x3f803f80u) : gsrc[j];
         gbits[4 * j] = t.x; gbits[4 * j + 1] = t.y; gbits[4 * j + 2] = t.z; gbits[4 * j + 3] = t.w;
       }
     }
@@ -178,8 +188,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
         a = a * sc2.x + sh2.x;
         c = c * sc2.y + sh2.y;
       }
-      if (f_gate && valid) {
-        // derivative of ReLU / LeakyReLU of the tensor this gradient flows into
+      if (f_gate && valid && !relu_gate && !gate_t) {
+        // derivative of LeakyReLU of the tensor this gradient flows into
         const float2 gv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gbits[j >> 1]));
         if (!(gv.x > 0.f)) a *= p.gate_slope;
         if (!(gv.y > 0.f)) c *= p.gate_slope;
@@ -191,7 +201,16 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
         a = a > 0.f ? a : a * p.slope;
         c = c > 0.f ? c : c * p.slope;
       }
-      packed[j >> 1] = pack_bf16x2(a, c);
+      uint32_t pk = pack_bf16x2(a, c);
+      if (f_gate && valid && relu_gate && !gate_t) {
+        // ReLU derivative (slope 0, no activation after it): multiply the packed result by [gate > 0] in {1, 0};
+        // exact, two packed instructions per element pair instead of unpack / compare / multiply per element
+        const __nv_bfloat162 on = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&gbits[j >> 1]),
+                                         __floats2bfloat162_rn(0.f, 0.f));
+        const __nv_bfloat162 r2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&pk), on);
+        pk = *reinterpret_cast<const uint32_t*>(&r2);
+      }
+      packed[j >> 1] = pk;
     }
     {
       const int cbase = (ch % kChunksPerStage) * 4;
@@ -208,7 +227,28 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
         const int row = i * (32 / kLPR) + lane / kLPR;
         const int chunk = lane % kLPR;
         const int key = (kSC == 64) ? (row & 7) : ((row >> 1) & 3);
-        const uint4 val = *reinterpret_cast<const uint4*>(stage + row * kRowBytes + ((chunk ^ key) << 4));
+        uint4 val = *reinterpret_cast<const uint4*>(stage + row * kRowBytes + ((chunk ^ key) << 4));
+        if (gate_t) {
+          // derivative of (Leaky)ReLU on the packed bf16 pairs: factor 1 where gate > 0, else the slope
+          const uint4 g4 = pre->g[i & 3];
+          const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+          const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+          uint32_t vw[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 on = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]), zero2);
+            const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&vw[e]);
+            __nv_bfloat162 r2;
+            if (p.gate_slope == 0.f) {
+              r2 = __hmul2(x2, on);
+            } else {   // LeakyReLU: fp32 multiply by the slope, rounded once
+              const float2 xf = __bfloat1622float2(x2), of = __bfloat1622float2(on);
+              r2 = __floats2bfloat162_rn(of.x > 0.f ? xf.x : xf.x * p.gate_slope, of.y > 0.f ? xf.y : xf.y * p.gate_slope);
+            }
+            vw[e] = *reinterpret_cast<const uint32_t*>(&r2);
+          }
+          val = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+        }
         // pixel index of the row this lane stores: held by lane `row` of the warp
         const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(pix & 0xffffffffu), row);
         const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(static_cast<unsigned long long>(pix) >> 32), row);

@@ -201,12 +201,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int th = (tile / p.tiles_w) % p.tiles_h;
         const int tb = tile / (p.tiles_w * p.tiles_h);
         EpiPrefetch pre;
-        conv_epilogue_prefetch<BN, kMode>(p, 0, 0, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);
+        conv_epilogue_prefetch<BN, kMode, true>(p, q, lane, 0, 0, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
         if (!(p.debug & 2))
-          conv_epilogue_tile<BN, kHaloVec, kSC, kMode>(p, q, lane, 0, 0, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
+          conv_epilogue_tile<BN, kHaloVec, kSC, kMode, true>(p, q, lane, 0, 0, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
                                                        s_out + (warp - 4) * (32 * kSC * 2), hsel, e_wt, e_ht, e_bt,
                                                        BN == 64 ? racc : nullptr, &pre);
         tc_fence_before();

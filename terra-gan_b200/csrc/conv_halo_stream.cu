@@ -193,16 +193,16 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int tw0 = tile0 % p.tiles_w, th0 = (tile0 / p.tiles_w) % p.tiles_h, tb0 = tile0 / (p.tiles_w * p.tiles_h);
         const int tw1 = tile1 % p.tiles_w, th1 = (tile1 / p.tiles_w) % p.tiles_h, tb1 = tile1 / (p.tiles_w * p.tiles_h);
         EpiPrefetch pre0, pre1;
-        conv_epilogue_prefetch<BN, kMode>(p, 0, 0, tw0, th0, tb0, hsel, e_wt, e_ht, e_bt, pre0);
-        conv_epilogue_prefetch<BN, kMode>(p, 0, 0, tw1, th1, tb1, hsel, e_wt, e_ht, e_bt, pre1);
+        conv_epilogue_prefetch<BN, kMode, true>(p, q, lane, 0, 0, tw0, th0, tb0, hsel, e_wt, e_ht, e_bt, pre0);
+        conv_epilogue_prefetch<BN, kMode, true>(p, q, lane, 0, 0, tw1, th1, tb1, hsel, e_wt, e_ht, e_bt, pre1);
         mbar_wait(&tfull[set], (ucount >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * 2 * BN;
-        conv_epilogue_tile<BN, kHsVec, kSC, kMode>(p, q, lane, 0, 0, tw0, th0, tb0, t_addr, s_vec, my_stats, has_vec,
+        conv_epilogue_tile<BN, kHsVec, kSC, kMode, true>(p, q, lane, 0, 0, tw0, th0, tb0, t_addr, s_vec, my_stats, has_vec,
                                                    s_out + (warp - 4) * (32 * kSC * 2), hsel, e_wt, e_ht, e_bt,
                                                    BN == 64 ? racc : nullptr, &pre0);
         if (nt == 2)
-          conv_epilogue_tile<BN, kHsVec, kSC, kMode>(p, q, lane, 0, 0, tw1, th1, tb1, t_addr + BN, s_vec, my_stats, has_vec,
+          conv_epilogue_tile<BN, kHsVec, kSC, kMode, true>(p, q, lane, 0, 0, tw1, th1, tb1, t_addr + BN, s_vec, my_stats, has_vec,
                                                      s_out + (warp - 4) * (32 * kSC * 2), hsel, e_wt, e_ht, e_bt,
                                                      BN == 64 ? racc : nullptr, &pre1);
         tc_fence_before();

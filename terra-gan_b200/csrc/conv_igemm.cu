@@ -199,7 +199,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tb = mt / (p.tiles_w * p.tiles_h);
         EpiPrefetch pre;
-        conv_epilogue_prefetch<BN, kMode>(p, nt, sb, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);
+        conv_epilogue_prefetch<BN, kMode>(p, q, lane, nt, sb, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
