@@ -246,6 +246,239 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stride-2 data gradient with N = 64 (the gradients of enc2 and of Discriminator model[2] w.r.t. their
+// parity-split inputs): four sub-problems, one per input parity, each a handful of taps with offsets in {-1,0,1}
+// on the SAME channels-last gradient tensor. One halo per 64-channel block serves all 16 / 25 taps; the weight
+// slabs stream through the ring; the four sub-problems accumulate in four TMEM accumulators and the epilogue
+// writes the four output planes. (The generic kernel runs them as four separate tile passes, re-fetching the
+// A tile per tap: ~110 B/clk/SM of operands, 400-530 TFLOP/s.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kS2Slots = 8;                                // 8 KB weight slabs
+constexpr int kS2HaloSlots = 3;
+constexpr int kS2Smem = kS2HaloSlots * kHsHaloBytes + kS2Slots * 8192 + (4 * 2 * kHsVec + 3 * kHsVec) * 4 + 8 * 32 * 32 * 2 + 1024 + 1024;
+
+__global__ void __launch_bounds__(384, 1)
+conv_halo_s2dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ ConvKParams p) {
+  constexpr int BN = 64, kSC = 32, kSlab = 8192;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_a = smem;
+  uint8_t* s_w = s_a + kS2HaloSlots * kHsHaloBytes;
+  float* s_stats = reinterpret_cast<float*>(s_w + kS2Slots * kSlab);
+  float* s_vec = s_stats + 4 * 2 * kHsVec;
+  uint8_t* s_out = reinterpret_cast<uint8_t*>(s_vec + 3 * kHsVec);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + 8 * 32 * kSC * 2);
+  uint64_t* hfull = bars;
+  uint64_t* hempty = bars + kS2HaloSlots;
+  uint64_t* bfull = bars + 2 * kS2HaloSlots;
+  uint64_t* bempty = bfull + kS2Slots;
+  uint64_t* tfull = bempty + kS2Slots;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* s_tapoff = tmem_slot + 2;                       // [kMaxTaps + 1] halo row offset of each tap, >> 4
+  int* s_sub = reinterpret_cast<int*>(s_tapoff + kMaxTaps + 2);   // [4][2] tap_begin, tap_count
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < 4 * 2 * kHsVec; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i <= kMaxTaps; i += blockDim.x)
+    s_tapoff[i] = i < kMaxTaps ? static_cast<uint32_t>((p.tap_dh[i] + 1) * (kHsW + 2) + (p.tap_dw[i] + 1)) * 8u : 0u;
+  if (threadIdx.x < 4) {
+    s_sub[2 * threadIdx.x] = p.sub[threadIdx.x].tap_begin;
+    s_sub[2 * threadIdx.x + 1] = p.sub[threadIdx.x].tap_count;
+  }
+  const bool has_vec = p.bias != nullptr || p.scale != nullptr || p.shift != nullptr;
+  if (has_vec) {
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+      s_vec[i] = p.bias ? p.bias[i] : 0.f;
+      s_vec[kHsVec + i] = p.scale ? p.scale[i] : 1.f;
+      s_vec[2 * kHsVec + i] = p.shift ? p.shift[i] : 0.f;
+    }
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kS2HaloSlots; ++i) {
+      mbar_init(&hfull[i], 1);
+      mbar_init(&hempty[i], 1);
+    }
+    for (int i = 0; i < kS2Slots; ++i) {
+      mbar_init(&bfull[i], 1);
+      mbar_init(&bempty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = p.tiles_b * p.tiles_h * p.tiles_w;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t hcount = 0, bcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tw = tile % p.tiles_w;
+        const int th = (tile / p.tiles_w) % p.tiles_h;
+        const int tb = tile / (p.tiles_w * p.tiles_h);
+        for (int cb = 0; cb < p.cin_blocks; ++cb, ++hcount) {
+          const int hs = hcount % kS2HaloSlots;
+          mbar_wait(&hempty[hs], ((hcount / kS2HaloSlots) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&hfull[hs], kHsRows * 128);
+          tma_load_5d(s_a + hs * kHsHaloBytes, &tmA, &hfull[hs], cb * 64, tw * kHsW - 1, th * kHsH - 1, 0, tb);
+          for (int sb = 0; sb < 4; ++sb) {
+            const ConvSubK sub = p.sub[sb];
+            for (int t = 0; t < sub.tap_count; ++t, ++bcount) {
+              const int slot = bcount % kS2Slots;
+              mbar_wait(&bempty[slot], ((bcount / kS2Slots) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&bfull[slot], kSlab);
+              tma_load_2d(s_w + slot * kSlab, &tmB, &bfull[slot], sub.k_off + (t * p.cin_blocks + cb) * 64, 0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+    const uint64_t da0 = make_smem_desc(smem_u32(s_a), 16, (kHsW + 2) * 128);
+    const uint64_t db0 = make_smem_desc(smem_u32(s_w), 16, 1024);
+    const uint32_t a_hi = static_cast<uint32_t>(da0 >> 32), b_hi = static_cast<uint32_t>(db0 >> 32);
+    const uint32_t a_lo0 = static_cast<uint32_t>(da0), b_lo0 = static_cast<uint32_t>(db0);
+    uint32_t hcount = 0, bcount = 0, ucount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ucount) {
+      const int set = ucount & 1u;
+      mbar_wait(&tempty[set], ((ucount >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int cb = 0; cb < p.cin_blocks; ++cb, ++hcount) {
+        const int hs = hcount % kS2HaloSlots;
+        mbar_wait(&hfull[hs], (hcount / kS2HaloSlots) & 1u);
+        const uint32_t a0 = a_lo0 + static_cast<uint32_t>(hs) * (kHsHaloBytes >> 4);
+        for (int sb = 0; sb < 4; ++sb) {
+          const int tb0 = s_sub[2 * sb], tcnt = s_sub[2 * sb + 1];
+          const uint32_t d = tmem_base + set * 4 * BN + sb * BN;
+          uint32_t off_next = s_tapoff[tb0];                 // tap offsets come one iteration ahead of their use
+          for (int t = 0; t < tcnt; ++t, ++bcount) {
+            const int bs = bcount % kS2Slots;
+            const uint32_t al = a0 + off_next;
+            off_next = s_tapoff[tb0 + t + 1];
+            mbar_wait(&bfull[bs], (bcount / kS2Slots) & 1u);
+            tc_fence_after();
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(bs) * (kSlab >> 4);
+            const uint32_t accum = static_cast<uint32_t>((cb | t) != 0);
+            if (elect_one()) {
+              if (!(p.debug & 4)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16_lh(d, al + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k ? 1u : accum);
+              }
+              umma_commit(&bempty[bs]);
+            }
+          }
+        }
+        if (elect_one()) umma_commit(&hempty[hs]);
+      }
+      if (elect_one()) umma_commit(&tfull[set]);
+    }
+  } else if (warp >= 4) {
+    const int q = (warp - 4) & 3;
+    const int hsel = (warp - 4) >> 2;
+    float* my_stats = s_stats + q * (2 * kHsVec);
+    const int row = q * 32 + lane;
+    const int e_wt = row % kHsW, e_ht = row / kHsW, e_bt = 0;
+    const int epi_mode = conv_epilogue_mode(p.code, nullptr, p.gate, p.scale, p.shift, p.bias);   // no statistics here
+    conv_epilogue_dispatch(epi_mode, [&](auto mode_tag) {
+      constexpr int kMode = decltype(mode_tag)::value;
+      uint32_t ucount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ucount) {
+        const int tw = tile % p.tiles_w;
+        const int th = (tile / p.tiles_w) % p.tiles_h;
+        const int tb = tile / (p.tiles_w * p.tiles_h);
+        const int set = ucount & 1u;
+        EpiPrefetch pre, nxt;
+        conv_epilogue_prefetch<BN, kMode, true>(p, q, lane, 0, 0, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);
+        mbar_wait(&tfull[set], (ucount >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * 4 * BN;
+        uint8_t* stg = s_out + (warp - 4) * (32 * kSC * 2);
+#pragma unroll 1
+        for (int sb = 0; sb < 4; ++sb) {
+          // the next plane's ratio code / gate rows are requested before this plane's tile is drained
+          if (sb < 3) conv_epilogue_prefetch<BN, kMode, true>(p, q, lane, 0, sb + 1, tw, th, tb, hsel, e_wt, e_ht, e_bt, nxt);
+          if (!(p.debug & 2))
+            conv_epilogue_tile<BN, kHsVec, kSC, kMode, true>(p, q, lane, 0, sb, tw, th, tb, t_addr + sb * BN, s_vec, my_stats,
+                                                             has_vec, stg, hsel, e_wt, e_ht, e_bt, nullptr, &pre);
+          pre = nxt;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[set]);
+      }
+    });
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// stride-2 data gradient, N = 64: P = 1 input, four output parity planes of the input's size, taps within +-1
+bool conv_halo_s2dgrad_eligible(const tg_conv_args* a) {
+  if (a->P != 1 || a->Po != 4 || a->num_sub != 4 || a->N != 64 || a->stats != nullptr) return false;
+  if (a->Ho != a->H || a->Wo != a->W || a->Ho % kHsH || a->Wo % kHsW) return false;
+  if (a->num_taps > TG_MAX_TAPS) return false;
+  for (int t = 0; t < a->num_taps; ++t)
+    if (a->tap_plane[t] != 0 || a->tap_dh[t] < -1 || a->tap_dh[t] > 1 || a->tap_dw[t] < -1 || a->tap_dw[t] > 1)
+      return false;
+  for (int s = 0; s < 4; ++s)
+    if (a->sub[s].tap_count < 1) return false;
+  return true;
+}
+
+int conv_halo_s2dgrad_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st) {
+  kp.Bt = 1;
+  kp.Ht = kHsH;
+  kp.Wt = kHsW;
+  kp.tiles_w = a->Wo / kHsW;
+  kp.tiles_h = a->Ho / kHsH;
+  kp.tiles_b = a->B;
+  kp.n_tiles = 1;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, 1, (uint64_t)a->B};
+    uint64_t str[4] = {(uint64_t)a->C * 2, (uint64_t)a->C * 2 * a->W, (uint64_t)a->C * 2 * a->W * a->H,
+                       (uint64_t)a->C * 2 * a->W * a->H};
+    uint32_t box[5] = {64, kHsW + 2, kHsH + 2, 1, 1};
+    if (make_tmap_bf16(&tmA, a->x, 5, dims, str, box) != 0) return -3;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->Ktot, (uint64_t)a->N};
+    uint64_t str[1] = {(uint64_t)a->Ktot * 2};
+    uint32_t box[2] = {64, 64};
+    if (make_tmap_bf16(&tmB, a->w, 2, dims, str, box) != 0) return -3;
+  }
+  const long total_tiles = (long)kp.tiles_b * kp.tiles_h * kp.tiles_w;
+  const int sms = num_sms();
+  const int grid = (int)(total_tiles < sms ? total_tiles : sms);
+  a->stats_rows_used = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_s2dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS2Smem));
+    attr_set = true;
+  }
+  conv_halo_s2dgrad_kernel<<<grid, 384, kS2Smem, st>>>(tmA, tmB, kp);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int BN>
 static int launch_halo_stream(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKParams& kp, int grid, cudaStream_t st) {
   static bool attr_set = false;

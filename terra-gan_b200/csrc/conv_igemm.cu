@@ -247,6 +247,8 @@ bool conv_halo_eligible(const tg_conv_args* a);                       // conv_ha
 int conv_halo_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st);
 bool conv_halo_stream_eligible(const tg_conv_args* a);                // conv_halo_stream.cu
 int conv_halo_stream_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st);
+bool conv_halo_s2dgrad_eligible(const tg_conv_args* a);
+int conv_halo_s2dgrad_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st);
 
 static bool halo_enabled() {
   static int v = -1;
@@ -365,6 +367,8 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   if (halo_enabled() && conv_halo_eligible(a)) return conv_halo_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
   if (halo_enabled() != 0 && halo_stream_enabled() && conv_halo_stream_eligible(a))
     return conv_halo_stream_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
+  if (halo_enabled() != 0 && halo_stream_enabled() && conv_halo_s2dgrad_eligible(a))
+    return conv_halo_s2dgrad_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
 
   // A: channels-last activations as a 5-D tensor (C, W, H, P, B)
   CUtensorMap tmA, tmB;
