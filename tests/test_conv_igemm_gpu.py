@@ -148,3 +148,65 @@ def test_wgrad(Cin, Cout, k, s, p, H, B):
     assert rel_err(dw, dw_ref) < 1e-2
     ops.wgrad_igemm(xin, nhwc(g).unsqueeze(1).contiguous(), pl, blks, perm, dw, accumulate=True)
     assert rel_err(dw, 2 * dw_ref) < 1e-2
+
+
+# (Cin, Cout, k, stride, pad, H, W, B, slope): data gradient with the activation-derivative gate of the tensor the
+# gradient flows into, on every kernel that serves it: resident-weight halo (64->64), streaming halo (N = 128 with
+# large weights, N = 64 with 192 input channels of the forward layer), stride-2 halo (four parity planes) and the
+# generic kernel (N = 256). Non-square shapes give the halo kernels an odd number of 8x16 tiles.
+GATED = [
+    (64, 64, 3, 1, 1, 32, 32, 2, 0.0),
+    (64, 64, 3, 1, 1, 16, 24, 1, 0.2),
+    (128, 128, 3, 1, 1, 16, 24, 3, 0.0),
+    (64, 192, 3, 1, 1, 16, 16, 2, 0.0),
+    (64, 128, 4, 2, 1, 32, 32, 2, 0.2),
+    (64, 128, 5, 2, 2, 32, 48, 1, 0.0),
+    (256, 128, 3, 1, 1, 16, 16, 2, 0.0),
+]
+
+
+@pytest.mark.parametrize("Cin,Cout,k,s,p,H,W,B,slope", GATED)
+def test_dgrad_gate(Cin, Cout, k, s, p, H, W, B, slope):
+    torch.manual_seed(5)
+    dev = "cuda"
+    x = torch.randn(B, Cin, H, W, device=dev, requires_grad=True)
+    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cout * k * k) ** 0.5).bfloat16().float()
+    y = F.conv2d(x, w, None, s, p)
+    g = torch.randn_like(y).bfloat16()
+    (dx,) = torch.autograd.grad(y, x, g.float())
+    act_out = torch.randn(B, Cin, H, W, device=dev).bfloat16()          # output of the (Leaky)ReLU the input came through
+    factor = torch.where(act_out.float() > 0, torch.ones((), device=dev), torch.full((), slope, device=dev))
+    ref = nhwc(dx * factor)
+    pl = P.dgrad_plan(k, s, p)
+    wp = P.pack_w_dgrad(w, pl)
+    gin = nhwc(g).unsqueeze(1).contiguous()
+    if s == 1:
+        gate = nhwc(act_out).unsqueeze(1).contiguous()
+        out, _ = ops.conv_igemm(gin, wp, pl, (H, W), gate=gate, gate_slope=slope)
+        got = out[:, 0]
+    else:
+        gate = P.to_parity_split(nhwc(act_out))
+        out, _ = ops.conv_igemm(gin, wp, pl, (H // 2, W // 2), gate=gate, gate_slope=slope)
+        got = P.from_parity_split(out)
+    torch.cuda.synchronize()
+    assert rel_err(got, ref) < 1e-2
+
+
+# streaming-weights halo kernel with the full forward epilogue (ratio LUT, BN statistics) on a non-square grid
+@pytest.mark.parametrize("Cin,Cout,H,W,B", [(192, 64, 16, 24, 3), (384, 128, 32, 16, 1)])
+def test_fprop_stream_halo_lut_stats(Cin, Cout, H, W, B):
+    torch.manual_seed(6)
+    dev = "cuda"
+    x = torch.randn(B, Cin, H, W, device=dev).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device=dev) / (Cin * 9) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device=dev)
+    code = torch.randint(0, 10, (B, 1, H, W), device=dev, dtype=torch.uint8)
+    lut = P.ratio_lut(3)
+    pl = P.fprop_plan(3, 1, 1)
+    out, stats = ops.conv_igemm(nhwc(x).unsqueeze(1).contiguous(), P.pack_w_fprop(w.float()), pl, (H, W), code=code, lut=lut,
+                                bias=bias, want_stats=True)
+    z = nhwc(F.conv2d(x.float(), w.float(), bias, 1, 1)) * torch.tensor(lut, device=dev)[code.long()].reshape(B, H, W, 1)
+    assert rel_err(out[:, 0], z) < 1e-2
+    s = stats.double().sum(0)
+    assert rel_err(s[0], z.double().sum((0, 1, 2))) < 1e-3
+    assert rel_err(s[1], (z.double() ** 2).sum((0, 1, 2))) < 1e-3
