@@ -277,7 +277,7 @@ def run_ours(args):
         t = json.load(open(tpath))
         traffic = t["dram_gbytes"] * 1e9 / t["launches"]
         traffic_note = (f"dram__bytes_read+write: {t['dram_gbytes']:.1f} GB over the {t['launches']} tensor-core launches of one "
-                        f"B=64 step (profiles/r01_ncu_full_tensorcore_kernels.csv); bytes per launch (mean)")
+                        f"B=64 step (profiles/r01_ncu_tensorcore_step_metrics.csv); bytes per launch (mean)")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
