@@ -241,9 +241,12 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
             __nv_bfloat162 r2;
             if (p.gate_slope == 0.f) {
               r2 = __hmul2(x2, on);
-            } else {   // LeakyReLU: fp32 multiply by the slope, rounded once
-              const float2 xf = __bfloat1622float2(x2), of = __bfloat1622float2(on);
-              r2 = __floats2bfloat162_rn(of.x > 0.f ? xf.x : xf.x * p.gate_slope, of.y > 0.f ? xf.y : xf.y * p.gate_slope);
+            } else {   // LeakyReLU: fp32 multiply by the slope, rounded once; per-half select through a bit mask
+              const float2 xf = __bfloat1622float2(x2);
+              const __nv_bfloat162 s2 = __floats2bfloat162_rn(xf.x * p.gate_slope, xf.y * p.gate_slope);
+              const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]), zero2);
+              const uint32_t bits = (vw[e] & m) | (*reinterpret_cast<const uint32_t*>(&s2) & ~m);
+              r2 = *reinterpret_cast<const __nv_bfloat162*>(&bits);
             }
             vw[e] = *reinterpret_cast<const uint32_t*>(&r2);
           }

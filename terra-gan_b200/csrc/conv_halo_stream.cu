@@ -254,9 +254,9 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 // writes the four output planes. (The generic kernel runs them as four separate tile passes, re-fetching the
 // A tile per tap: ~110 B/clk/SM of operands, 400-530 TFLOP/s.)
 // ------------------------------------------------------------------------------------------------
-constexpr int kS2Slots = 8;                                // 8 KB weight slabs
+constexpr int kS2Slots = 4;                                // ring slots of two 8 KB weight slabs (two taps)
 constexpr int kS2HaloSlots = 3;
-constexpr int kS2Smem = kS2HaloSlots * kHsHaloBytes + kS2Slots * 8192 + (4 * 2 * kHsVec + 3 * kHsVec) * 4 + 8 * 32 * 32 * 2 + 1024 + 1024;
+constexpr int kS2Smem = kS2HaloSlots * kHsHaloBytes + kS2Slots * 2 * 8192 + (4 * 2 * kHsVec + 3 * kHsVec) * 4 + 8 * 32 * 32 * 2 + 1024 + 1024;
 
 __global__ void __launch_bounds__(384, 1)
 conv_halo_s2dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -266,7 +266,7 @@ conv_halo_s2dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* s_a = smem;
   uint8_t* s_w = s_a + kS2HaloSlots * kHsHaloBytes;
-  float* s_stats = reinterpret_cast<float*>(s_w + kS2Slots * kSlab);
+  float* s_stats = reinterpret_cast<float*>(s_w + kS2Slots * 2 * kSlab);
   float* s_vec = s_stats + 4 * 2 * kHsVec;
   uint8_t* s_out = reinterpret_cast<uint8_t*>(s_vec + 3 * kHsVec);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + 8 * 32 * kSC * 2);
@@ -277,13 +277,13 @@ conv_halo_s2dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tfull = bempty + kS2Slots;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint32_t* s_tapoff = tmem_slot + 2;                       // [kMaxTaps + 1] halo row offset of each tap, >> 4
-  int* s_sub = reinterpret_cast<int*>(s_tapoff + kMaxTaps + 2);   // [4][2] tap_begin, tap_count
+  uint32_t* s_tapoff = tmem_slot + 2;                       // [kMaxTaps + 4] halo row offset of each tap, >> 4
+  int* s_sub = reinterpret_cast<int*>(s_tapoff + kMaxTaps + 4);   // [4][2] tap_begin, tap_count
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   for (int i = threadIdx.x; i < 4 * 2 * kHsVec; i += blockDim.x) s_stats[i] = 0.f;
-  for (int i = threadIdx.x; i <= kMaxTaps; i += blockDim.x)
+  for (int i = threadIdx.x; i < kMaxTaps + 4; i += blockDim.x)
     s_tapoff[i] = i < kMaxTaps ? static_cast<uint32_t>((p.tap_dh[i] + 1) * (kHsW + 2) + (p.tap_dw[i] + 1)) * 8u : 0u;
   if (threadIdx.x < 4) {
     s_sub[2 * threadIdx.x] = p.sub[threadIdx.x].tap_begin;
@@ -337,11 +337,13 @@ conv_halo_s2dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tma_load_5d(s_a + hs * kHsHaloBytes, &tmA, &hfull[hs], cb * 64, tw * kHsW - 1, th * kHsH - 1, 0, tb);
           for (int sb = 0; sb < 4; ++sb) {
             const ConvSubK sub = p.sub[sb];
-            for (int t = 0; t < sub.tap_count; ++t, ++bcount) {
+            for (int t = 0; t < sub.tap_count; t += 2, ++bcount) {        // a ring slot holds the slabs of two taps
+              const int n = min(2, sub.tap_count - t);
               const int slot = bcount % kS2Slots;
               mbar_wait(&bempty[slot], ((bcount / kS2Slots) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(&bfull[slot], kSlab);
-              tma_load_2d(s_w + slot * kSlab, &tmB, &bfull[slot], sub.k_off + (t * p.cin_blocks + cb) * 64, 0);
+              mbar_arrive_expect_tx(&bfull[slot], n * kSlab);
+              for (int j = 0; j < n; ++j)
+                tma_load_2d(s_w + (slot * 2 + j) * kSlab, &tmB, &bfull[slot], sub.k_off + ((t + j) * p.cin_blocks + cb) * 64, 0);
             }
           }
         }
@@ -365,19 +367,26 @@ conv_halo_s2dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int sb = 0; sb < 4; ++sb) {
           const int tb0 = s_sub[2 * sb], tcnt = s_sub[2 * sb + 1];
           const uint32_t d = tmem_base + set * 4 * BN + sb * BN;
-          uint32_t off_next = s_tapoff[tb0];                 // tap offsets come one iteration ahead of their use
-          for (int t = 0; t < tcnt; ++t, ++bcount) {
+          uint32_t off0 = s_tapoff[tb0], off1 = s_tapoff[tb0 + 1];   // tap offsets come one iteration ahead of their use
+          for (int t = 0; t < tcnt; t += 2, ++bcount) {
             const int bs = bcount % kS2Slots;
-            const uint32_t al = a0 + off_next;
-            off_next = s_tapoff[tb0 + t + 1];
+            const bool two = t + 1 < tcnt;
+            const uint32_t al0 = a0 + off0, al1 = a0 + off1;
+            off0 = s_tapoff[tb0 + t + 2];
+            off1 = s_tapoff[tb0 + t + 3];
             mbar_wait(&bfull[bs], (bcount / kS2Slots) & 1u);
             tc_fence_after();
-            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(bs) * (kSlab >> 4);
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(bs) * (2 * kSlab >> 4);
             const uint32_t accum = static_cast<uint32_t>((cb | t) != 0);
             if (elect_one()) {
               if (!(p.debug & 4)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16_lh(d, al + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k ? 1u : accum);
+                for (int k = 0; k < 4; ++k) umma_bf16_lh(d, al0 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k ? 1u : accum);
+                if (two) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_lh(d, al1 + 2 * k, a_hi, b_lo + (kSlab >> 4) + 2 * k, b_hi, idesc, 1u);
+                }
               }
               umma_commit(&bempty[bs]);
             }
