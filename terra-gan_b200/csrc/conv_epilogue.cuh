@@ -24,7 +24,8 @@ __host__ __device__ inline int conv_epilogue_mode(const void* code, const void* 
   const int m = (code ? kEpiCode : 0) | (stats ? kEpiStats : 0) | (gate ? kEpiGate : 0) |
                 ((scale || shift) ? kEpiAffine : 0) | ((bias || scale || shift) ? kEpiVec : 0);
   switch (m) {
-    case 0: case kEpiCode: case kEpiGate: case kEpiVec: case kEpiVec | kEpiStats: case kEpiVec | kEpiCode | kEpiStats:
+    case 0: case kEpiCode: case kEpiGate: case kEpiVec: case kEpiVec | kEpiCode: case kEpiVec | kEpiStats:
+    case kEpiVec | kEpiCode | kEpiStats:
     case kEpiVec | kEpiAffine: case kEpiVec | kEpiCode | kEpiAffine:
       return m;
     default:
@@ -39,6 +40,7 @@ __device__ __forceinline__ void conv_epilogue_dispatch(int mode, F f) {
     case kEpiCode: f(std::integral_constant<int, kEpiCode>{}); break;
     case kEpiGate: f(std::integral_constant<int, kEpiGate>{}); break;
     case kEpiVec: f(std::integral_constant<int, kEpiVec>{}); break;
+    case kEpiVec | kEpiCode: f(std::integral_constant<int, kEpiVec | kEpiCode>{}); break;
     case kEpiVec | kEpiStats: f(std::integral_constant<int, kEpiVec | kEpiStats>{}); break;
     case kEpiVec | kEpiCode | kEpiStats: f(std::integral_constant<int, kEpiVec | kEpiCode | kEpiStats>{}); break;
     case kEpiVec | kEpiAffine: f(std::integral_constant<int, kEpiVec | kEpiAffine>{}); break;

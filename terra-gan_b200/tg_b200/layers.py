@@ -238,6 +238,16 @@ class GeneratorEngine:
             merged = ops.upsample_concat(up, skip, pyr.dec_mm[i])
             hh, ww = merged.shape[2], merged.shape[3]
             code = pyr.dec_s[i]
+            if not training and save is None:
+                # inference: running-statistics BatchNorm + ReLU folded into the conv epilogue (one pass less per layer)
+                scale, shift, _, _ = bn_coeffs(None, B * hh * ww, bns[name], False)
+                y, _ = ops.conv_igemm(merged, pk.w_fprop(params[name + ".input_conv.weight"]), pk.fplan, (hh, ww),
+                                      code=code, lut=pk.lut, bias=params[name + ".input_conv.bias"], scale=scale,
+                                      shift=shift, act=ACT_RELU)
+                if trace is not None:
+                    trace[name + ".y"] = y
+                up = y
+                continue
             z, stats = ops.conv_igemm(merged, pk.w_fprop(params[name + ".input_conv.weight"]), pk.fplan, (hh, ww),
                                       code=code, lut=pk.lut, bias=params[name + ".input_conv.bias"],
                                       want_stats=training)
