@@ -109,7 +109,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
       ((static_cast<long>(b) * p.Po + p.sub[sb].out_plane) * p.Ho + h) * p.Wo + w;
   float rs = 1.f;
   if (f_code && valid) rs = pre ? pre->rs : p.lut[p.code[pix]];
-  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const unsigned vmask = kBox8 ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
+  const long box_pix = ((static_cast<long>(tb) * p.Po + p.sub[sb].out_plane) * p.Ho + th * p.Ht) * p.Wo + tw * p.Wt;
   const bool has_affine = kGen ? (p.scale != nullptr || p.shift != nullptr) : ((MODE & kEpiAffine) != 0);
   const int sw_w = (kSC == 64) ? (lane & 7) : ((lane >> 1) & 3);     // write-side swizzle key of this row
   const __nv_bfloat16* grow = f_gate ? p.gate + pix * p.Cout + nt * BN : nullptr;
@@ -254,12 +255,20 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
           }
           val = make_uint4(vw[0], vw[1], vw[2], vw[3]);
         }
-        // pixel index of the row this lane stores: held by lane `row` of the warp
-        const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(pix & 0xffffffffu), row);
-        const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(static_cast<unsigned long long>(pix) >> 32), row);
-        if (((vmask >> row) & 1u) && !(p.debug & 1)) {
-          const long pix2 = static_cast<long>((static_cast<unsigned long long>(hi) << 32) | lo);
-          *reinterpret_cast<uint4*>(p.out + pix2 * p.Cout + col0 + chunk * 8) = val;
+        if (kBox8) {
+          // 8 x 16 pixel boxes that always lie inside the image: the row's pixel follows from the tile origin
+          // (no shuffles, no validity mask on the store path)
+          const int rr = q * 32 + row;
+          const long pix2 = box_pix + static_cast<long>(rr >> 3) * p.Wo + (rr & 7);
+          if (!(p.debug & 1)) *reinterpret_cast<uint4*>(p.out + pix2 * p.Cout + col0 + chunk * 8) = val;
+        } else {
+          // pixel index of the row this lane stores: held by lane `row` of the warp
+          const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(pix & 0xffffffffu), row);
+          const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(static_cast<unsigned long long>(pix) >> 32), row);
+          if (((vmask >> row) & 1u) && !(p.debug & 1)) {
+            const long pix2 = static_cast<long>((static_cast<unsigned long long>(hi) << 32) | lo);
+            *reinterpret_cast<uint4*>(p.out + pix2 * p.Cout + col0 + chunk * 8) = val;
+          }
         }
       }
       __syncwarp();

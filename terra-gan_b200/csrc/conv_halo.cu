@@ -196,10 +196,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr int kMode = decltype(mode_tag)::value;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int tw = tile % p.tiles_w;
-        const int th = (tile / p.tiles_w) % p.tiles_h;
-        const int tb = tile / (p.tiles_w * p.tiles_h);
+      TileWalk tk(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tk.next()) {
+        const int tw = tk.tw, th = tk.th, tb = tk.tb;
         EpiPrefetch pre;
         conv_epilogue_prefetch<BN, kMode, true>(p, q, lane, 0, 0, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);
         mbar_wait(&tfull_bar[acc], acc_phase);

@@ -186,12 +186,13 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     conv_epilogue_dispatch(epi_mode, [&](auto mode_tag) {
       constexpr int kMode = decltype(mode_tag)::value;
       uint32_t ucount = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x, ++ucount) {
+      TileWalk tk0(2 * blockIdx.x, 2 * gridDim.x, p.tiles_w, p.tiles_h);
+      TileWalk tk1(2 * blockIdx.x + 1, 2 * gridDim.x, p.tiles_w, p.tiles_h);
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++ucount, tk0.next(), tk1.next()) {
         const int nt = (2 * u + 1 < total_tiles) ? 2 : 1;
         const int set = ucount & 1u;
-        const int tile0 = 2 * u, tile1 = 2 * u + (nt - 1);
-        const int tw0 = tile0 % p.tiles_w, th0 = (tile0 / p.tiles_w) % p.tiles_h, tb0 = tile0 / (p.tiles_w * p.tiles_h);
-        const int tw1 = tile1 % p.tiles_w, th1 = (tile1 / p.tiles_w) % p.tiles_h, tb1 = tile1 / (p.tiles_w * p.tiles_h);
+        const int tw0 = tk0.tw, th0 = tk0.th, tb0 = tk0.tb;
+        const int tw1 = nt == 2 ? tk1.tw : tw0, th1 = nt == 2 ? tk1.th : th0, tb1 = nt == 2 ? tk1.tb : tb0;
         EpiPrefetch pre0, pre1;
         conv_epilogue_prefetch<BN, kMode, true>(p, q, lane, 0, 0, tw0, th0, tb0, hsel, e_wt, e_ht, e_bt, pre0);
         conv_epilogue_prefetch<BN, kMode, true>(p, q, lane, 0, 0, tw1, th1, tb1, hsel, e_wt, e_ht, e_bt, pre1);
@@ -406,10 +407,9 @@ conv_halo_s2dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     conv_epilogue_dispatch(epi_mode, [&](auto mode_tag) {
       constexpr int kMode = decltype(mode_tag)::value;
       uint32_t ucount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ucount) {
-        const int tw = tile % p.tiles_w;
-        const int th = (tile / p.tiles_w) % p.tiles_h;
-        const int tb = tile / (p.tiles_w * p.tiles_h);
+      TileWalk tk(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ucount, tk.next()) {
+        const int tw = tk.tw, th = tk.th, tb = tk.tb;
         const int set = ucount & 1u;
         EpiPrefetch pre, nxt;
         conv_epilogue_prefetch<BN, kMode, true>(p, q, lane, 0, 0, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);

@@ -44,6 +44,35 @@ struct ConvKParams {
   int debug;                      // perf experiments only: 1 no stores, 2 no epilogue work, 4 no MMA
 };
 
+#ifdef __CUDACC__
+// (tw, th, tb) of the tiles first, first + stride, ... without per-tile integer divisions (they sat on the
+// epilogue warps' dependent chain once per tile)
+struct TileWalk {
+  int tw, th, tb, dw, dh, db, nw, nh;
+  __device__ __forceinline__ TileWalk(int first, int stride, int tiles_w, int tiles_h) {
+    nw = tiles_w;
+    nh = tiles_h;
+    tw = first % nw;
+    int r = first / nw;
+    th = r % nh;
+    tb = r / nh;
+    dw = stride % nw;
+    r = stride / nw;
+    dh = r % nh;
+    db = r / nh;
+  }
+  __device__ __forceinline__ void next() {
+    tw += dw;
+    int c = tw >= nw ? 1 : 0;
+    tw -= c ? nw : 0;
+    th += dh + c;
+    c = th >= nh ? 1 : 0;
+    th -= c ? nh : 0;
+    tb += db + c;
+  }
+};
+#endif
+
 struct WgradBlk {                 // one 64-row block of dW^T: (tap, 64-channel block of the input)
   int8_t plane, dh, dw, pad;
   int cb;                         // input channel block
