@@ -237,6 +237,7 @@ def run_ours(args):
         loss_host.copy_(torch.stack([out["g_total_loss"], out["d_loss"]]), non_blocking=True)
         torch.cuda.current_stream().synchronize()     # the user reads the losses every step (train.py:222-225)
 
+    ops.profile_pool(2 * 100 * args.steps + 64)      # timing events for every tensor-core launch of the timed steps
     for _ in range(args.warmup):
         step_resident()
     # ---- timed region 1: resident inputs; tensor-core launches timed with CUDA events ----

@@ -17,14 +17,28 @@ from .plan import TapPlan
 BF16 = torch.bfloat16
 
 # bench.py sets PROFILE = [] to time every tensor-core launch with CUDA events on the launching stream:
-# entries are (kind, algorithmic FLOPs, start event, end event).
+# entries are (kind, algorithmic FLOPs, start event, end event). Events come from a pool created up front
+# (profile_pool): creating a timing event costs ~100 us of host time, which made the timed region CPU-bound.
 PROFILE = None
+_POOL: list = []
+
+
+def profile_pool(n_events: int) -> None:
+    """Pre-create `n_events` timing events (call before the timed region)."""
+    while len(_POOL) < n_events:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()                      # torch creates the CUDA event lazily, on the first record
+        _POOL.append(ev)
+
+
+def _event():
+    return _POOL.pop() if _POOL else torch.cuda.Event(enable_timing=True)
 
 
 def _prof_begin():
     if PROFILE is None:
         return None
-    ev = torch.cuda.Event(enable_timing=True)
+    ev = _event()
     ev.record()
     return ev
 
@@ -32,7 +46,7 @@ def _prof_begin():
 def _prof_end(kind: str, flops: float, ev0, shape: str = "") -> None:
     if ev0 is None:
         return
-    ev1 = torch.cuda.Event(enable_timing=True)
+    ev1 = _event()
     ev1.record()
     PROFILE.append((kind, flops, ev0, ev1, shape))
 
