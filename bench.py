@@ -161,8 +161,13 @@ def run_ours(args):
     D.to(dev).train()
     os.environ.setdefault("TERRA_VGG_SEED", "3")       # no network: seeded random VGG16[:16] weights
     criterion = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=dev)
-    opt_G = torch.optim.Adam(G.parameters(), lr=2e-4)
-    opt_D = torch.optim.Adam(D.parameters(), lr=2e-4)
+    if args.torch_adam:                                # the reference loops' optimizer object, unchanged
+        make_adam = lambda m, lr: torch.optim.Adam(m.parameters(), lr=lr)
+    else:                                              # same update, one fused kernel that also refreshes the packed weights
+        from tg_b200 import optim as tg_optim
+        make_adam = lambda m, lr: tg_optim.Adam(m.parameters(), lr=lr, modules=[m])
+    opt_G = make_adam(G, 2e-4)
+    opt_D = make_adam(D, 2e-4)
     reducer = None
     if world > 1:
         broadcast_module_state([G, D])
@@ -176,7 +181,7 @@ def run_ours(args):
                             "modes": {"human_guided": {"human_feedback_weight": 0.3, "base_loss_weight": 0.7,
                                                        "learning_rate": 1e-4}}}}
         hg_crit = HumanGuidedLoss(cfg, device=dev)
-        hg_stepper = HumanGuidedStep(G, hg_crit, torch.optim.Adam(G.parameters(), lr=1e-4), reducer)
+        hg_stepper = HumanGuidedStep(G, hg_crit, make_adam(G, 1e-4), reducer)
     if args.workload == "infer":       # BASELINE.json configs[1]: generator inference (evaluate.py:47-50)
         G.eval()
 
@@ -339,6 +344,7 @@ def main():
     ap.add_argument("--ref-graph", action="store_true",
                     help="also compute the discriminator weight gradients of the generator step (discarded by the reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam instead of tg_b200.optim.Adam")
     ap.add_argument("--workload", default="train", choices=["train", "infer", "hg"],
                     help="train: adversarial step (headline, configs[2]); infer: generator inference (configs[1]); "
                          "hg: human-guided fine-tune step (configs[4])")

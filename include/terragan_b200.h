@@ -256,6 +256,25 @@ int tg_l1_bf16_fwd(const void* a, const void* b, long n, float* partial, int row
 int tg_l1_bf16_bwd(const void* a, const void* b, long n, const float* grad_out, int relu_gate, void* ga,
                    void* stream);
 
+/* ---- fused Adam step + packed-weight refresh (adam_kernels.cu) ---------------------------------------
+ * Replaces torch.optim.Adam.step() of the reference loops (mvp_gan/src/train.py:207,219,
+ * training/human_guided_trainer.py:153; amsgrad off, weight_decay 0) for a list of fp32 parameter tensors and,
+ * for conv weights, writes the bf16 fprop / dgrad operand matrices in the same pass: packed[dst[i]] = bf16(p[i]).
+ * `tensors` is a HOST array; all pointers inside are device pointers. `step` is the 1-based step count. */
+typedef struct tg_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  void* packed_fprop;           /* bf16 or NULL */
+  const int32_t* dst_fprop;     /* [n] or NULL */
+  void* packed_dgrad;           /* bf16 or NULL */
+  const int32_t* dst_dgrad;     /* [n] or NULL */
+  int64_t n;
+} tg_adam_tensor;
+int tg_adam_repack(const tg_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2, float eps,
+                   int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,13 @@ class WgradArgs(C.Structure):
 
 # name -> (restype, argtypes). Every symbol include/terragan_b200.h declares appears here; the
 # CPU test-suite checks the library exports all of them.
+class AdamTensor(C.Structure):
+    """mirrors tg_adam_tensor"""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("packed_fprop", c_void_p), ("dst_fprop", c_void_p), ("packed_dgrad", c_void_p), ("dst_dgrad", c_void_p),
+                ("n", C.c_int64)]
+
+
 PROTOTYPES = {
     "tg_version": (c_int, []),
     "tg_last_error": (c_size_t, [C.c_char_p, c_size_t]),
@@ -104,6 +111,7 @@ PROTOTYPES = {
                                 C.POINTER(C.c_int8), C.POINTER(C.c_int8), c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_size_t, c_void_p]),
     "tg_conv_to1_fwd_scratch_floats": (C.c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "tg_adam_repack": (c_int, [C.POINTER(AdamTensor), c_int, C.c_float, C.c_float, C.c_float, C.c_float, c_int, c_void_p]),
     "tg_conv_to1_bwd_data": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, C.POINTER(C.c_int8),
                                      C.POINTER(C.c_int8), c_int, c_int, c_int, c_void_p, c_void_p]),
     "tg_conv_to1_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,

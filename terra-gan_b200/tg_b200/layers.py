@@ -57,6 +57,10 @@ class ConvPack:
                 self._wd = P.pack_w_dgrad(w, self.dplan)
             self._key = key
 
+    def mark_fresh(self, w: torch.Tensor) -> None:
+        """The packed copies were just written in place from `w` (tg_b200.optim.Adam): no re-pack needed."""
+        self._key = (w.data_ptr(), w._version, str(w.device))
+
     def w_fprop(self, w: torch.Tensor) -> torch.Tensor:
         self._refresh(w)
         return self._wf

@@ -13,7 +13,7 @@ mvp_gan/src/models/pconv.py:30 and mvp_gan/src/models/discriminator.py:11.
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Tuple
+from typing import Optional, List, Tuple
 
 import torch
 
@@ -77,19 +77,41 @@ def dgrad_plan(k: int, stride: int, pad: int) -> TapPlan:
     return TapPlan(taps, subs, kpos, 1, 4, k, stride, pad, False)
 
 
+def _arrange_fprop(w: torch.Tensor) -> torch.Tensor:
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+
+
+def _arrange_dgrad(w: torch.Tensor, plan: TapPlan) -> torch.Tensor:
+    co, ci, kh, kw = w.shape
+    wk = w.reshape(co, ci, kh * kw)                             # [co, ci, kpos]
+    idx = torch.as_tensor(plan.kpos, device=w.device, dtype=torch.long)
+    sel = wk.index_select(2, idx)                               # [co, ci, T]
+    return sel.permute(1, 2, 0).reshape(ci, len(plan.kpos) * co)
+
+
 def pack_w_fprop(w: torch.Tensor) -> torch.Tensor:
     """[Cout, Cin, kh, kw] fp32 -> bf16 [Cout, kh*kw*Cin] (tap-major, channel-minor)."""
-    co, ci, kh, kw = w.shape
-    return w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16).contiguous()
+    return _arrange_fprop(w.detach()).to(torch.bfloat16).contiguous()
 
 
 def pack_w_dgrad(w: torch.Tensor, plan: TapPlan) -> torch.Tensor:
     """[Cout, Cin, kh, kw] fp32 -> bf16 [Cin, T*Cout] in the tap order of `plan` (a dgrad plan)."""
-    co, ci, kh, kw = w.shape
-    wk = w.detach().reshape(co, ci, kh * kw)                  # [co, ci, kpos]
-    idx = torch.as_tensor(plan.kpos, device=w.device, dtype=torch.long)
-    sel = wk.index_select(2, idx)                               # [co, ci, T]
-    return sel.permute(1, 2, 0).reshape(ci, len(plan.kpos) * co).to(torch.bfloat16).contiguous()
+    return _arrange_dgrad(w.detach(), plan).to(torch.bfloat16).contiguous()
+
+
+def pack_scatter_index(shape, plan: Optional[TapPlan], device) -> torch.Tensor:
+    """int32 [numel]: position in the packed matrix (fprop layout if plan is None, else the dgrad layout of
+    `plan`) of every element of a [Cout, Cin, kh, kw] weight in its natural order. Both packings are
+    permutations, so a fused optimizer step can write the bf16 copies while it updates the fp32 master."""
+    n = 1
+    for d in shape:
+        n *= d
+    src = torch.arange(n, dtype=torch.int64, device=device).reshape(shape)
+    arranged = (_arrange_fprop(src) if plan is None else _arrange_dgrad(src, plan)).reshape(-1)
+    dst = torch.empty(n, dtype=torch.int32, device=device)
+    dst[arranged] = torch.arange(n, dtype=torch.int32, device=device)
+    return dst
 
 
 def to_parity_split(x: torch.Tensor) -> torch.Tensor:

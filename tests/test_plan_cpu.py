@@ -88,3 +88,17 @@ def test_ratio_lut_matches_reference_expression(k):
     lut = torch.tensor(P.ratio_lut(k))
     assert torch.equal(lut, ref)
     assert lut[0] == 0 and lut[k * k] == 1.0
+
+
+def test_pack_scatter_index_is_the_packing_permutation():
+    """tg_b200.optim.Adam writes packed[dst[i]] = bf16(w.flat[i]); dst must reproduce pack_w_fprop / pack_w_dgrad."""
+    torch.manual_seed(0)
+    for (co, ci, k, s, p) in [(8, 4, 3, 1, 1), (6, 2, 4, 2, 1), (4, 3, 5, 2, 2)]:
+        w = torch.randn(co, ci, k, k)
+        for plan in (None, P.dgrad_plan(k, s, p)):
+            dst = P.pack_scatter_index(w.shape, plan, "cpu")
+            want = (P.pack_w_fprop(w) if plan is None else P.pack_w_dgrad(w, plan)).reshape(-1)
+            got = torch.empty_like(want)
+            got[dst.long()] = w.reshape(-1).to(torch.bfloat16)
+            assert sorted(dst.tolist()) == list(range(w.numel()))
+            assert torch.equal(got, want)
