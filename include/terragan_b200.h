@@ -41,6 +41,9 @@ extern "C" {
 int tg_version(void);                               /* ABI version (this header: 1) */
 size_t tg_last_error(char* buf, size_t cap);        /* copies the last error text of this thread */
 int tg_num_sms(void);                               /* SM count of the current device (<=0: error) */
+/* Hit / miss counters of the calling thread's TMA tensor-map cache (descriptors are keyed by pointer, shape and
+ * box, SURVEY.md §8b "TMA descriptor cache keyed by pointer/shape"). */
+int tg_tmap_cache_stats(uint64_t* hits, uint64_t* misses);
 
 /* ---- mask pyramid -------------------------------------------------------------------------
  * Integer restatement of mask_conv + (>0) (pconv.py:33-40) and of the decoder mask merge
@@ -255,6 +258,14 @@ int tg_l1_bf16_fwd(const void* a, const void* b, long n, float* partial, int row
                    void* stream);
 int tg_l1_bf16_bwd(const void* a, const void* b, long n, const float* grad_out, int relu_gate, void* ga,
                    void* stream);
+/* nn.BCEWithLogitsLoss() (mean reduction) of the adversarial terms (train.py:115, used at :203, :215-216):
+ *   out[0] = mean_i( max(x_i,0) - x_i*t_i + log1p(exp(-|x_i|)) ),   grad_logits_i = grad_out[0]*(sigmoid(x_i)-t_i)/n.
+ * `target` is a device fp32 [n] or NULL, in which case every t_i = target_const (the loops pass
+ * torch.ones_like / torch.zeros_like). Deterministic (fixed summation order), no workspace. */
+int tg_bce_logits_fwd(const float* logits, const float* target, float target_const, long n, float* out,
+                      void* stream);
+int tg_bce_logits_bwd(const float* logits, const float* target, float target_const, long n,
+                      const float* grad_out, float* grad_logits, void* stream);
 
 /* ---- fused Adam step + packed-weight refresh (adam_kernels.cu) ---------------------------------------
  * Replaces torch.optim.Adam.step() of the reference loops (mvp_gan/src/train.py:207,219,

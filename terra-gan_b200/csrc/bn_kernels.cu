@@ -484,11 +484,7 @@ extern "C" int tg_bn_bwd_reduce(const tg_grad_src* g0, const tg_grad_src* g1, co
   const size_t ring_bytes = static_cast<size_t>(kRing) * 3 * 256 * 16;
   if (smem < ring_bytes) smem = ring_bytes;
   {
-    static bool attr = false;
-    if (!attr) {
-      TG_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr = true;
-    }
+    TG_SET_SMEM_ONCE((bn_bwd_reduce_kernel), 64 * 1024);
   }
   bn_bwd_reduce_kernel<<<static_cast<int>(grid), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       s0, s1, reinterpret_cast<const __nv_bfloat16*>(z), M, C, H, W, scale, shift, act, slope, code, lut_dev,
@@ -520,11 +516,7 @@ extern "C" int tg_bn_bwd_apply(const tg_grad_src* g0, const tg_grad_src* g1, con
   if (g1 && g1->ptr) s1 = to_src(*g1);
   else { s1.ptr = nullptr; s1.pix_stride = 0; s1.chan_off = 0; s1.split = 0; }
   {
-    static bool attr = false;
-    if (!attr) {
-      TG_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr = true;
-    }
+    TG_SET_SMEM_ONCE((bn_bwd_apply_kernel), 64 * 1024);
   }
   bn_bwd_apply_kernel<<<ew_grid(M * (C / 8), 256), 256, kRing * 3 * 256 * 16, reinterpret_cast<cudaStream_t>(stream)>>>(
       s0, s1, reinterpret_cast<const __nv_bfloat16*>(z), static_cast<unsigned>(M), C, H, W, shift, coeff, act, slope, code, lut_dev,

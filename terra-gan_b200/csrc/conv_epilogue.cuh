@@ -77,7 +77,7 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const ConvKParams& p, int
       const int rr = q * 32 + i * 8 + (lane >> 2);
       const long px = tile_pix + static_cast<long>(rr >> 3) * p.Wo + (rr & 7);
       const uint4* src = reinterpret_cast<const uint4*>(p.gate + px * p.Cout + nt * BN + hsel * 32 + (lane & 3) * 8);
-      pre.g[i] = (p.debug & 16) ? make_uint4(0x3f803f80u, 0x3f803f80u, 0xbf80bf80u, 0x3f803f80u) : *src;
+      pre.g[i] = TG_DBG(p, 16) ? make_uint4(0x3f803f80u, 0x3f803f80u, 0xbf80bf80u, 0x3f803f80u) : *src;
     }
   }
 }
@@ -122,7 +122,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
   for (int ch = 0; ch < BN / 32; ++ch) {
     if (((ch / kChunksPerStage) & 1) != hsel) continue;
     uint32_t raw[32];
-    if (!(p.debug & 8)) {
+    if (!TG_DBG(p, 8)) {
       tmem_ld_32x32(t_addr + ch * 32, raw);
       tmem_ld_wait();
     } else {
@@ -178,7 +178,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
       const uint4* gsrc = reinterpret_cast<const uint4*>(grow + ch * 32);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 t = (p.debug & 16) ? make_uint4(0x3f803f80u, 0x3f803f80u, 0xbf80bf80u, 0x3f803f80u) : gsrc[j];
+        const uint4 t = TG_DBG(p, 16) ? make_uint4(0x3f803f80u, 0x3f803f80u, 0xbf80bf80u, 0x3f803f80u) : gsrc[j];
         gbits[4 * j] = t.x; gbits[4 * j + 1] = t.y; gbits[4 * j + 2] = t.z; gbits[4 * j + 3] = t.w;
       }
     }
@@ -222,7 +222,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
         *reinterpret_cast<uint4*>(stage + lane * kRowBytes + (((cbase + j) ^ sw_w) << 4)) =
             make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
     }
-    if ((ch % kChunksPerStage) == kChunksPerStage - 1 && !(p.debug & 32)) {
+    if ((ch % kChunksPerStage) == kChunksPerStage - 1 && !TG_DBG(p, 32)) {
       __syncwarp();
       const int col0 = nt * BN + (ch - (kChunksPerStage - 1)) * 32;   // first channel held by the staging tile
 #pragma unroll
@@ -260,12 +260,12 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
           // (no shuffles, no validity mask on the store path)
           const int rr = q * 32 + row;
           const long pix2 = box_pix + static_cast<long>(rr >> 3) * p.Wo + (rr & 7);
-          if (!(p.debug & 1)) *reinterpret_cast<uint4*>(p.out + pix2 * p.Cout + col0 + chunk * 8) = val;
+          if (!TG_DBG(p, 1)) *reinterpret_cast<uint4*>(p.out + pix2 * p.Cout + col0 + chunk * 8) = val;
         } else {
           // pixel index of the row this lane stores: held by lane `row` of the warp
           const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(pix & 0xffffffffu), row);
           const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(static_cast<unsigned long long>(pix) >> 32), row);
-          if (((vmask >> row) & 1u) && !(p.debug & 1)) {
+          if (((vmask >> row) & 1u) && !TG_DBG(p, 1)) {
             const long pix2 = static_cast<long>((static_cast<unsigned long long>(hi) << 32) | lo);
             *reinterpret_cast<uint4*>(p.out + pix2 * p.Cout + col0 + chunk * 8) = val;
           }

@@ -148,7 +148,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = 0; t < 9; ++t) tap_off[t] = static_cast<uint32_t>((p.tap_dh[t] + 1) * (kHaloW + 2) + (p.tap_dw[t] + 1)) * 8u;
       const uint32_t slab16 = static_cast<uint32_t>(kSlabBytes >> 4);
       const uint32_t tap_step = static_cast<uint32_t>(p.cin_blocks) * slab16;
-      const bool skip_mma = (p.debug & 4) != 0;
+      const bool skip_mma = TG_DBG(p, 4);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -204,7 +204,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-        if (!(p.debug & 2))
+        if (!TG_DBG(p, 2))
           conv_epilogue_tile<BN, kHaloVec, kSC, kMode, true>(p, q, lane, 0, 0, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
                                                        s_out + (warp - 4) * (32 * kSC * 2), hsel, e_wt, e_ht, e_bt,
                                                        BN == 64 ? racc : nullptr, &pre);

@@ -380,7 +380,7 @@ conv_halo_s2dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(bs) * (2 * kSlab >> 4);
             const uint32_t accum = static_cast<uint32_t>((cb | t) != 0);
             if (elect_one()) {
-              if (!(p.debug & 4)) {
+              if (!TG_DBG(p, 4)) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16_lh(d, al0 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k ? 1u : accum);
                 if (two) {
@@ -421,7 +421,7 @@ conv_halo_s2dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int sb = 0; sb < 4; ++sb) {
           // the next plane's ratio code / gate rows are requested before this plane's tile is drained
           if (sb < 3) conv_epilogue_prefetch<BN, kMode, true>(p, q, lane, 0, sb + 1, tw, th, tb, hsel, e_wt, e_ht, e_bt, nxt);
-          if (!(p.debug & 2))
+          if (!TG_DBG(p, 2))
             conv_epilogue_tile<BN, kHsVec, kSC, kMode, true>(p, q, lane, 0, sb, tw, th, tb, t_addr + sb * BN, s_vec, my_stats,
                                                              has_vec, stg, hsel, e_wt, e_ht, e_bt, nullptr, &pre);
           pre = nxt;
@@ -478,11 +478,7 @@ int conv_halo_s2dgrad_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st) {
   const int sms = num_sms();
   const int grid = (int)(total_tiles < sms ? total_tiles : sms);
   a->stats_rows_used = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_s2dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS2Smem));
-    attr_set = true;
-  }
+  TG_SET_SMEM_ONCE((conv_halo_s2dgrad_kernel), kS2Smem);
   conv_halo_s2dgrad_kernel<<<grid, 384, kS2Smem, st>>>(tmA, tmB, kp);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -490,12 +486,7 @@ int conv_halo_s2dgrad_launch(tg_conv_args* a, ConvKParams kp, cudaStream_t st) {
 
 template <int BN>
 static int launch_halo_stream(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKParams& kp, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    TG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_stream_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       HsCfg<BN>::kSmem));
-    attr_set = true;
-  }
+  TG_SET_SMEM_ONCE((conv_halo_stream_kernel<BN>), HsCfg<BN>::kSmem);
   conv_halo_stream_kernel<BN><<<grid, 384, HsCfg<BN>::kSmem, st>>>(tmA, tmB, kp);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -282,12 +282,7 @@ template <int BN>
 static int launch_conv(const tg_conv_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        const ConvKParams& kp, int grid, cudaStream_t st) {
   using S = ConvSmem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
+  TG_SET_SMEM_ONCE((conv_igemm_kernel<BN>), S::kTotal);
   conv_igemm_kernel<BN><<<grid, 384, S::kTotal, st>>>(tmA, tmB, kp);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -358,10 +353,12 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   kp.stats = a->stats;
   kp.gate = reinterpret_cast<const __nv_bfloat16*>(a->gate);
   kp.gate_slope = a->gate_slope;
+#ifdef TG_PERF_DEBUG
   {
-    const char* e = getenv("TG_CONV_DEBUG");
-    kp.debug = e ? atoi(e) : 0;
+    static const int dbg = [] { const char* e = getenv("TG_CONV_DEBUG"); return e ? atoi(e) : 0; }();
+    kp.debug = dbg;
   }
+#endif
 
   // small-N 3x3 stride-1 layers: halo-tile reuse + resident weights (conv_halo.cu)
   if (halo_enabled() && conv_halo_eligible(a)) return conv_halo_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));

@@ -220,6 +220,48 @@ __global__ void final_bwd_pre_kernel(const float* __restrict__ g_out, const floa
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// BCEWithLogitsLoss (mean) on the discriminator logits — nn.BCEWithLogitsLoss() of train.py:115 as used at
+// train.py:203,215-216: loss = mean(max(x,0) - x*t + log1p(exp(-|x|))), d/dx = (sigmoid(x) - t) / n.
+// The targets on the path are torch.ones_like / zeros_like: `target` may be NULL with the constant `t_const`.
+// n = B*31*31 logits (61 504 at batch 64): one 1024-thread block, fixed summation order (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+bce_logits_fwd_kernel(const float* __restrict__ x, const float* __restrict__ target, float t_const, long n,
+                      float* __restrict__ out) {
+  __shared__ double s_part[32];
+  double acc = 0.0;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    const float t = target ? target[i] : t_const;
+    acc += static_cast<double>(fmaxf(v, 0.f) - v * t + log1pf(expf(-fabsf(v))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) s += s_part[w];
+    out[0] = static_cast<float>(s / static_cast<double>(n));
+  }
+}
+
+__global__ void bce_logits_bwd_kernel(const float* __restrict__ x, const float* __restrict__ target, float t_const,
+                                      long n, const float* __restrict__ go, float inv_n, float* __restrict__ gx) {
+  const float s = go[0] * inv_n;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    const float t = target ? target[i] : t_const;
+    // sigmoid without overflow for large |v|
+    const float e = expf(-fabsf(v));
+    const float sig = v >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+    gx[i] = (sig - t) * s;
+  }
+}
+
 static int ls_grid(long n, int block, int per_sm) {
   long g = (n + block - 1) / block;
   const long cap = static_cast<long>(num_sms() > 0 ? num_sms() : 148) * per_sm;
@@ -293,6 +335,25 @@ extern "C" int tg_final_bwd_pre(const float* g_out, const float* sig, const uint
   TG_REQUIRE(g_out && sig && mask && g_pre && n > 0, "tg_final_bwd_pre: bad arguments");
   final_bwd_pre_kernel<<<ls_grid(n, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g_out, sig, mask, n,
                                                                                                g_pre);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_bce_logits_fwd(const float* logits, const float* target, float target_const, long n, float* out,
+                                 void* stream) {
+  using namespace tg;
+  TG_REQUIRE(logits && out && n > 0, "tg_bce_logits_fwd: bad arguments");
+  bce_logits_fwd_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, target, target_const, n, out);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_bce_logits_bwd(const float* logits, const float* target, float target_const, long n,
+                                 const float* grad_out, float* grad_logits, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(logits && grad_out && grad_logits && n > 0, "tg_bce_logits_bwd: bad arguments");
+  bce_logits_bwd_kernel<<<ls_grid(n, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, target, target_const, n, grad_out, static_cast<float>(1.0 / static_cast<double>(n)), grad_logits);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -41,10 +41,35 @@ void set_last_error(const char* fmt, ...);
 
 int num_sms();  // cached SM count of the current device
 
+// Opt a kernel into > 48 KB of dynamic shared memory once per DEVICE (the attribute is per context; a
+// process-wide flag was wrong for a process that drives more than one GPU).
+#define TG_SET_SMEM_ONCE(kernel, bytes)                                                            \
+  do {                                                                                             \
+    static bool _done[64] = {};                                                                    \
+    int _dev = 0;                                                                                  \
+    TG_CHECK_CUDA(cudaGetDevice(&_dev));                                                           \
+    if (!_done[_dev & 63]) {                                                                       \
+      TG_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                         static_cast<int>(bytes)));                                \
+      _done[_dev & 63] = true;                                                                     \
+    }                                                                                              \
+  } while (0)
+
+// Perf-experiment switches (skip stores / loads / MMAs) used to live behind run-time `p.debug` bits that every
+// epilogue tile evaluated; they are compiled out unless the library is built with -DTG_PERF_DEBUG.
+#ifdef TG_PERF_DEBUG
+#define TG_DBG(p, bit) (((p).debug & (bit)) != 0)
+#else
+#define TG_DBG(p, bit) false
+#endif
+
 // Encode a bf16 tiled tensor map (SWIZZLE_128B, zero OOB fill). dims/strides innermost first;
 // strides_bytes has rank-1 entries (dims 1..rank-1). Returns 0 on success.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
+// Same for fp32 elements (the TF32 verification path: fp32 storage, kind::tf32 MMAs).
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box);
 
 // ----------------------------------------------------------------------------------------------
 // device helpers

@@ -112,7 +112,7 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
 #pragma unroll
       for (int kw = 0; kw < K; ++kw) {
         const int w = p.flip ? wb - kw : wb + kw;
-        const bool in = valid && h >= 0 && h < p.H && w >= 0 && w < p.W && !(p.debug & 2);
+        const bool in = valid && h >= 0 && h < p.H && w >= 0 && w < p.W && !TG_DBG(p, 2);
         const int off = in ? h * p.W + w : 0;
         // out-of-image taps read element 0 of the image and are zeroed through the mask byte / `inb` bit below
         v[kh * K + kw] = __ldg(sb + off);
@@ -123,7 +123,7 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
   // which taps of this thread's pixel fall inside the image (bit t), recomputed at build time: pure ALU
   auto inside_bits = [&](unsigned tile) -> unsigned long long {
     const unsigned P = tile * 128u + tid;
-    if (P >= p.total || (p.debug & 2)) return 0ull;
+    if (P >= p.total || TG_DBG(p, 2)) return 0ull;
     const unsigned b = P / HoWo, rem = P - b * HoWo;
     const int ho = static_cast<int>(rem / p.Wo), wo = static_cast<int>(rem - static_cast<unsigned>(ho) * p.Wo);
     const int hb = p.flip ? ho * p.S + p.pad : ho * p.S - p.pad;
@@ -243,7 +243,7 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
     if (!p.out_split) {
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0 && !(p.debug & 1)) {
+      if (lane == 0 && !TG_DBG(p, 1)) {
         tma_store_2d(&tm_out, st, 0, static_cast<int>(tile * 128u + warp * 32));   // rows >= total are clipped
         bulk_commit_group();
       }
@@ -296,7 +296,7 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
       umma_commit(&mbar[buf]);
     }
     if (have && tile + gridDim.x < tiles) load_src(tile + gridDim.x, v, mk);
-    if (tile + 4 * gridDim.x < tiles && !(p.debug & 4)) prefetch_src(tile + 4 * gridDim.x);
+    if (tile + 4 * gridDim.x < tiles && !TG_DBG(p, 4)) prefetch_src(tile + 4 * gridDim.x);
     if (NBUF == 1) {
       if (have) {
         mbar_wait(&mbar[0], it & 1);
@@ -333,11 +333,7 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
 template <int K, bool MASKED>
 static int rowgemm_launch(const RowGemmParams& p, int grid_cap, int* grid_used, cudaStream_t st) {
   using Cfg = RowGemmCfg<K>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TG_CHECK_CUDA(cudaFuncSetAttribute(rowgemm64_kernel<K, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    attr_set = true;
-  }
+  TG_SET_SMEM_ONCE((rowgemm64_kernel<K, MASKED>), Cfg::kSmem);
   CUtensorMap tm_out;
   memset(&tm_out, 0, sizeof(tm_out));
   if (!p.out_split) {
@@ -355,10 +351,12 @@ static int rowgemm_launch(const RowGemmParams& p, int grid_cap, int* grid_used, 
   if (grid < 1) grid = 1;
   if (grid_used) *grid_used = static_cast<int>(grid);
   RowGemmParams q = p;
+#ifdef TG_PERF_DEBUG
   {
-    const char* e = getenv("TG_THIN_DEBUG");
-    q.debug = e ? atoi(e) : 0;
+    static const int dbg = [] { const char* e = getenv("TG_THIN_DEBUG"); return e ? atoi(e) : 0; }();
+    q.debug = dbg;
   }
+#endif
   rowgemm64_kernel<K, MASKED><<<static_cast<int>(grid), 128, Cfg::kSmem, st>>>(q, tm_out);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -610,11 +608,7 @@ __global__ void tapwgrad_reduce_kernel(const float* __restrict__ partial, const 
 
 template <int K, bool MASKED>
 static int tapwgrad_launch(const TapWgradParams& p, const void* y, int grid_cap, int* grid_used, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    TG_CHECK_CUDA(cudaFuncSetAttribute(tapwgrad_kernel<K, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTwSmem));
-    attr_set = true;
-  }
+  TG_SET_SMEM_ONCE((tapwgrad_kernel<K, MASKED>), kTwSmem);
   CUtensorMap tm_y;
   const uint64_t dims[2] = {64, p.total};
   const uint64_t str[1] = {128};
@@ -825,11 +819,7 @@ int to1_fwd_mma(const void* x, int x_split, int B, int H, int W, const float* wg
   if (scratch == nullptr || scratch_floats < static_cast<size_t>(ntaps) * total) return -1;
   if (x_split && (H % 2 || W % 2)) return -1;
   if (total % 4 != 0) return -1;                       // 16-byte stores into the rows of T
-  static bool attr_set = false;
-  if (!attr_set) {
-    TG_CHECK_CUDA(cudaFuncSetAttribute(tapdot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
-    attr_set = true;
-  }
+  TG_SET_SMEM_ONCE((tapdot_kernel), kTdSmem);
   CUtensorMap tm_x;
   const uint64_t dims[2] = {64, static_cast<uint64_t>(total)};
   const uint64_t str[1] = {128};

@@ -235,11 +235,7 @@ int wgrad_halo_launch(tg_wgrad_args* a, cudaStream_t st) {
     uint32_t box[5] = {64, 8, 8, 1, 1};
     if (make_tmap_bf16(&tmG, a->g, 5, dims, str, box) != 0) return -3;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    TG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWhSmem));
-    attr_set = true;
-  }
+  TG_SET_SMEM_ONCE((wgrad_halo_kernel), kWhSmem);
   const int units = kp.cin_blocks * kp.splits;
   const int grid = units < sms ? units : sms;
   wgrad_halo_kernel<<<grid, 256, kWhSmem, st>>>(tmX, tmG, kp);

@@ -242,33 +242,42 @@ static void choose_kbox(int Ho, int Wo, int* Bt, int* Ht, int* Wt) {
   *Bt = 64 / (wt * ht);
 }
 
+// Split-K factor over the pixel boxes. The kernel is persistent (one CTA per SM, static round-robin over
+// units = m tiles x n tiles x splits), so its time is waves x (K blocks per unit + a fixed per-unit cost), with
+// waves = ceil(units / SMs). The round-1 rule "about 2 units per SM" produced 297 and 299 units on 148 SMs for dec3
+// and enc2 -- a third, almost empty wave (535 / 525 TFLOP/s). Every candidate is now costed and the cheapest
+// taken; ties go to the smaller split (fewer fp32 partial shares for tg_wgrad_reduce to read back).
 static int choose_splits(int B, int Ho, int Wo, int num_blk, int N, int sms) {
   int Bt, Ht, Wt;
   choose_kbox(Ho, Wo, &Bt, &Ht, &Wt);
   const long kboxes = (long)((B + Bt - 1) / Bt) * ((Ho + Ht - 1) / Ht) * ((Wo + Wt - 1) / Wt);
   const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
   const long mn = (long)((num_blk + 1) / 2) * (N / BN);
-  long splits = (2L * sms + mn - 1) / mn;  // aim for ~2 units per SM
-  const long max_by_k = (kboxes + 7) / 8;  // at least 8 K blocks per unit
-  if (splits > max_by_k) splits = max_by_k;
-  if (splits < 1) splits = 1;
-  if (splits > 256) splits = 256;
-  // no empty trailing share: shrink until every split owns at least one box
-  const long per = (kboxes + splits - 1) / splits;
-  splits = (kboxes + per - 1) / per;
-  return (int)splits;
+  long max_splits = (kboxes + 3) / 4;            // at least 4 K blocks per unit
+  if (max_splits > 256) max_splits = 256;
+  if (max_splits < 1) max_splits = 1;
+  const double unit_fixed = 3.0;                 // accumulator drain + pipeline fill, in K-block times
+  const double reduce_per_split = 0.75 * (double)BN / 128.0;   // partial write + read-back per share, same unit
+  long best = 1;
+  double best_cost = 1e30;
+  for (long s = 1; s <= max_splits; ++s) {
+    const long per = (kboxes + s - 1) / s;
+    if ((kboxes + per - 1) / per != s) continue;  // would leave an empty trailing share
+    const long waves = (mn * s + sms - 1) / sms;
+    const double cost = (double)waves * ((double)per + unit_fixed) + reduce_per_split * (double)s / (double)waves;
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return (int)best;
 }
 
 template <int BN>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmG, const WgradKParams& kp,
                         int grid, cudaStream_t st) {
   using S = WgradSmem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_igemm_kernel<BN>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
+  TG_SET_SMEM_ONCE((wgrad_igemm_kernel<BN>), S::kTotal);
   wgrad_igemm_kernel<BN><<<grid, 256, S::kTotal, st>>>(tmX, tmG, kp);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;

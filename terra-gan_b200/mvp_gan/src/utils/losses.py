@@ -143,8 +143,13 @@ class InpaintingLoss(nn.Module):
 
     def total_variation_loss(self, x):
         """TV of an arbitrary tensor (reference :118-127) — mask of ones-complement = no masking."""
-        zeros = torch.zeros_like(x[:, :1])
-        return InpaintTermsFn.apply(x, x.detach(), zeros, 0, 1e-6)[1]
+        b, c, h, w = x.shape
+        # the fused kernel works on single-channel tiles: fold C into the batch axis. The reference divides by
+        # batch_size = x.size(0) once more (:127), so the folded result (divided by b*c) is scaled back by c.
+        xf = x.reshape(b * c, 1, h, w)
+        zeros = torch.zeros_like(xf)
+        tv = InpaintTermsFn.apply(xf, xf.detach(), zeros, 0, 1e-6)[1]
+        return tv * float(c) if c != 1 else tv
 
     def _tensor_size(self, t):
         return t.numel()

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "tg_version": (c_int, []),
     "tg_last_error": (c_size_t, [C.c_char_p, c_size_t]),
     "tg_num_sms": (c_int, []),
+    "tg_tmap_cache_stats": (c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tg_mask_window_sum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "tg_mask_merge_up": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -126,6 +127,8 @@ PROTOTYPES = {
                                     c_void_p, c_void_p, c_void_p]),
     "tg_l1_bf16_fwd": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]),
     "tg_l1_bf16_bwd": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]),
+    "tg_bce_logits_fwd": (c_int, [c_void_p, c_void_p, c_float, c_long, c_void_p, c_void_p]),
+    "tg_bce_logits_bwd": (c_int, [c_void_p, c_void_p, c_float, c_long, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -164,7 +167,7 @@ KERNELS_PER_CALL = {
     "tg_bn_bwd_apply": 1, "tg_upsample_concat": 1, "tg_upsample_concat_bwd": 1, "tg_maxpool2": 1,
     "tg_maxpool2_bwd": 1, "tg_conv_c1_fwd": 1, "tg_conv_c1_wgrad": 2, "tg_conv_to1_fwd": 1, "tg_conv_to1_fwd+tapsum": 1, "tg_conv_to1_fwd_scratch_floats": 0,
     "tg_conv_to1_bwd_data": 1, "tg_conv_to1_wgrad": 2, "tg_final_bwd_pre": 1, "tg_inpaint_loss_fwd": 2,
-    "tg_inpaint_loss_bwd": 1, "tg_l1_bf16_fwd": 2, "tg_l1_bf16_bwd": 1,
+    "tg_inpaint_loss_bwd": 1, "tg_l1_bf16_fwd": 2, "tg_l1_bf16_bwd": 1, "tg_bce_logits_fwd": 1, "tg_bce_logits_bwd": 1,
 }
 
 

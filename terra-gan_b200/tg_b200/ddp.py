@@ -36,7 +36,7 @@ class BucketedGradReducer:
         self._pending: List[torch.Tensor] = []
         self._pending_keys: List[tuple] = []
         self._pending_bytes = 0
-        self._inflight = []         # (work, flat bucket, [(module, param name)], [numel])
+        self._inflight = []         # (work, flat bucket, [(module, param name)], [numel], source tensors)
         self._comm_stream: Optional[torch.cuda.Stream] = None
         self.buckets_launched = 0
         for m in self.modules:
@@ -77,7 +77,9 @@ class BucketedGradReducer:
         else:
             flat = torch.cat([t.reshape(-1) for t in tensors])
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._inflight.append((work, flat, keys, [t.numel() for t in tensors]))
+        # `tensors` were allocated on the compute stream but are read by the cat on the comm stream: keep them alive
+        # until finish() so the caching allocator cannot hand their memory to a later backward kernel first
+        self._inflight.append((work, flat, keys, [t.numel() for t in tensors], tensors))
         self.buckets_launched += 1
 
     # ---- called by the training step before optimizer.step() ----
@@ -93,7 +95,7 @@ class BucketedGradReducer:
 
         def scatter_back():
             seen = set()
-            for work, flat, keys, sizes in inflight:
+            for work, flat, keys, sizes, _src in inflight:
                 work.wait()
                 flat.mul_(inv)
                 off = 0

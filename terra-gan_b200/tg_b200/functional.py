@@ -140,6 +140,38 @@ class InpaintTermsFn(torch.autograd.Function):
         return grad, None, None, None, None
 
 
+class BCEWithLogitsFn(torch.autograd.Function):
+    """nn.BCEWithLogitsLoss()(logits, target) with mean reduction — train.py:115,203,215-216. `target` is a tensor or a
+    Python float (the loops pass ones_like / zeros_like: a constant needs no target tensor at all)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        _require_cuda(logits, "BCEWithLogits")
+        x = logits.detach().float().contiguous()
+        if isinstance(target, torch.Tensor):
+            t, tc = target.detach().float().contiguous(), 0.0
+        else:
+            t, tc = None, float(target)
+        out = ops.bce_logits_fwd(x, t, tc)
+        ctx.saved = (x, t, tc, logits.shape)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, go):
+        x, t, tc, shape = ctx.saved
+        gx = ops.bce_logits_bwd(x, go.reshape(1).float().contiguous(), t, tc)
+        ctx.saved = None
+        return gx.reshape(shape), None
+
+
+class BCEWithLogitsLoss(torch.nn.Module):
+    """Drop-in for the `adversarial_loss = nn.BCEWithLogitsLoss()` object of train.py:115 on the B200 path: same call
+    signature `(input, target) -> scalar`; targets that are constant tensors may also be passed as a Python float."""
+
+    def forward(self, input, target):
+        return BCEWithLogitsFn.apply(input, target)
+
+
 class PConv2dFn(torch.autograd.Function):
     """Stand-alone PConv2d.forward(input, mask) -> (output, output_mask) — pconv.py:25-50 — for shapes
     with Cin == 1 (Cout == 64; 7x7/s2, 4x4/s2, 3x3/s1) or Cin % 64 == 0 (stride 1 or 2)."""

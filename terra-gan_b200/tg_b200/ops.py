@@ -444,6 +444,9 @@ def inpaint_loss_fwd(pred, target, mask, flags=0, eps=1e-6):
     """fp32 [B,1,H,W] x3 -> terms fp32 [4] = (l1, tv, boundary, boundary_count)."""
     for n, t in (("pred", pred), ("target", target), ("mask", mask)):
         _req(t, torch.float32, n)
+    if pred.dim() != 4 or pred.shape[1] != 1 or target.shape != pred.shape or mask.shape != pred.shape:
+        raise RuntimeError("inpaint_loss: pred / target / mask must all be [B,1,H,W] (single-channel DSM tiles), got "
+                           f"{tuple(pred.shape)}, {tuple(target.shape)}, {tuple(mask.shape)}")
     B, _, H, W = pred.shape
     rows = lib().tg_loss_rows()
     partial = torch.empty((rows * 5,), dtype=torch.float32, device=pred.device)
@@ -479,3 +482,24 @@ def l1_bf16_bwd(a, b, grad_out, relu_gate=True):
     check(lib().tg_l1_bf16_bwd(ptr(a), ptr(b), a.numel(), ptr(grad_out), 1 if relu_gate else 0, ptr(ga),
                                stream_ptr()), "tg_l1_bf16_bwd")
     return ga
+
+
+def bce_logits_fwd(logits, target=None, target_const=0.0):
+    """mean BCE-with-logits over all elements -> fp32 [1]. target: fp32 tensor of logits' shape, or None (constant)."""
+    _req(logits, torch.float32, "logits")
+    if target is not None:
+        _req(target, torch.float32, "target")
+        if target.numel() != logits.numel():
+            raise RuntimeError("bce_logits: target must have the shape of the logits")
+    out = torch.empty((1,), dtype=torch.float32, device=logits.device)
+    check(lib().tg_bce_logits_fwd(ptr(logits), ptr(target), float(target_const), logits.numel(), ptr(out),
+                                  stream_ptr()), "tg_bce_logits_fwd")
+    return out
+
+
+def bce_logits_bwd(logits, grad_out, target=None, target_const=0.0):
+    _req(grad_out, torch.float32, "grad_out")
+    gx = torch.empty_like(logits)
+    check(lib().tg_bce_logits_bwd(ptr(logits), ptr(target), float(target_const), logits.numel(), ptr(grad_out),
+                                  ptr(gx), stream_ptr()), "tg_bce_logits_bwd")
+    return gx

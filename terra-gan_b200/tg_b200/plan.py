@@ -129,8 +129,8 @@ def from_parity_split(x: torch.Tensor) -> torch.Tensor:
 
 
 def ratio_lut(k: int) -> List[float]:
-    """Mask-ratio LUT of PConv2d (pconv.py:38-40): r(s) = fl(fl(1/(s + 1e-8)) * k^2) * [s > 0],
-    evaluated with the reference's own fp32 op order (reciprocal then multiply — NOT k^2/s)."""
+    """Mask-ratio LUT of PConv2d (pconv.py:38-40): r(s) = (k^2 / (s + 1e-8)) * [s > 0], evaluated with the
+    reference's own expression on fp32 tensors (`slide_winsize / (mask_sum + 1e-8)`: torch's scalar / tensor)."""
     s = torch.arange(0, k * k + 1, dtype=torch.float32)
     r = (float(k * k) / (s + 1e-8)) * (s > 0).float()
     return [float(v) for v in r]

@@ -19,6 +19,7 @@ from typing import Dict, Optional
 import torch
 
 from .ddp import BucketedGradReducer
+from .functional import BCEWithLogitsLoss
 
 
 @contextmanager
@@ -41,7 +42,7 @@ class AdversarialStep:
                  reducer: Optional[BucketedGradReducer] = None, skip_discarded_d_wgrad: bool = True):
         self.G, self.D, self.criterion = generator, discriminator, criterion
         self.opt_G, self.opt_D = optimizer_G, optimizer_D
-        self.adversarial_loss = torch.nn.BCEWithLogitsLoss()          # train.py:115
+        self.adversarial_loss = BCEWithLogitsLoss()                   # train.py:115 (tg_bce_logits_fwd/bwd)
         self.reducer = reducer
         self.skip_discarded_d_wgrad = skip_discarded_d_wgrad
 
@@ -53,7 +54,7 @@ class AdversarialStep:
         g_loss = self.criterion(gen_imgs, real_imgs, masks)
         with _frozen(self.D, self.skip_discarded_d_wgrad):
             fake_validity = self.D(gen_imgs)
-        g_adv_loss = self.adversarial_loss(fake_validity, torch.ones_like(fake_validity))
+        g_adv_loss = self.adversarial_loss(fake_validity, 1.0)          # target = ones_like (:203)
         g_total_loss = g_loss + g_adv_loss
         g_total_loss.backward()
         if self.reducer is not None:
@@ -63,8 +64,8 @@ class AdversarialStep:
         self.opt_D.zero_grad()
         real_validity = self.D(real_imgs)
         fake_validity = self.D(gen_imgs.detach())
-        real_loss = self.adversarial_loss(real_validity, torch.ones_like(real_validity))
-        fake_loss = self.adversarial_loss(fake_validity, torch.zeros_like(fake_validity))
+        real_loss = self.adversarial_loss(real_validity, 1.0)          # :213-216
+        fake_loss = self.adversarial_loss(fake_validity, 0.0)
         d_loss = 0.5 * (real_loss + fake_loss)
         d_loss.backward()
         if self.reducer is not None:
