@@ -36,9 +36,14 @@ extern "C" {
 #define TG_ACT_NONE 0
 #define TG_ACT_RELU 1
 #define TG_ACT_LEAKY 2
+/* Activation storage type. BF16 is the product path (bf16 storage, kind::f16 MMAs, fp32 accumulate). F32 is the
+ * verification path of BASELINE.json's north star ("TF32 path <= 1e-3"): fp32 storage, kind::tf32 MMAs; the same
+ * entry points with a `dtype` field, and `_f32` twins of the bandwidth kernels. */
+#define TG_DTYPE_BF16 0
+#define TG_DTYPE_F32 1
 
 /* ---- library ------------------------------------------------------------------------------ */
-int tg_version(void);                               /* ABI version (this header: 1) */
+int tg_version(void);                               /* ABI version (this header: 2) */
 size_t tg_last_error(char* buf, size_t cap);        /* copies the last error text of this thread */
 int tg_num_sms(void);                               /* SM count of the current device (<=0: error) */
 /* Hit / miss counters of the calling thread's TMA tensor-map cache (descriptors are keyed by pointer, shape and
@@ -106,6 +111,10 @@ typedef struct tg_conv_args {
   const void* gate;         /* bf16, same shape as out, or NULL: out *= (gate > 0 ? 1 : gate_slope) —
                                ReLU/LeakyReLU derivative of the tensor a dgrad result flows into */
   float gate_slope;
+  int32_t dtype;            /* TG_DTYPE_*: storage type of x, w, out and gate (F32: C % 32 == 0, generic kernel) */
+  const float* addend;      /* F32 only, or NULL: fp32 tensor of out's shape added to the accumulator before bias / ratio /
+                               statistics (tf32x3: the lo*hi + hi*lo cross terms computed by a first launch, so that the
+                               long hi*hi accumulation chain is not lengthened by them) */
 } tg_conv_args;
 int tg_conv_igemm(tg_conv_args* args, void* stream);
 
@@ -131,6 +140,8 @@ typedef struct tg_wgrad_args {
   int32_t splits;           /* out: split-K factor chosen (pass to tg_wgrad_reduce) */
   const void* blks;         /* device table of num_taps*C/64 tg_wgrad_blk, tap-major then channel block */
   int32_t num_blk;
+  int32_t dtype;            /* TG_DTYPE_*: storage type of x and g. F32: blks are 32-channel blocks (num_taps*C/32
+                               entries, row = tap*C + cb*32), C % 32 == 0, N % 32 == 0 */
 } tg_wgrad_args;
 int tg_wgrad_igemm(tg_wgrad_args* args, void* stream);
 /* dw[n][c][tap_of(kh,kw)] (+)= sum_s partial[s][tap*C + c][n];  tap order is the caller's tap table,
@@ -139,6 +150,7 @@ int tg_wgrad_reduce(const float* partial, int splits, int num_taps, int C, int N
                     const int32_t* tap_perm_dev, float* dw, int accumulate, void* stream);
 /* How many fp32 the `partial` workspace of tg_wgrad_igemm needs for this problem. */
 int64_t tg_wgrad_partial_floats(int B, int Ho, int Wo, int num_taps, int C, int N);
+int64_t tg_wgrad_partial_floats_f32(int B, int Ho, int Wo, int num_taps, int C, int N);   /* dtype = TG_DTYPE_F32 */
 
 
 /* ---- BatchNorm2d + activation (HBM-bound, 16-byte vectorised) -------------------------------
@@ -266,6 +278,56 @@ int tg_bce_logits_fwd(const float* logits, const float* target, float target_con
                       void* stream);
 int tg_bce_logits_bwd(const float* logits, const float* target, float target_const, long n,
                       const float* grad_out, float* grad_logits, void* stream);
+
+/* ---- fp32-storage verification path ("TF32 path <= 1e-3", BASELINE.json north star) ---------------------------
+ * Twins of the entry points above with fp32 activations instead of bf16 (same argument meaning; every `void*`
+ * activation / gradient pointer is a float tensor). The implicit-GEMM entry points take `dtype = TG_DTYPE_F32` in
+ * their argument block instead. These run the SAME kernel templates with the storage type swapped (BatchNorm,
+ * resampling, pooling, L1) or the CUDA-core kernels of direct_conv.cu in fp32 (the 1<->64-channel convolutions);
+ * they exist to prove the forward / backward formulation against the fp32 reference to a sharp bound. */
+int tg_bn_apply_f32(const void* z, int B, int H, int W, int C, const float* scale, const float* shift,
+                    int act, float slope, const uint8_t* code, void* y_nhwc, void* y_split,
+                    int mask_split, void* stream);
+int tg_bn_bwd_reduce_f32(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H, int W,
+                         int C, const float* scale, const float* shift, int act, float slope,
+                         const uint8_t* code, const float* lut_dev, float* partial, int rows_cap,
+                         int* rows_used, void* stream);
+int tg_bn_bwd_apply_f32(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H, int W,
+                        int C, const float* shift, const float* coeff, int act, float slope,
+                        const uint8_t* code, const float* lut_dev, void* gz, void* stream);
+int tg_upsample_concat_f32(const void* up, int B, int h, int w, int Cu, const void* skip, int Cs,
+                           const uint8_t* merged_mask, void* out, void* stream);
+int tg_upsample_concat_bwd_f32(const void* d_merged, int B, int h, int w, int Cu, int Ctot, void* d_up,
+                               void* stream);
+int tg_maxpool2_f32(const void* x, int B, int H, int W, int C, void* y, void* stream);
+int tg_maxpool2_bwd_f32(const void* x, const void* gy, int B, int H, int W, int C, int relu_gate, void* gx,
+                        void* stream);
+int tg_conv_c1_fwd_f32(const float* x, const uint8_t* xmask, int B, int H, int W, int k, int s, int pad,
+                       const float* wgt, const float* bias, const uint8_t* code, const float* lut_dev, int act,
+                       float slope, void* out, int out_split, float* stats, int stats_rows_cap,
+                       int* stats_rows_used, void* stream);
+int tg_conv_c1_wgrad_f32(const float* x, const uint8_t* xmask, int B, int H, int W, int k, int s, int pad,
+                         const void* g, int g_split, float* partial, int rows_cap, float* dw, float* db,
+                         int accumulate, void* stream);
+int tg_conv_to1_fwd_f32(const void* x, int x_split, int B, int H, int W, int C, const float* wgt, int ncls,
+                        const int* cls_count, const int8_t* tap_dh, const int8_t* tap_dw, const float* bias,
+                        int Ho, int Wo, int mode, const uint8_t* mask, const float* xin, float* out,
+                        float* sig_out, void* stream);
+int tg_conv_to1_bwd_data_f32(const float* g, int B, int Ho, int Wo, const float* wgt, int ntaps,
+                             const int8_t* tap_dh, const int8_t* tap_dw, int H, int W, int C, void* dx,
+                             void* stream);
+int tg_conv_to1_wgrad_f32(const void* x, int B, int H, int W, int C, const float* g, int Ho, int Wo, int ntaps,
+                          const int8_t* tap_dh, const int8_t* tap_dw, float* partial, float* partial_b,
+                          int rows_cap, float* dw, float* db, int accumulate, void* stream);
+int tg_l1_f32_fwd(const void* a, const void* b, long n, float* partial, int rows_cap, float* out, void* stream);
+int tg_l1_f32_bwd(const void* a, const void* b, long n, const float* grad_out, int relu_gate, void* ga,
+                  void* stream);
+/* Two-term TF32 split of an fp32 tensor [rows][C] along its last dimension: hi = tf32(x), lo = tf32(x - hi).
+ * layout 0: out [rows][3C] = [hi | lo | hi]; 1: [hi | hi | lo]; 2: out [rows][2C] = [hi | lo]; 3: out [rows][C] = hi;
+ * 4: out [rows][2C] = [lo | hi]. A contraction of a [lo | hi] operand with a [hi | lo] operand over the concatenated
+ * axis gives the cross terms lo*hi + hi*lo, hi against hi the main term: together fp32-grade products from
+ * kind::tf32 passes ("tf32x3" precision of tg_b200.precision). */
+int tg_split_tf32(const float* x, long rows, int C, int layout, float* out, void* stream);
 
 /* ---- fused Adam step + packed-weight refresh (adam_kernels.cu) ---------------------------------------
  * Replaces torch.optim.Adam.step() of the reference loops (mvp_gan/src/train.py:207,219,

@@ -95,6 +95,140 @@ def _q(x: Tensor) -> Tensor:
     return x if ROUND is None else ROUND(x)
 
 
+# ---- gate tape (tests only) -----------------------------------------------------------------------
+# The reference's gradients are piecewise smooth: every ReLU / LeakyReLU gate [pre > 0] and every max-pool
+# routing is a discontinuity. Two correct implementations whose forward values differ by 1e-6 take different
+# branches on the ~1e-6 of elements whose pre-activation lies that close to zero, and with a random upstream
+# gradient that alone perturbs a weight-gradient tensor by ~sqrt(1e-6) = 1e-3 (measured: 1e-2 from the ~1e-5
+# forward noise of tensor-core fp32 accumulation). To compare BACKWARD arithmetic to a sharp bound the tests
+# therefore replay the branch decisions of the implementation under test into this restatement:
+# `with gate_tape(gates)` makes every activation / pooling call use the recorded decision of the same call site
+# (keys: "<layer>." for the PConv layers, "D<pass>.<idx>" and "vgg<pass>.<idx>", "vgg<pass>.pool<idx>"), and records how
+# many decisions differed from this restatement's own and how close to the threshold those elements were.
+TAPE = None
+
+
+class _GatedAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pre, gate, slope):
+        f = torch.where(gate, torch.ones_like(pre), torch.full_like(pre, slope))
+        ctx.save_for_backward(f)
+        return pre * f
+
+    @staticmethod
+    def backward(ctx, g):
+        (f,) = ctx.saved_tensors
+        return g * f, None, None
+
+
+class gate_tape:
+    def __init__(self, gates: dict):
+        self.gates = gates
+        self.passes: dict = {}
+        self.report: dict = {}        # key -> (decisions that differ, elements, max |pre| / std(pre) among them)
+
+    def __enter__(self):
+        global TAPE
+        self.prev, TAPE = TAPE, self
+        return self
+
+    def __exit__(self, *a):
+        global TAPE
+        TAPE = self.prev
+
+    def next_pass(self, family: str) -> int:
+        self.passes[family] = self.passes.get(family, -1) + 1
+        return self.passes[family]
+
+
+def _act(pre: Tensor, slope: float, key: str) -> Tensor:
+    if TAPE is None or TAPE.gates.get(key) is None:
+        return F.leaky_relu(pre, slope) if slope else F.relu(pre)
+    gate = TAPE.gates[key]
+    with torch.no_grad():
+        diff = gate != (pre > 0)
+        n = int(diff.sum())
+        TAPE.report[key] = (n, pre.numel(), float(pre[diff].abs().max() / pre.std()) if n else 0.0)
+    return _GatedAct.apply(pre, gate, slope)
+
+
+class _RoutedPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = x.shape
+        b, c, h, w = x.shape
+        return x.reshape(b, c, h * w).gather(2, idx.reshape(b, c, -1)).reshape(idx.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        b, c, h, w = ctx.shape
+        gx = torch.zeros((b, c, h * w), dtype=g.dtype)
+        gx.scatter_(2, idx.reshape(b, c, -1), g.reshape(b, c, -1))
+        return gx.reshape(ctx.shape), None
+
+
+class _SignedL1(torch.autograd.Function):
+    """mean |a - b| whose backward uses a recorded sign(a - b) (the L1 kink is a branch decision too)."""
+    @staticmethod
+    def forward(ctx, a, b, sgn):
+        ctx.save_for_backward(sgn)
+        return (a - b).abs().mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        (sgn,) = ctx.saved_tensors
+        ga = g * sgn / sgn.numel()
+        return ga, -ga, None
+
+
+def _l1(a: Tensor, b: Tensor, key: str) -> Tensor:
+    if TAPE is None or TAPE.gates.get(key) is None:
+        return F.l1_loss(a, b)
+    sgn = TAPE.gates[key].to(a.dtype)
+    with torch.no_grad():
+        own = torch.sign(a - b)
+        diff = own != sgn
+        n = int(diff.sum())
+        TAPE.report[key] = (n, sgn.numel(), float((a - b)[diff].abs().max() / (a - b).std()) if n else 0.0)
+    return _SignedL1.apply(a, b, sgn)
+
+
+class _SignedAbs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, d, sgn):
+        ctx.save_for_backward(sgn)
+        return d.abs()
+
+    @staticmethod
+    def backward(ctx, g):
+        (sgn,) = ctx.saved_tensors
+        return g * sgn, None
+
+
+def _abs(d: Tensor, key: str) -> Tensor:
+    """|d| of a pixel-space difference pred - target (L1, boundary and human-region terms share its sign)."""
+    if TAPE is None or TAPE.gates.get(key) is None:
+        return torch.abs(d)
+    sgn = TAPE.gates[key].to(d.dtype)
+    with torch.no_grad():
+        diff = (torch.sign(d) != sgn) & (sgn != 0)
+        n = int(diff.sum())
+        TAPE.report[key] = (n, sgn.numel(), float(d[diff].abs().max() / d.std()) if n else 0.0)
+    return _SignedAbs.apply(d, sgn * (d != 0))
+
+
+def _pool(x: Tensor, key: str) -> Tensor:
+    if TAPE is None or TAPE.gates.get(key) is None:
+        return F.max_pool2d(x, 2, 2)
+    idx = TAPE.gates[key]
+    with torch.no_grad():
+        _, own = F.max_pool2d(x, 2, 2, return_indices=True)
+        TAPE.report[key] = (int((own != idx).sum()), idx.numel(), 0.0)
+    return _RoutedPool.apply(x, idx)
+
+
 # --------------------------------------------------------------------------------------------------
 # deterministic parameter construction (shared by the golden generator and every parity test)
 # --------------------------------------------------------------------------------------------------
@@ -223,8 +357,8 @@ def pconv2d(x: Tensor, mask: Tensor, sd: SD, prefix: str, stride: int, pad: int,
     z = F.conv2d(x * mask, w, b, stride, pad)                          # :27,30  (bias inside)
     with torch.no_grad():
         msum = F.conv2d(mask, mw, None, stride, pad)                   # :34 / :38
-        new_mask = (msum > 0).float()                                  # :35
-        ratio = (winsize / (msum + 1e-8)) * (msum > 0).float()         # :39-40 (reciprocal * k^2)
+        new_mask = (msum > 0).to(mask.dtype)                           # :35 (.float() in the reference; fp64 only in diagnostics)
+        ratio = (winsize / (msum + 1e-8)) * (msum > 0).to(mask.dtype)  # :39-40 (reciprocal * k^2)
     z = _q(z * ratio)                                                  # :43
     if trace is not None:
         trace[prefix + "msum"] = msum
@@ -235,7 +369,7 @@ def pconv2d(x: Tensor, mask: Tensor, sd: SD, prefix: str, stride: int, pad: int,
                          BN_MOMENTUM, BN_EPS)
         if training:
             sd[prefix + "bn.num_batches_tracked"] += 1
-    y = _q(F.relu(z))                                                  # :48
+    y = _q(_act(z, 0.0, prefix))                                       # :48
     if trace is not None:
         trace[prefix + "y"] = y
         trace[prefix + "mask"] = new_mask
@@ -282,6 +416,7 @@ def pconv_unet(x: Tensor, mask: Tensor, sd: SD, training: bool, trace: Optional[
 # --------------------------------------------------------------------------------------------------
 def discriminator(img: Tensor, sd: SD, training: bool) -> Tensor:
     h = img
+    pass_no = TAPE.next_pass("D") if TAPE is not None else 0
     for idx, _, _, _, s, p, bn in DISC:
         w = sd[f"model.{idx}.weight"]
         h = F.conv2d(h, _q(w) if idx in (2, 5, 8) else w, sd[f"model.{idx}.bias"], s, p)
@@ -294,7 +429,7 @@ def discriminator(img: Tensor, sd: SD, training: bool) -> Tensor:
                              sd[f"model.{bn}.weight"], sd[f"model.{bn}.bias"], training, BN_MOMENTUM, BN_EPS)
             if training:
                 sd[f"model.{bn}.num_batches_tracked"] += 1
-        h = _q(F.leaky_relu(h, 0.2))
+        h = _q(_act(h, 0.2, f"D{pass_no}.{idx}"))
     return h
 
 
@@ -304,11 +439,12 @@ def discriminator(img: Tensor, sd: SD, training: bool) -> Tensor:
 def vgg_features(x3: Tensor, vgg: SD) -> Tensor:
     """torchvision vgg16().features[:16] (conv3x3+ReLU x2, pool, x2, pool, x3), frozen, eval."""
     h = x3
+    pass_no = TAPE.next_pass("vgg") if TAPE is not None else 0
     for idx, _, _ in VGG_CONVS:
         w = vgg[f"{idx}.weight"]
-        h = _q(F.relu(F.conv2d(h, _q(w) if idx > 0 else w, vgg[f"{idx}.bias"], 1, 1)))
+        h = _q(_act(F.conv2d(h, _q(w) if idx > 0 else w, vgg[f"{idx}.bias"], 1, 1), 0.0, f"vgg{pass_no}.{idx}"))
         if idx in VGG_POOL_AFTER:
-            h = F.max_pool2d(h, 2, 2)
+            h = _pool(h, f"vgg{pass_no}.pool{idx}")
     return h
 
 
@@ -328,7 +464,7 @@ def boundary_loss(pred: Tensor, target: Tensor, mask: Tensor, eps: float = 1e-6)
     bd = torch.clamp(dil - ero, 0.0, 1.0)
     if bd.sum() < 1.0:                                                 # :411
         return torch.zeros((), dtype=pred.dtype)
-    loss = (torch.abs(pred - target) * bd).sum() / (bd.sum() + eps)    # :415-416
+    loss = (_abs(pred - target, "sign.pixel") * bd).sum() / (bd.sum() + eps)    # :415-416
     if torch.isnan(loss) or torch.isinf(loss):                         # :419
         return torch.zeros((), dtype=pred.dtype)
     return loss
@@ -338,12 +474,12 @@ def inpainting_loss(inp: Tensor, target: Tensor, mask: Tensor, vgg: SD, perceptu
                     tv_weight: float = 0.1, boundary_weight: float = 0.5,
                     terms: Optional[dict] = None) -> Tensor:
     """InpaintingLoss.forward, losses.py:58-116."""
-    l1 = F.l1_loss(inp, target)                                        # :73
+    l1 = _abs(inp - target, "sign.pixel").mean()                       # :73 (nn.L1Loss, mean reduction)
     total = l1
     if terms is not None:
         terms["l1"] = l1.detach()
     if perceptual_weight > 0:                                          # :77-90
-        pl = F.l1_loss(vgg_features(inp.repeat(1, 3, 1, 1), vgg), vgg_features(target.repeat(1, 3, 1, 1), vgg))
+        pl = _l1(vgg_features(inp.repeat(1, 3, 1, 1), vgg), vgg_features(target.repeat(1, 3, 1, 1), vgg), "l1.perceptual")
         total = total + perceptual_weight * pl
         if terms is not None:
             terms["perceptual"] = pl.detach()
@@ -370,7 +506,7 @@ def human_guided_loss(inp: Tensor, target: Tensor, mask: Tensor, human_mask: Opt
     if human_mask is not None:
         hm = (human_mask > 0).float()                                  # :168
         if hm.sum() > 0:                                               # :171
-            human = F.l1_loss(inp * hm, target * hm)                   # :172-175
+            human = _abs(inp * hm - target * hm, "sign.pixel").mean() if TAPE is not None else F.l1_loss(inp * hm, target * hm)   # :172-175
             if boundary_weight > 0:                                    # :178-185
                 human = human + boundary_weight * boundary_loss(inp, target, hm)
     if terms is not None:

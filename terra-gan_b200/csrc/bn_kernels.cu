@@ -42,6 +42,8 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   raw.w = pack_bf16x2(f[6], f[7]);
   *reinterpret_cast<uint4*>(p) = raw;
 }
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) { vload8(p, f); }
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) { vstore8(p, f); }
 __device__ __forceinline__ void ldg8f(const float* p, float (&f)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -120,11 +122,12 @@ __global__ void bn_eval_coeff_kernel(int C, const float* __restrict__ gamma, con
 // Channel-stationary: a thread owns one 8-channel vector (scale/shift live in registers) and strides
 // over pixels; 256 threads = (C/8) channel vectors x 256/(C/8) pixel lanes; two pixels in flight per
 // iteration; 32-bit pixel arithmetic.
+template <typename T>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const __nv_bfloat16* __restrict__ z, unsigned M, int C, int H, int W,
+bn_apply_kernel(const T* __restrict__ z, unsigned M, int C, int H, int W,
                 const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope,
-                const uint8_t* __restrict__ code, __nv_bfloat16* __restrict__ y_nhwc,
-                __nv_bfloat16* __restrict__ y_split, int mask_split) {
+                const uint8_t* __restrict__ code, T* __restrict__ y_nhwc,
+                T* __restrict__ y_split, int mask_split) {
   const unsigned cv = C >> 3;
   const unsigned lanes = blockDim.x / cv;
   const unsigned c = (threadIdx.x % cv) << 3;
@@ -169,23 +172,15 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, unsigned M, int C, int H, i
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-struct GradSrc {
-  const __nv_bfloat16* ptr;  // null = absent
+template <typename T>
+struct GradSrcT {
+  const T* ptr;              // null = absent
   long pix_stride;           // elements between consecutive pixels
   int chan_off;              // first channel of this layer's slice inside the source tensor
   int split;                 // 1: source pixels are in parity-split order
 };
 
-__device__ __forceinline__ void load_grad(const GradSrc& s0, const GradSrc& s1, long p, long ps, int c,
-                                          float (&g)[8]) {
-  load8(s0.ptr + (s0.split ? ps : p) * s0.pix_stride + s0.chan_off + c, g);
-  if (s1.ptr) {
-    float t[8];
-    load8(s1.ptr + (s1.split ? ps : p) * s1.pix_stride + s1.chan_off + c, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] += t[j];
-  }
-}
+using GradSrc = GradSrcT<__nv_bfloat16>;
 
 // ---- per-thread cp.async ring ---------------------------------------------------------------
 // The backward kernels stream two or three bf16 tensors with one 16-byte vector per thread and pixel. Held in
@@ -201,22 +196,23 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+// one ring slot = the 8-element vector of one thread: 16 bytes of bf16 or 32 bytes of fp32
+template <typename T>
+__device__ __forceinline__ void cp_async_vec8(uint32_t saddr, const T* g) {
+  cp_async16(saddr, g);
+  if (sizeof(T) == 4) cp_async16(saddr + 16, reinterpret_cast<const uint8_t*>(g) + 16);
 }
+__device__ __forceinline__ void unpack8(const __nv_bfloat16* slot, float (&f)[8]) { vload8(slot, f); }
+__device__ __forceinline__ void unpack8(const float* slot, float (&f)[8]) { vload8(slot, f); }
 // Streams (g0 [+ g1], z, ratio) of pixels p = first, first + stride, ... < M to `body(p, g[8], z[8], r)`.
 // ring: kRing * 3 * blockDim.x uint4 of shared memory.
-template <typename Body>
-__device__ __forceinline__ void stream_grad_z(const GradSrc& s0, const GradSrc& s1, const __nv_bfloat16* __restrict__ z,
+template <typename T, typename Body>
+__device__ __forceinline__ void stream_grad_z(const GradSrcT<T>& s0, const GradSrcT<T>& s1, const T* __restrict__ z,
                                               unsigned M, int C, int H, int W, int c, unsigned first, unsigned stride,
                                               const uint8_t* __restrict__ code, const float* __restrict__ lut,
-                                              uint4* ring, Body body) {
+                                              uint4* ring_raw, Body body) {
+  constexpr unsigned kSlot = 8 * sizeof(T);     // bytes per ring slot
+  T* ring = reinterpret_cast<T*>(ring_raw);
   const bool need_split = s0.split || (s1.ptr && s1.split);
   const unsigned HW = static_cast<unsigned>(H) * W;
   const unsigned nthr = blockDim.x, tid = threadIdx.x;
@@ -230,10 +226,10 @@ __device__ __forceinline__ void stream_grad_z(const GradSrc& s0, const GradSrc& 
         const unsigned h = rem / W, w = rem - h * W;
         ps = split_index(b, h, w, H, W);
       }
-      cp_async16(ring_s + ((d * 3 + 0) * nthr + tid) * 16, s0.ptr + (s0.split ? ps : static_cast<long>(p)) * s0.pix_stride + s0.chan_off + c);
+      cp_async_vec8(ring_s + ((d * 3 + 0) * nthr + tid) * kSlot, s0.ptr + (s0.split ? ps : static_cast<long>(p)) * s0.pix_stride + s0.chan_off + c);
       if (s1.ptr)
-        cp_async16(ring_s + ((d * 3 + 1) * nthr + tid) * 16, s1.ptr + (s1.split ? ps : static_cast<long>(p)) * s1.pix_stride + s1.chan_off + c);
-      cp_async16(ring_s + ((d * 3 + 2) * nthr + tid) * 16, z + static_cast<size_t>(p) * C + c);
+        cp_async_vec8(ring_s + ((d * 3 + 1) * nthr + tid) * kSlot, s1.ptr + (s1.split ? ps : static_cast<long>(p)) * s1.pix_stride + s1.chan_off + c);
+      cp_async_vec8(ring_s + ((d * 3 + 2) * nthr + tid) * kSlot, z + static_cast<size_t>(p) * C + c);
       codes[d] = code ? __ldg(code + p) : static_cast<uint8_t>(0);
     }
     cp_async_commit();
@@ -247,14 +243,14 @@ __device__ __forceinline__ void stream_grad_z(const GradSrc& s0, const GradSrc& 
       if (p < M) {
         cp_async_wait<kRing - 1>();
         float g[8], zz[8];
-        unpack8(ring[(d * 3 + 0) * nthr + tid], g);
+        unpack8(ring + ((d * 3 + 0) * nthr + tid) * 8, g);
         if (s1.ptr) {
           float t[8];
-          unpack8(ring[(d * 3 + 1) * nthr + tid], t);
+          unpack8(ring + ((d * 3 + 1) * nthr + tid) * 8, t);
 #pragma unroll
           for (int j = 0; j < 8; ++j) g[j] += t[j];
         }
-        unpack8(ring[(d * 3 + 2) * nthr + tid], zz);
+        unpack8(ring + ((d * 3 + 2) * nthr + tid) * 8, zz);
         const float r = code ? __ldg(lut + codes[d]) : 1.f;
         issue(p + kRing * stride, d);      // the slot has been read into registers: refill it
         body(p, g, zz, r);
@@ -266,7 +262,8 @@ __device__ __forceinline__ void stream_grad_z(const GradSrc& s0, const GradSrc& 
 
 // sums per channel over all pixels: [0] g', [1] g'*z, [2] r*g', [3] r*z, [4] r   (g' = g * act'(z*scale+shift))
 // block = 256 threads = (C/8 channel vectors) x (256/(C/8) pixel lanes); partial[block][5][C]
-__global__ void bn_bwd_reduce_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16* __restrict__ z, long M,
+template <typename T>
+__global__ void bn_bwd_reduce_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, long M,
                                      int C, int H, int W, const float* __restrict__ scale,
                                      const float* __restrict__ shift, int act, float slope,
                                      const uint8_t* __restrict__ code, const float* __restrict__ lut,
@@ -362,11 +359,12 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, doubl
 
 // gz[p][c] = r[p] * scale[c] * (g' - c1[c] - zhat * c2[c]) = r[p] * (A[c]*g' + Bz[c]*z + Cc[c])
 // Channel-stationary like bn_apply_kernel: the five per-channel coefficients live in registers.
+template <typename T>
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(GradSrc s0, GradSrc s1, const __nv_bfloat16* __restrict__ z, unsigned M, int C, int H, int W,
+bn_bwd_apply_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, unsigned M, int C, int H, int W,
                     const float* __restrict__ shift, const float* __restrict__ coeff, int act, float slope,
                     const uint8_t* __restrict__ code, const float* __restrict__ lut,
-                    __nv_bfloat16* __restrict__ gz) {
+                    T* __restrict__ gz) {
   const unsigned cv = C >> 3;
   const unsigned lanes = blockDim.x / cv;
   const unsigned c = (threadIdx.x % cv) << 3;
@@ -410,13 +408,85 @@ static int ew_grid(long n, int block) {
   return static_cast<int>(g);
 }
 
-static GradSrc to_src(const tg_grad_src& s) {
-  GradSrc r;
-  r.ptr = reinterpret_cast<const __nv_bfloat16*>(s.ptr);
-  r.pix_stride = s.pix_stride;
-  r.chan_off = s.chan_off;
-  r.split = s.split;
+template <typename T>
+static GradSrcT<T> to_src(const tg_grad_src* s) {
+  GradSrcT<T> r;
+  if (s != nullptr && s->ptr != nullptr) {
+    r.ptr = reinterpret_cast<const T*>(s->ptr);
+    r.pix_stride = s->pix_stride;
+    r.chan_off = s->chan_off;
+    r.split = s->split;
+  } else {
+    r.ptr = nullptr;
+    r.pix_stride = 0;
+    r.chan_off = 0;
+    r.split = 0;
+  }
   return r;
+}
+
+template <typename T>
+static int bn_apply_impl(const void* z, int B, int H, int W, int C, const float* scale, const float* shift,
+                         int act, float slope, const uint8_t* code, void* y_nhwc, void* y_split,
+                         int mask_split, void* stream) {
+  TG_REQUIRE(z && scale && shift && C % 8 == 0, "tg_bn_apply: bad arguments (C=%d)", C);
+  TG_REQUIRE(y_nhwc || y_split, "tg_bn_apply: no output requested");
+  TG_REQUIRE(!y_split || (H % 2 == 0 && W % 2 == 0), "tg_bn_apply: parity-split output needs even H, W");
+  TG_REQUIRE(!(mask_split && y_split) || code, "tg_bn_apply: mask_split needs code");
+  const long M = static_cast<long>(B) * H * W;
+  TG_REQUIRE(C / 8 <= 256 && 256 % (C / 8) == 0 && M < (1L << 31), "tg_bn_apply: unsupported C=%d or too many pixels", C);
+  bn_apply_kernel<T><<<ew_grid(M * (C / 8), 512), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const T*>(z), static_cast<unsigned>(M), C, H, W, scale, shift, act, slope, code,
+      reinterpret_cast<T*>(y_nhwc), reinterpret_cast<T*>(y_split), mask_split);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int bn_bwd_reduce_impl(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H,
+                              int W, int C, const float* scale, const float* shift, int act, float slope,
+                              const uint8_t* code, const float* lut_dev, float* partial, int rows_cap,
+                              int* rows_used, void* stream) {
+  TG_REQUIRE(g0 && g0->ptr && z && scale && shift && partial && rows_used, "tg_bn_bwd_reduce: null pointer");
+  TG_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "tg_bn_bwd_reduce: unsupported C=%d", C);
+  TG_REQUIRE(!code || lut_dev, "tg_bn_bwd_reduce: code needs a device LUT");
+  const long M = static_cast<long>(B) * H * W;
+  const int cv = C / 8, lanes = 256 / cv;
+  long grid = (M + lanes - 1) / lanes;
+  const long cap = static_cast<long>(num_sms()) * 4;
+  if (grid > cap) grid = cap;
+  if (grid > rows_cap) grid = rows_cap;
+  TG_REQUIRE(grid >= 1, "tg_bn_bwd_reduce: rows_cap must be >= 1");
+  *rows_used = static_cast<int>(grid);
+  size_t smem = static_cast<size_t>(lanes) * cv * 40 * sizeof(float);
+  const size_t ring_bytes = static_cast<size_t>(kRing) * 3 * 256 * 8 * sizeof(T);
+  if (smem < ring_bytes) smem = ring_bytes;
+  {
+    TG_SET_SMEM_ONCE((bn_bwd_reduce_kernel<T>), 100 * 1024);
+  }
+  bn_bwd_reduce_kernel<T><<<static_cast<int>(grid), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      to_src<T>(g0), to_src<T>(g1), reinterpret_cast<const T*>(z), M, C, H, W, scale, shift, act, slope, code, lut_dev,
+      partial);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int bn_bwd_apply_impl(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H, int W,
+                             int C, const float* shift, const float* coeff, int act, float slope,
+                             const uint8_t* code, const float* lut_dev, void* gz, void* stream) {
+  TG_REQUIRE(g0 && g0->ptr && z && shift && coeff && gz, "tg_bn_bwd_apply: null pointer");
+  TG_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "tg_bn_bwd_apply: unsupported C=%d", C);
+  TG_REQUIRE(!code || lut_dev, "tg_bn_bwd_apply: code needs a device LUT");
+  const long M = static_cast<long>(B) * H * W;
+  {
+    TG_SET_SMEM_ONCE((bn_bwd_apply_kernel<T>), 100 * 1024);
+  }
+  bn_bwd_apply_kernel<T><<<ew_grid(M * (C / 8), 256), 256, kRing * 3 * 256 * 8 * sizeof(T), reinterpret_cast<cudaStream_t>(stream)>>>(
+      to_src<T>(g0), to_src<T>(g1), reinterpret_cast<const T*>(z), static_cast<unsigned>(M), C, H, W, shift, coeff, act, slope,
+      code, lut_dev, reinterpret_cast<T*>(gz));
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace tg
@@ -447,50 +517,27 @@ extern "C" int tg_bn_eval_coeff(int C, const float* gamma, const float* beta, co
 extern "C" int tg_bn_apply(const void* z, int B, int H, int W, int C, const float* scale, const float* shift,
                            int act, float slope, const uint8_t* code, void* y_nhwc, void* y_split,
                            int mask_split, void* stream) {
-  using namespace tg;
-  TG_REQUIRE(z && scale && shift && C % 8 == 0, "tg_bn_apply: bad arguments (C=%d)", C);
-  TG_REQUIRE(y_nhwc || y_split, "tg_bn_apply: no output requested");
-  TG_REQUIRE(!y_split || (H % 2 == 0 && W % 2 == 0), "tg_bn_apply: parity-split output needs even H, W");
-  TG_REQUIRE(!(mask_split && y_split) || code, "tg_bn_apply: mask_split needs code");
-  const long M = static_cast<long>(B) * H * W;
-  TG_REQUIRE(C / 8 <= 256 && 256 % (C / 8) == 0 && M < (1L << 31), "tg_bn_apply: unsupported C=%d or too many pixels", C);
-  bn_apply_kernel<<<ew_grid(M * (C / 8), 512), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(z), static_cast<unsigned>(M), C, H, W, scale, shift, act, slope, code,
-      reinterpret_cast<__nv_bfloat16*>(y_nhwc), reinterpret_cast<__nv_bfloat16*>(y_split), mask_split);
-  TG_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return tg::bn_apply_impl<__nv_bfloat16>(z, B, H, W, C, scale, shift, act, slope, code, y_nhwc, y_split, mask_split, stream);
+}
+extern "C" int tg_bn_apply_f32(const void* z, int B, int H, int W, int C, const float* scale, const float* shift,
+                               int act, float slope, const uint8_t* code, void* y_nhwc, void* y_split,
+                               int mask_split, void* stream) {
+  return tg::bn_apply_impl<float>(z, B, H, W, C, scale, shift, act, slope, code, y_nhwc, y_split, mask_split, stream);
 }
 
 extern "C" int tg_bn_bwd_reduce(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H,
                                 int W, int C, const float* scale, const float* shift, int act, float slope,
                                 const uint8_t* code, const float* lut_dev, float* partial, int rows_cap,
                                 int* rows_used, void* stream) {
-  using namespace tg;
-  TG_REQUIRE(g0 && g0->ptr && z && scale && shift && partial && rows_used, "tg_bn_bwd_reduce: null pointer");
-  TG_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "tg_bn_bwd_reduce: unsupported C=%d", C);
-  TG_REQUIRE(!code || lut_dev, "tg_bn_bwd_reduce: code needs a device LUT");
-  const long M = static_cast<long>(B) * H * W;
-  const int cv = C / 8, lanes = 256 / cv;
-  long grid = (M + lanes - 1) / lanes;
-  const long cap = static_cast<long>(num_sms()) * 4;
-  if (grid > cap) grid = cap;
-  if (grid > rows_cap) grid = rows_cap;
-  TG_REQUIRE(grid >= 1, "tg_bn_bwd_reduce: rows_cap must be >= 1");
-  *rows_used = static_cast<int>(grid);
-  GradSrc s0 = to_src(*g0), s1;
-  if (g1 && g1->ptr) s1 = to_src(*g1);
-  else { s1.ptr = nullptr; s1.pix_stride = 0; s1.chan_off = 0; s1.split = 0; }
-  size_t smem = static_cast<size_t>(lanes) * cv * 40 * sizeof(float);
-  const size_t ring_bytes = static_cast<size_t>(kRing) * 3 * 256 * 16;
-  if (smem < ring_bytes) smem = ring_bytes;
-  {
-    TG_SET_SMEM_ONCE((bn_bwd_reduce_kernel), 64 * 1024);
-  }
-  bn_bwd_reduce_kernel<<<static_cast<int>(grid), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      s0, s1, reinterpret_cast<const __nv_bfloat16*>(z), M, C, H, W, scale, shift, act, slope, code, lut_dev,
-      partial);
-  TG_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return tg::bn_bwd_reduce_impl<__nv_bfloat16>(g0, g1, z, B, H, W, C, scale, shift, act, slope, code, lut_dev, partial,
+                                               rows_cap, rows_used, stream);
+}
+extern "C" int tg_bn_bwd_reduce_f32(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H,
+                                    int W, int C, const float* scale, const float* shift, int act, float slope,
+                                    const uint8_t* code, const float* lut_dev, float* partial, int rows_cap,
+                                    int* rows_used, void* stream) {
+  return tg::bn_bwd_reduce_impl<float>(g0, g1, z, B, H, W, C, scale, shift, act, slope, code, lut_dev, partial, rows_cap,
+                                       rows_used, stream);
 }
 
 extern "C" int tg_bn_bwd_finalize(const float* partial, int rows, int C, double count, const float* scale,
@@ -507,20 +554,10 @@ extern "C" int tg_bn_bwd_finalize(const float* partial, int rows, int C, double 
 extern "C" int tg_bn_bwd_apply(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H, int W,
                                int C, const float* shift, const float* coeff, int act, float slope,
                                const uint8_t* code, const float* lut_dev, void* gz, void* stream) {
-  using namespace tg;
-  TG_REQUIRE(g0 && g0->ptr && z && shift && coeff && gz, "tg_bn_bwd_apply: null pointer");
-  TG_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "tg_bn_bwd_apply: unsupported C=%d", C);
-  TG_REQUIRE(!code || lut_dev, "tg_bn_bwd_apply: code needs a device LUT");
-  const long M = static_cast<long>(B) * H * W;
-  GradSrc s0 = to_src(*g0), s1;
-  if (g1 && g1->ptr) s1 = to_src(*g1);
-  else { s1.ptr = nullptr; s1.pix_stride = 0; s1.chan_off = 0; s1.split = 0; }
-  {
-    TG_SET_SMEM_ONCE((bn_bwd_apply_kernel), 64 * 1024);
-  }
-  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8), 256), 256, kRing * 3 * 256 * 16, reinterpret_cast<cudaStream_t>(stream)>>>(
-      s0, s1, reinterpret_cast<const __nv_bfloat16*>(z), static_cast<unsigned>(M), C, H, W, shift, coeff, act, slope, code, lut_dev,
-      reinterpret_cast<__nv_bfloat16*>(gz));
-  TG_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return tg::bn_bwd_apply_impl<__nv_bfloat16>(g0, g1, z, B, H, W, C, shift, coeff, act, slope, code, lut_dev, gz, stream);
+}
+extern "C" int tg_bn_bwd_apply_f32(const tg_grad_src* g0, const tg_grad_src* g1, const void* z, int B, int H, int W,
+                                   int C, const float* shift, const float* coeff, int act, float slope,
+                                   const uint8_t* code, const float* lut_dev, void* gz, void* stream) {
+  return tg::bn_bwd_apply_impl<float>(g0, g1, z, B, H, W, C, shift, coeff, act, slope, code, lut_dev, gz, stream);
 }

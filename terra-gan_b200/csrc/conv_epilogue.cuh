@@ -276,4 +276,80 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
   }
 }
 
+// fp32-storage epilogue of the verification path (kind::tf32 MMAs, fp32 activations): same arithmetic as
+// conv_epilogue_tile with every feature decided at run time and plain per-row stores (it need not be fast; it has
+// to be the same formula at fp32 precision). `p.out` / `p.gate` are fp32 tensors here.
+template <int BN, int kVec>
+__device__ __forceinline__ void conv_epilogue_tile_f32(const ConvKParams& p, int q, int lane, int nt, int sb, int tw,
+                                                       int th, int tb, uint32_t t_addr, const float* s_vec,
+                                                       float* my_stats, bool has_vec, int hsel, int wt, int ht,
+                                                       int bt) {
+  const int w = tw * p.Wt + wt, h = th * p.Ht + ht, b = tb * p.Bt + bt;
+  const bool valid = (w < p.Wo) && (h < p.Ho) && (b < p.B);
+  const long pix = ((static_cast<long>(b) * p.Po + p.sub[sb].out_plane) * p.Ho + h) * p.Wo + w;
+  float rs = 1.f;
+  if (p.code != nullptr && valid) rs = p.lut[p.code[pix]];
+  const bool has_affine = p.scale != nullptr || p.shift != nullptr;
+  float* out = reinterpret_cast<float*>(p.out);
+  const float* gate = reinterpret_cast<const float*>(p.gate);
+#pragma unroll 1
+  for (int ch = 0; ch < BN / 32; ++ch) {
+    if ((ch & 1) != hsel) continue;
+    uint32_t raw[32];
+    tmem_ld_32x32(t_addr + ch * 32, raw);
+    tmem_ld_wait();
+    const int n0 = nt * BN + ch * 32;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+    if (p.addend != nullptr && valid) {
+      const float* ar = p.addend + pix * p.Cout + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(ar + j);
+        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+      }
+    }
+    if (has_vec) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += s_vec[n0 + j];
+    }
+    if (p.code != nullptr || p.stats != nullptr) {
+      const float rsv = valid ? rs : 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= rsv;
+    }
+    if (p.stats != nullptr) {
+      float sq[32], sm[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        sm[j] = v[j];
+        sq[j] = v[j] * v[j];
+      }
+      const float csum = warp_transpose_sum32(sm);
+      const float csq = warp_transpose_sum32(sq);
+      my_stats[n0 + lane] += csum;
+      my_stats[kVec + n0 + lane] += csq;
+    }
+    if (valid) {
+      float* orow = out + pix * p.Cout + n0;
+      const float* grow = gate ? gate + pix * p.Cout + n0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float a = v[j + e];
+          if (has_affine) a = a * s_vec[kVec + n0 + j + e] + s_vec[2 * kVec + n0 + j + e];
+          if (grow != nullptr && !(grow[j + e] > 0.f)) a *= p.gate_slope;
+          if (p.act == 1) a = fmaxf(a, 0.f);
+          else if (p.act == 2) a = a > 0.f ? a : a * p.slope;
+          o[e] = a;
+        }
+        *reinterpret_cast<float4*>(orow + j) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 }  // namespace tg

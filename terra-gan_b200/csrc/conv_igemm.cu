@@ -43,7 +43,9 @@ struct ConvSmem {
   static constexpr int kTotal = kTiles + (kStatsFloats + kVecFloats) * 4 + kStageOutBytes + 256 + 1024;
 };
 
-template <int BN>
+// kF32: fp32 activations / weights in shared memory (TMA boxes of 32 channels = the same 128-byte rows),
+// kind::tf32 MMAs, fp32 output -- the verification path.
+template <int BN, bool kF32 = false>
 __global__ void __launch_bounds__(384, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvKParams p) {
@@ -65,6 +67,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int kKB = kF32 ? 32 : 64;      // channels per K block (128 bytes)
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
 
@@ -126,8 +129,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint8_t* sa = smem + stage * S::kStageBytes;
             uint8_t* sbm = sa + kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-            tma_load_5d(sa, &tmA, &full_bar[stage], cb * 64, w0 + dw, h0 + dh, pl, b0);
-            tma_load_2d(sbm, &tmB, &full_bar[stage], sub.k_off + (t * p.cin_blocks + cb) * 64,
+            tma_load_5d(sa, &tmA, &full_bar[stage], cb * kKB, w0 + dw, h0 + dh, pl, b0);
+            tma_load_2d(sbm, &tmB, &full_bar[stage], sub.k_off + (t * p.cin_blocks + cb) * kKB,
                         nt * BN);
             if (++stage == kStages) {
               stage = 0;
@@ -141,7 +144,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== MMA issuer =====================
     // whole warp runs the loop (warp-uniform descriptors in uniform registers); one elected lane issues
     {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+      constexpr uint32_t idesc = kF32 ? make_idesc_tf32(128, BN, false, false) : make_idesc_bf16(128, BN, false, false);
       const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);     // A and B: K-major, 8-row atoms 1024 B apart
       const uint32_t d_lo0 = static_cast<uint32_t>(d0), d_hi = static_cast<uint32_t>(d0 >> 32);
       int stage = 0;
@@ -162,8 +165,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t b_lo = a_lo + (kABytes >> 4);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_lh(d_tmem, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
+            for (int k = 0; k < 4; ++k) {
+              if (kF32) umma_tf32_lh(d_tmem, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
+              else umma_bf16_lh(d_tmem, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
+            }
             umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           }
           if (++stage == kStages) {
@@ -185,6 +190,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* my_stats = s_stats + q * (2 * 512);
     const int row = q * 32 + lane;                     // row of the tile = pixel in box order
     const int e_wt = row % p.Wt, e_ht = (row / p.Wt) % p.Ht, e_bt = row / (p.Wt * p.Ht);
+    if constexpr (kF32) {
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int rest = tile / p.n_tiles;
+        const int mt = rest % m_tiles;
+        const int sb = rest / m_tiles;
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int tb = mt / (p.tiles_w * p.tiles_h);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+        conv_epilogue_tile_f32<BN, 512>(p, q, lane, nt, sb, tw, th, tb, t_addr, s_vec, my_stats, has_vec, hsel, e_wt,
+                                        e_ht, e_bt);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    } else {
     const int epi_mode = conv_epilogue_mode(p.code, p.stats, p.gate, p.scale, p.shift, p.bias);
     conv_epilogue_dispatch(epi_mode, [&](auto mode_tag) {
       constexpr int kMode = decltype(mode_tag)::value;
@@ -215,6 +245,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     });
+    }
     // flush the per-CTA BatchNorm partials: one row per CTA, summed by tg_bn_finalize
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -278,12 +309,12 @@ static void choose_box(int Ho, int Wo, int pixels, int* Bt, int* Ht, int* Wt) {
   *Bt = pixels / (wt * ht);
 }
 
-template <int BN>
+template <int BN, bool kF32 = false>
 static int launch_conv(const tg_conv_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        const ConvKParams& kp, int grid, cudaStream_t st) {
   using S = ConvSmem<BN>;
-  TG_SET_SMEM_ONCE((conv_igemm_kernel<BN>), S::kTotal);
-  conv_igemm_kernel<BN><<<grid, 384, S::kTotal, st>>>(tmA, tmB, kp);
+  TG_SET_SMEM_ONCE((conv_igemm_kernel<BN, kF32>), S::kTotal);
+  conv_igemm_kernel<BN, kF32><<<grid, 384, S::kTotal, st>>>(tmA, tmB, kp);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -293,7 +324,11 @@ static int launch_conv(const tg_conv_args* a, const CUtensorMap& tmA, const CUte
 extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   using namespace tg;
   TG_REQUIRE(a != nullptr, "tg_conv_igemm: null args");
-  TG_REQUIRE(a->C > 0 && a->C % 64 == 0, "tg_conv_igemm: C=%d must be a positive multiple of 64", a->C);
+  TG_REQUIRE(a->dtype == TG_DTYPE_BF16 || a->dtype == TG_DTYPE_F32, "tg_conv_igemm: bad dtype %d", a->dtype);
+  const bool f32 = a->dtype == TG_DTYPE_F32;
+  const int kb_elems = f32 ? 32 : 64;          // channels per 128-byte K block
+  const int esz = f32 ? 4 : 2;
+  TG_REQUIRE(a->C > 0 && a->C % kb_elems == 0, "tg_conv_igemm: C=%d must be a positive multiple of %d", a->C, kb_elems);
   const bool per_channel = a->bias || a->scale || a->shift || a->stats;
   TG_REQUIRE(a->N > 0 && a->N % 64 == 0 && a->N <= (per_channel ? 512 : 1024),
              "tg_conv_igemm: N=%d must be a multiple of 64 and <= %d", a->N, per_channel ? 512 : 1024);
@@ -304,7 +339,7 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   TG_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
              "tg_conv_igemm: x/w/out must be 16-byte aligned");
-  TG_REQUIRE(a->Ktot % 64 == 0, "tg_conv_igemm: Ktot=%d must be a multiple of 64", a->Ktot);
+  TG_REQUIRE(a->Ktot % kb_elems == 0, "tg_conv_igemm: Ktot=%d must be a multiple of %d", a->Ktot, kb_elems);
   for (int s = 0; s < a->num_sub; ++s) {
     const tg_conv_sub& sb = a->sub[s];
     TG_REQUIRE(sb.tap_begin >= 0 && sb.tap_count >= 1 && sb.tap_begin + sb.tap_count <= a->num_taps,
@@ -335,7 +370,7 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
     kp.tap_dh[t] = a->tap_dh[t];
     kp.tap_dw[t] = a->tap_dw[t];
   }
-  kp.cin_blocks = a->C / 64;
+  kp.cin_blocks = a->C / kb_elems;
   kp.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   kp.B = a->B;
   kp.Ho = a->Ho;
@@ -353,6 +388,8 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   kp.stats = a->stats;
   kp.gate = reinterpret_cast<const __nv_bfloat16*>(a->gate);
   kp.gate_slope = a->gate_slope;
+  kp.addend = a->addend;
+  TG_REQUIRE(a->addend == nullptr || f32, "tg_conv_igemm: addend is an fp32-path feature");
 #ifdef TG_PERF_DEBUG
   {
     static const int dbg = [] { const char* e = getenv("TG_CONV_DEBUG"); return e ? atoi(e) : 0; }();
@@ -360,27 +397,29 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   }
 #endif
 
-  // small-N 3x3 stride-1 layers: halo-tile reuse + resident weights (conv_halo.cu)
-  if (halo_enabled() && conv_halo_eligible(a)) return conv_halo_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
-  if (halo_enabled() != 0 && halo_stream_enabled() && conv_halo_stream_eligible(a))
-    return conv_halo_stream_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
-  if (halo_enabled() != 0 && halo_stream_enabled() && conv_halo_s2dgrad_eligible(a))
-    return conv_halo_s2dgrad_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
+  // small-N 3x3 stride-1 layers: halo-tile reuse + resident weights (conv_halo.cu); bf16 storage only
+  if (!f32) {
+    if (halo_enabled() && conv_halo_eligible(a)) return conv_halo_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
+    if (halo_enabled() != 0 && halo_stream_enabled() && conv_halo_stream_eligible(a))
+      return conv_halo_stream_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
+    if (halo_enabled() != 0 && halo_stream_enabled() && conv_halo_s2dgrad_eligible(a))
+      return conv_halo_s2dgrad_launch(a, kp, reinterpret_cast<cudaStream_t>(stream));
+  }
 
   // A: channels-last activations as a 5-D tensor (C, W, H, P, B)
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[5] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->P, (uint64_t)a->B};
-    uint64_t str[4] = {(uint64_t)a->C * 2, (uint64_t)a->C * 2 * a->W, (uint64_t)a->C * 2 * a->W * a->H,
-                       (uint64_t)a->C * 2 * a->W * a->H * a->P};
-    uint32_t box[5] = {64, (uint32_t)kp.Wt, (uint32_t)kp.Ht, 1, (uint32_t)kp.Bt};
-    if (make_tmap_bf16(&tmA, a->x, 5, dims, str, box) != 0) return -3;
+    uint64_t str[4] = {(uint64_t)a->C * esz, (uint64_t)a->C * esz * a->W, (uint64_t)a->C * esz * a->W * a->H,
+                       (uint64_t)a->C * esz * a->W * a->H * a->P};
+    uint32_t box[5] = {(uint32_t)kb_elems, (uint32_t)kp.Wt, (uint32_t)kp.Ht, 1, (uint32_t)kp.Bt};
+    if ((f32 ? make_tmap_f32 : make_tmap_bf16)(&tmA, a->x, 5, dims, str, box) != 0) return -3;
   }
   {
     uint64_t dims[2] = {(uint64_t)a->Ktot, (uint64_t)a->N};
-    uint64_t str[1] = {(uint64_t)a->Ktot * 2};
-    uint32_t box[2] = {64, (uint32_t)BN};
-    if (make_tmap_bf16(&tmB, a->w, 2, dims, str, box) != 0) return -3;
+    uint64_t str[1] = {(uint64_t)a->Ktot * esz};
+    uint32_t box[2] = {(uint32_t)kb_elems, (uint32_t)BN};
+    if ((f32 ? make_tmap_f32 : make_tmap_bf16)(&tmB, a->w, 2, dims, str, box) != 0) return -3;
   }
   const long total_tiles = (long)kp.num_sub * kp.tiles_b * kp.tiles_h * kp.tiles_w * kp.n_tiles;
   const int sms = num_sms();
@@ -391,6 +430,12 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   }
   a->stats_rows_used = grid;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (f32) {
+    if (BN == 256) return launch_conv<256, true>(a, tmA, tmB, kp, grid, st);
+    if (BN == 192) return launch_conv<192, true>(a, tmA, tmB, kp, grid, st);
+    if (BN == 128) return launch_conv<128, true>(a, tmA, tmB, kp, grid, st);
+    return launch_conv<64, true>(a, tmA, tmB, kp, grid, st);
+  }
   if (BN == 256) return launch_conv<256>(a, tmA, tmB, kp, grid, st);
   if (BN == 192) return launch_conv<192>(a, tmA, tmB, kp, grid, st);
   if (BN == 128) return launch_conv<128>(a, tmA, tmB, kp, grid, st);

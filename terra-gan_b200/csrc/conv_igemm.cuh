@@ -42,6 +42,7 @@ struct ConvKParams {
   const __nv_bfloat16* gate;      // same shape as out, or null: out *= (gate > 0 ? 1 : gate_slope)
   float gate_slope;
   int debug;                      // perf experiments only: 1 no stores, 2 no epilogue work, 4 no MMA
+  const float* addend;            // fp32 path only: [out shape] added to the accumulator before the epilogue, or null
 };
 
 #ifdef __CUDACC__

@@ -25,12 +25,12 @@ __device__ __forceinline__ long dc_split_index(int b, int h, int w, int H, int W
 // ------------------------------------------------------------------------------------------------
 constexpr int kC1TW = 32, kC1TH = 4;
 
-template <int K, int S>
+template <int K, int S, typename TO = __nv_bfloat16>
 __global__ void __launch_bounds__(128, 4)
 conv_c1_fwd_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmask, int B, int H, int W, int pad,
                    const float* __restrict__ wgt /*[64][K*K]*/, const float* __restrict__ bias, int Ho, int Wo,
                    const uint8_t* __restrict__ code, const float* __restrict__ lut, int act, float slope,
-                   __nv_bfloat16* __restrict__ out, int out_split, float* __restrict__ stats) {
+                   TO* __restrict__ out, int out_split, float* __restrict__ stats) {
   constexpr int IW = (kC1TW - 1) * S + K, IH = (kC1TH - 1) * S + K;
   __shared__ float s_w[K * K][64];
   __shared__ float s_in[IH][IW + 1];
@@ -105,6 +105,25 @@ conv_c1_fwd_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmas
     // A thread owns one pixel row (128 B): storing it directly would touch 32 different lines per
     // instruction. Rows go through a per-warp XOR-swizzled staging tile and are written back 4 rows
     // (512 contiguous bytes in the plain layout) per instruction.
+    if constexpr (sizeof(TO) == 4) {
+      // fp32 storage (verification path): each thread writes its own 256-byte pixel row
+      if (valid) {
+        const long opix = out_split ? dc_split_index(b, ho, wo, Ho, Wo) : pix;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float t = acc[8 * j + q];
+            if (act == 1) t = fmaxf(t, 0.f);
+            else if (act == 2) t = t > 0.f ? t : t * slope;
+            v[q] = t;
+          }
+          vstore8(reinterpret_cast<float*>(out) + opix * 64 + 8 * j, v);
+        }
+      }
+      continue;
+    }
     uint4* st = &s_stage[warp][0];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -148,10 +167,15 @@ conv_c1_fwd_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmas
 // 1 -> 64 channels, weight (and bias) gradient. Warp = pixel stream, lane = output-channel pair.
 // partial[block][64][K*K (+1 for bias)]
 // ------------------------------------------------------------------------------------------------
-template <int K, int S>
+__device__ __forceinline__ float2 dc_ld2(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+__device__ __forceinline__ float2 dc_ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+template <int K, int S, typename TG = __nv_bfloat16>
 __global__ void __launch_bounds__(256, 2)
 conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xmask, int B, int H, int W, int pad,
-                     const __nv_bfloat16* __restrict__ g /*[B][Ho][Wo][64]*/, int Ho, int Wo, int g_split,
+                     const TG* __restrict__ g /*[B][Ho][Wo][64]*/, int Ho, int Wo, int g_split,
                      float* __restrict__ partial) {
   // Block = one 32x4 tile of output pixels at a time (persistent over tiles); the masked, zero-padded
   // input patch is staged in shared memory once, then warp w streams 16 of the 128 pixels: lane =
@@ -174,15 +198,15 @@ conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xm
     const int ih0 = th * kC1TH * S - pad, iw0 = tw * kC1TW * S - pad;
     // gradient rows of this warp's 16 pixels, fetched in batches of 4 one batch ahead of their use
     // (one dependent 128-byte load per pixel left the kernel latency-bound at ~0.4 TB/s)
-    auto load_g = [&](int q) -> __nv_bfloat162 {
+    auto load_g = [&](int q) -> float2 {
       const int pt = warp * 16 + q;
       const int ho = th * kC1TH + pt / kC1TW, wo = tw * kC1TW + pt % kC1TW;
-      if (ho >= Ho || wo >= Wo) return __floats2bfloat162_rn(0.f, 0.f);   // contributes nothing
+      if (ho >= Ho || wo >= Wo) return make_float2(0.f, 0.f);   // contributes nothing
       const long p = (static_cast<long>(b) * Ho + ho) * Wo + wo;
       const long gp = g_split ? dc_split_index(b, ho, wo, Ho, Wo) : p;
-      return *reinterpret_cast<const __nv_bfloat162*>(g + gp * 64 + 2 * lane);
+      return dc_ld2(g + gp * 64 + 2 * lane);
     };
-    __nv_bfloat162 gn[4];
+    float2 gn[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) gn[j] = load_g(j);
     __syncthreads();
@@ -200,7 +224,7 @@ conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xm
     __syncthreads();
 #pragma unroll 1
     for (int qb = 0; qb < 4; ++qb) {
-      __nv_bfloat162 gc[4];
+      float2 gc[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) gc[j] = gn[j];
       if (qb < 3) {
@@ -211,7 +235,7 @@ conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xm
       for (int j = 0; j < 4; ++j) {
         const int pt = warp * 16 + qb * 4 + j;
         const int tx = pt % kC1TW, ty = pt / kC1TW;
-        const float2 gf = __bfloat1622float2(gc[j]);
+        const float2 gf = gc[j];
         acc[T][0] += gf.x;
         acc[T][1] += gf.y;
 #pragma unroll
@@ -263,8 +287,9 @@ __global__ void conv_c1_wgrad_reduce_kernel(const float* __restrict__ partial, i
 // 8 lanes per output pixel (8 channels each, 16-byte loads), 4 pixels per warp.
 // ------------------------------------------------------------------------------------------------
 
+template <typename TX>
 __global__ void __launch_bounds__(256)
-conv_to1_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_split, int B, int H, int W, int C,
+conv_to1_fwd_kernel(const TX* __restrict__ x, int x_split, int B, int H, int W, int C,
                     const float* __restrict__ wgt /*[ntaps][C]*/, To1Taps taps, const float* __restrict__ bias, int Ho, int Wo, int mode,
                     const uint8_t* __restrict__ mask, const float* __restrict__ xin, float* __restrict__ out,
                     float* __restrict__ sig_out) {
@@ -288,22 +313,20 @@ conv_to1_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_split, int B, int
         bh = oh >> 1;
         bw = ow >> 1;
       }
-      const __nv_bfloat16* xb = x + static_cast<long>(b) * H * W * C;
+      const TX* xb = x + static_cast<long>(b) * H * W * C;
       for (int t = taps.begin[cls]; t < taps.begin[cls] + taps.count[cls]; ++t) {
         const int h = bh + taps.dh[t], w = bw + taps.dw[t];
         if (h < 0 || h >= H || w < 0 || w >= W) continue;
-        const __nv_bfloat16* xp = x_split ? x + dc_split_index(b, h, w, H, W) * C
-                                          : xb + (static_cast<long>(h) * W + w) * C;
+        const TX* xp = x_split ? x + dc_split_index(b, h, w, H, W) * C
+                               : xb + (static_cast<long>(h) * W + w) * C;
         const float* wp = wgt + static_cast<long>(t) * C;
         for (int c = sub * 8; c < C; c += 64) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(xp + c);
-          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          float xv[8];
+          vload8(xp + c, xv);
           const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + c));
           const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + c) + 1);
-          const float2 a = __bfloat1622float2(hh[0]), bq = __bfloat1622float2(hh[1]);
-          const float2 cq = __bfloat1622float2(hh[2]), d = __bfloat1622float2(hh[3]);
-          acc += a.x * w0.x + a.y * w0.y + bq.x * w0.z + bq.y * w0.w + cq.x * w1.x + cq.y * w1.y + d.x * w1.z +
-                 d.y * w1.w;
+          acc += xv[0] * w0.x + xv[1] * w0.y + xv[2] * w0.z + xv[3] * w0.w + xv[4] * w1.x + xv[5] * w1.y + xv[6] * w1.z +
+                 xv[7] * w1.w;
         }
       }
     }
@@ -315,7 +338,7 @@ conv_to1_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_split, int B, int
       if (mode == 0) {
         out[p] = v;
       } else {
-        const float s = 1.f / (1.f + __expf(-v));
+        const float s = sizeof(TX) == 4 ? 1.f / (1.f + expf(-v)) : 1.f / (1.f + __expf(-v));
         if (sig_out) sig_out[p] = s;
         const float m = mask[p] ? 1.f : 0.f;
         out[p] = s * (1.f - m) + xin[p] * m;
@@ -602,9 +625,10 @@ static bool make_tap3x3(Tap3x3* tp, int ntaps, const int8_t* dh, const int8_t* d
 }
 
 // data gradient of a stride-1 C->1 conv: dx[b][h][w][c] = sum_t g[b][h - dh_t][w - dw_t] * w[t][c]
+template <typename TO>
 __global__ void __launch_bounds__(256)
 conv_to1_bwd_data_kernel(const float* __restrict__ g, int B, int Ho, int Wo, const float* __restrict__ wgt, To1Taps taps,
-                         int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
+                         int H, int W, int C, TO* __restrict__ dx) {
   const int cv = C >> 3;
   const long total = static_cast<long>(B) * H * W * cv;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -626,9 +650,7 @@ conv_to1_bwd_data_kernel(const float* __restrict__ g, int B, int Ho, int Wo, con
       acc[0] += gv * w0.x; acc[1] += gv * w0.y; acc[2] += gv * w0.z; acc[3] += gv * w0.w;
       acc[4] += gv * w1.x; acc[5] += gv * w1.y; acc[6] += gv * w1.z; acc[7] += gv * w1.w;
     }
-    *reinterpret_cast<uint4*>(dx + p * C + c) =
-        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                   pack_bf16x2(acc[6], acc[7]));
+    vstore8(dx + p * C + c, acc);
   }
 }
 
@@ -686,9 +708,9 @@ conv3x3_c64_to1_bwd_data_kernel(const float* __restrict__ g, int B, int H, int W
 
 // weight gradient of a stride-1 C->1 conv: dw[t][c] = sum_o g[o] * x[o + d_t][c]; db = sum_o g[o].
 // grid = (pixel blocks, C/64); 8 lanes per pixel; each lane keeps T x 8 accumulators.
-template <int T>
+template <int T, typename TX = __nv_bfloat16>
 __global__ void __launch_bounds__(128)
-conv_to1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ g,
+conv_to1_wgrad_kernel(const TX* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ g,
                       int Ho, int Wo, To1Taps taps, float* __restrict__ partial /*[gridDim.x][T][C]*/,
                       float* __restrict__ partial_b /*[gridDim.x]*/) {
   __shared__ float s_red[T][64];  // [tap][channel of the slab], accumulated with shared atomics
@@ -711,19 +733,15 @@ conv_to1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, 
     const int b = static_cast<int>(p / (static_cast<long>(Wo) * Ho));
     const float gv = __ldg(g + p);
     gsum += gv;
-    const __nv_bfloat16* xb = x + static_cast<long>(b) * H * W * C + c0;
+    const TX* xb = x + static_cast<long>(b) * H * W * C + c0;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const int h = oh + taps.dh[t], w = ow + taps.dw[t];
       if (h < 0 || h >= H || w < 0 || w >= W) continue;
-      const uint4 raw = *reinterpret_cast<const uint4*>(xb + (static_cast<long>(h) * W + w) * C);
-      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      float f[8];
+      vload8(xb + (static_cast<long>(h) * W + w) * C, f);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 f = __bfloat1622float2(hh[q]);
-        acc[t][2 * q] += gv * f.x;
-        acc[t][2 * q + 1] += gv * f.y;
-      }
+      for (int q = 0; q < 8; ++q) acc[t][q] += gv * f[q];
     }
   }
 #pragma unroll
@@ -918,7 +936,7 @@ extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, 
   }
   const long M = static_cast<long>(B) * Ho * Wo;
   const int grid = dc_grid(M * 8, 256, 8);
-  conv_to1_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  conv_to1_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), x_split, B, H, W, C, wgt, taps, bias, Ho, Wo, mode, mask, xin, out,
       sig_out);
   TG_CHECK_CUDA(cudaGetLastError());
@@ -959,7 +977,7 @@ extern "C" int tg_conv_to1_bwd_data(const float* g, int B, int Ho, int Wo, const
     TG_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
-  conv_to1_bwd_data_kernel<<<dc_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  conv_to1_bwd_data_kernel<__nv_bfloat16><<<dc_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       g, B, Ho, Wo, wgt, taps, H, W, C, reinterpret_cast<__nv_bfloat16*>(dx));
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1021,3 +1039,118 @@ extern "C" int tg_conv_to1_wgrad(const void* x, int B, int H, int W, int C, cons
 }
 
 extern "C" int tg_conv_to1_wgrad_rows(void) { return tg::num_sms() * 8; }
+
+// ------------------------------------------------------------------------------------------------
+// fp32-storage twins (verification path): the generic CUDA-core kernels above with fp32 activations.
+// ------------------------------------------------------------------------------------------------
+extern "C" int tg_conv_c1_fwd_f32(const float* x, const uint8_t* xmask, int B, int H, int W, int k, int s, int pad,
+                                  const float* wgt, const float* bias, const uint8_t* code, const float* lut_dev, int act,
+                                  float slope, void* out, int out_split, float* stats, int stats_rows_cap,
+                                  int* stats_rows_used, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && wgt && bias && out, "tg_conv_c1_fwd_f32: null pointer");
+  TG_REQUIRE(!code || lut_dev, "tg_conv_c1_fwd_f32: code needs a device LUT");
+  const int Ho = (H + 2 * pad - k) / s + 1, Wo = (W + 2 * pad - k) / s + 1;
+  TG_REQUIRE(!out_split || (Ho % 2 == 0 && Wo % 2 == 0), "tg_conv_c1_fwd_f32: parity-split output needs even Ho, Wo");
+  const long tiles = static_cast<long>(B) * ((Ho + kC1TH - 1) / kC1TH) * ((Wo + kC1TW - 1) / kC1TW);
+  int grid = static_cast<int>(tiles < 4L * num_sms() ? tiles : 4L * num_sms());
+  if (stats) {
+    TG_REQUIRE(stats_rows_used != nullptr, "tg_conv_c1_fwd_f32: stats_rows_used is null");
+    if (grid > stats_rows_cap) grid = stats_rows_cap;
+    TG_REQUIRE(grid >= 1, "tg_conv_c1_fwd_f32: stats_rows_cap must be >= 1");
+    *stats_rows_used = grid;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* o = reinterpret_cast<float*>(out);
+  bool handled = false;
+  TG_C1_DISPATCH(7, 2, (conv_c1_fwd_kernel<K, S, float><<<grid, 128, 0, st>>>(x, xmask, B, H, W, pad, wgt, bias, Ho, Wo, code, lut_dev, act, slope, o, out_split, stats)))
+  TG_C1_DISPATCH(4, 2, (conv_c1_fwd_kernel<K, S, float><<<grid, 128, 0, st>>>(x, xmask, B, H, W, pad, wgt, bias, Ho, Wo, code, lut_dev, act, slope, o, out_split, stats)))
+  TG_C1_DISPATCH(3, 1, (conv_c1_fwd_kernel<K, S, float><<<grid, 128, 0, st>>>(x, xmask, B, H, W, pad, wgt, bias, Ho, Wo, code, lut_dev, act, slope, o, out_split, stats)))
+  TG_REQUIRE(handled, "tg_conv_c1_fwd_f32: unsupported window k=%d s=%d (supported: 7/2, 4/2, 3/1)", k, s);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_conv_c1_wgrad_f32(const float* x, const uint8_t* xmask, int B, int H, int W, int k, int s, int pad,
+                                    const void* g, int g_split, float* partial, int rows_cap, float* dw, float* db,
+                                    int accumulate, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && g && partial && dw, "tg_conv_c1_wgrad_f32: null pointer");
+  const int Ho = (H + 2 * pad - k) / s + 1, Wo = (W + 2 * pad - k) / s + 1;
+  const long tiles = static_cast<long>(B) * ((Ho + kC1TH - 1) / kC1TH) * ((Wo + kC1TW - 1) / kC1TW);
+  int grid = static_cast<int>(tiles < 2L * num_sms() ? tiles : 2L * num_sms());
+  if (grid > rows_cap) grid = rows_cap;
+  TG_REQUIRE(grid >= 1, "tg_conv_c1_wgrad_f32: rows_cap must be >= 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float* gg = reinterpret_cast<const float*>(g);
+  bool handled = false;
+  TG_C1_DISPATCH(7, 2, (conv_c1_wgrad_kernel<K, S, float><<<grid, 256, 0, st>>>(x, xmask, B, H, W, pad, gg, Ho, Wo, g_split, partial)))
+  TG_C1_DISPATCH(4, 2, (conv_c1_wgrad_kernel<K, S, float><<<grid, 256, 0, st>>>(x, xmask, B, H, W, pad, gg, Ho, Wo, g_split, partial)))
+  TG_C1_DISPATCH(3, 1, (conv_c1_wgrad_kernel<K, S, float><<<grid, 256, 0, st>>>(x, xmask, B, H, W, pad, gg, Ho, Wo, g_split, partial)))
+  TG_REQUIRE(handled, "tg_conv_c1_wgrad_f32: unsupported window k=%d s=%d", k, s);
+  TG_CHECK_CUDA(cudaGetLastError());
+  const int T = k * k;
+  conv_c1_wgrad_reduce_kernel<<<(64 * (T + 1) + 127) / 128, 128, 0, st>>>(partial, grid, T, dw, db, accumulate);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_conv_to1_fwd_f32(const void* x, int x_split, int B, int H, int W, int C, const float* wgt, int ncls,
+                                   const int* cls_count, const int8_t* tap_dh, const int8_t* tap_dw, const float* bias,
+                                   int Ho, int Wo, int mode, const uint8_t* mask, const float* xin, float* out,
+                                   float* sig_out, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && wgt && out && cls_count && tap_dh && tap_dw, "tg_conv_to1_fwd_f32: null pointer");
+  TG_REQUIRE(C % 64 == 0, "tg_conv_to1_fwd_f32: C=%d must be a multiple of 64", C);
+  TG_REQUIRE(ncls == 1 || ncls == 4, "tg_conv_to1_fwd_f32: ncls must be 1 or 4");
+  TG_REQUIRE(mode == 0 || (mask && xin), "tg_conv_to1_fwd_f32: composite mode needs mask and xin");
+  To1Taps taps;
+  TG_REQUIRE(fill_taps(&taps, ncls, cls_count, tap_dh, tap_dw) > 0, "tg_conv_to1_fwd_f32: bad tap table");
+  const long M = static_cast<long>(B) * Ho * Wo;
+  conv_to1_fwd_kernel<float><<<dc_grid(M * 8, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float*>(x), x_split, B, H, W, C, wgt, taps, bias, Ho, Wo, mode, mask, xin, out, sig_out);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_conv_to1_bwd_data_f32(const float* g, int B, int Ho, int Wo, const float* wgt, int ntaps,
+                                        const int8_t* tap_dh, const int8_t* tap_dw, int H, int W, int C, void* dx,
+                                        void* stream) {
+  using namespace tg;
+  TG_REQUIRE(g && wgt && dx && tap_dh && tap_dw && C % 8 == 0, "tg_conv_to1_bwd_data_f32: bad arguments");
+  To1Taps taps;
+  TG_REQUIRE(fill_taps(&taps, 1, &ntaps, tap_dh, tap_dw) > 0, "tg_conv_to1_bwd_data_f32: bad tap table");
+  const long total = static_cast<long>(B) * H * W * (C / 8);
+  conv_to1_bwd_data_kernel<float><<<dc_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      g, B, Ho, Wo, wgt, taps, H, W, C, reinterpret_cast<float*>(dx));
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_conv_to1_wgrad_f32(const void* x, int B, int H, int W, int C, const float* g, int Ho, int Wo,
+                                     int ntaps, const int8_t* tap_dh, const int8_t* tap_dw, float* partial,
+                                     float* partial_b, int rows_cap, float* dw, float* db, int accumulate,
+                                     void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && g && partial && dw && tap_dh && tap_dw, "tg_conv_to1_wgrad_f32: null pointer");
+  TG_REQUIRE(C % 64 == 0, "tg_conv_to1_wgrad_f32: C must be a multiple of 64");
+  To1Taps taps;
+  TG_REQUIRE(fill_taps(&taps, 1, &ntaps, tap_dh, tap_dw) > 0, "tg_conv_to1_wgrad_f32: bad tap table");
+  const long M = static_cast<long>(B) * Ho * Wo;
+  int gx = dc_grid(M, 16, 4);
+  const int slabs = C / 64;
+  if (gx * slabs > 8 * num_sms()) gx = (8 * num_sms() + slabs - 1) / slabs;
+  if (gx > rows_cap) gx = rows_cap;
+  TG_REQUIRE(gx >= 1, "tg_conv_to1_wgrad_f32: rows_cap must be >= 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float* xx = reinterpret_cast<const float*>(x);
+  dim3 grid(gx, slabs);
+  if (ntaps == 9) conv_to1_wgrad_kernel<9, float><<<grid, 128, 0, st>>>(xx, B, H, W, C, g, Ho, Wo, taps, partial, partial_b);
+  else if (ntaps == 16) conv_to1_wgrad_kernel<16, float><<<grid, 128, 0, st>>>(xx, B, H, W, C, g, Ho, Wo, taps, partial, partial_b);
+  else TG_REQUIRE(false, "tg_conv_to1_wgrad_f32: unsupported tap count %d (supported: 9, 16)", ntaps);
+  TG_CHECK_CUDA(cudaGetLastError());
+  conv_to1_wgrad_reduce_kernel<<<(ntaps * C + 127) / 128, 128, 0, st>>>(partial, partial_b, gx, ntaps, C, dw, db,
+                                                                       accumulate);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -151,22 +151,19 @@ inpaint_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict_
 }
 
 // mean |a - b| over bf16 tensors (perceptual term on VGG features)
+template <typename T>
 __global__ void __launch_bounds__(256)
-l1_bf16_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, long n8,
+l1_bf16_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, long n8,
                    float* __restrict__ partial) {
   __shared__ float s_tmp[8];
   float acc = 0.f;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const uint4 ra = reinterpret_cast<const uint4*>(a)[i];
-    const uint4 rb = reinterpret_cast<const uint4*>(b)[i];
-    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ra);
-    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rb);
+    float fa[8], fb[8];
+    vload8(a + 8 * i, fa);
+    vload8(b + 8 * i, fb);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 fa = __bfloat1622float2(ha[q]), fb = __bfloat1622float2(hb[q]);
-      acc += fabsf(fa.x - fb.x) + fabsf(fa.y - fb.y);
-    }
+    for (int q = 0; q < 8; q += 2) acc += fabsf(fa[q] - fb[q]) + fabsf(fa[q + 1] - fb[q + 1]);
   }
   const float r = block_sum_256(acc, s_tmp);
   if (threadIdx.x == 0) partial[blockIdx.x] = r;
@@ -181,32 +178,24 @@ __global__ void l1_bf16_finalize_kernel(const float* __restrict__ partial, int r
 }
 
 // ga = go * sign(a - b) / n * [a > 0 if relu_gate]   (gradient w.r.t. the pre-ReLU conv output)
-__global__ void l1_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+template <typename T>
+__global__ void l1_bf16_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                    long n8, const float* __restrict__ go, float inv_n, int relu_gate,
-                                   __nv_bfloat16* __restrict__ ga) {
+                                   T* __restrict__ ga) {
   const float s = go[0] * inv_n;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const uint4 ra = reinterpret_cast<const uint4*>(a)[i];
-    const uint4 rb = reinterpret_cast<const uint4*>(b)[i];
-    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ra);
-    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rb);
-    float o[8];
+    float fa[8], fb[8], o[8];
+    vload8(a + 8 * i, fa);
+    vload8(b + 8 * i, fb);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 fa = __bfloat1622float2(ha[q]), fb = __bfloat1622float2(hb[q]);
-      const float d0 = fa.x - fb.x, d1 = fa.y - fb.y;
+    for (int q = 0; q < 8; ++q) {
+      const float d0 = fa[q] - fb[q];
       float g0 = d0 > 0.f ? s : (d0 < 0.f ? -s : 0.f);
-      float g1 = d1 > 0.f ? s : (d1 < 0.f ? -s : 0.f);
-      if (relu_gate) {
-        if (!(fa.x > 0.f)) g0 = 0.f;
-        if (!(fa.y > 0.f)) g1 = 0.f;
-      }
-      o[2 * q] = g0;
-      o[2 * q + 1] = g1;
+      if (relu_gate && !(fa[q] > 0.f)) g0 = 0.f;
+      o[q] = g0;
     }
-    reinterpret_cast<uint4*>(ga)[i] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    vstore8(ga + 8 * i, o);
   }
 }
 
@@ -310,8 +299,8 @@ extern "C" int tg_l1_bf16_fwd(const void* a, const void* b, long n, float* parti
   if (grid > rows_cap) grid = rows_cap;
   TG_REQUIRE(grid >= 1, "tg_l1_bf16_fwd: rows_cap must be >= 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  l1_bf16_fwd_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a),
-                                           reinterpret_cast<const __nv_bfloat16*>(b), n / 8, partial);
+  l1_bf16_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                                          reinterpret_cast<const __nv_bfloat16*>(b), n / 8, partial);
   TG_CHECK_CUDA(cudaGetLastError());
   l1_bf16_finalize_kernel<<<1, 32, 0, st>>>(partial, grid, static_cast<double>(n), out);
   TG_CHECK_CUDA(cudaGetLastError());
@@ -322,9 +311,74 @@ extern "C" int tg_l1_bf16_bwd(const void* a, const void* b, long n, const float*
                               void* stream) {
   using namespace tg;
   TG_REQUIRE(a && b && grad_out && ga && n > 0 && n % 8 == 0, "tg_l1_bf16_bwd: bad arguments");
-  l1_bf16_bwd_kernel<<<ls_grid(n / 8, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  l1_bf16_bwd_kernel<__nv_bfloat16><<<ls_grid(n / 8, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), n / 8, grad_out,
       static_cast<float>(1.0 / static_cast<double>(n)), relu_gate, reinterpret_cast<__nv_bfloat16*>(ga));
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_l1_f32_fwd(const void* a, const void* b, long n, float* partial, int rows_cap, float* out,
+                             void* stream) {
+  using namespace tg;
+  TG_REQUIRE(a && b && partial && out && n > 0 && n % 8 == 0, "tg_l1_f32_fwd: bad arguments");
+  int grid = ls_grid(n / 8, 256, 4);
+  if (grid > rows_cap) grid = rows_cap;
+  TG_REQUIRE(grid >= 1, "tg_l1_f32_fwd: rows_cap must be >= 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  l1_bf16_fwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(a), reinterpret_cast<const float*>(b),
+                                                  n / 8, partial);
+  TG_CHECK_CUDA(cudaGetLastError());
+  l1_bf16_finalize_kernel<<<1, 32, 0, st>>>(partial, grid, static_cast<double>(n), out);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tg_l1_f32_bwd(const void* a, const void* b, long n, const float* grad_out, int relu_gate, void* ga,
+                             void* stream) {
+  using namespace tg;
+  TG_REQUIRE(a && b && grad_out && ga && n > 0 && n % 8 == 0, "tg_l1_f32_bwd: bad arguments");
+  l1_bf16_bwd_kernel<float><<<ls_grid(n / 8, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float*>(a), reinterpret_cast<const float*>(b), n / 8, grad_out,
+      static_cast<float>(1.0 / static_cast<double>(n)), relu_gate, reinterpret_cast<float*>(ga));
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out[..][0:C) = tf32(x) (round to nearest), out[..][C:2C) = tf32(x - tf32(x)): the two-term TF32 split of an fp32
+// tensor along its last dimension, so that sum of hi*hi + lo*hi + hi*lo products (three kind::tf32 passes, expressed
+// as ONE launch over a K- or channel-concatenated operand) reproduces fp32 products to ~2^-21.
+namespace tg {
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// layout 0: [hi | lo | hi] (3C), 1: [hi | hi | lo] (3C), 2: [hi | lo] (2C), 3: [hi] (C), 4: [lo | hi] (2C)
+__global__ void split_tf32_kernel(const float* __restrict__ x, long rows, int C, int layout, float* __restrict__ out) {
+  const int parts = layout == 3 ? 1 : (layout == 2 || layout == 4) ? 2 : 3;
+  const long total = rows * C;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / C;
+    const int c = static_cast<int>(i - r * C);
+    const float v = x[i];
+    const float hi = to_tf32(v);
+    const float lo = to_tf32(v - hi);
+    float* o = out + r * parts * C + c;
+    if (layout == 0) { o[0] = hi; o[C] = lo; o[2 * C] = hi; }
+    else if (layout == 1) { o[0] = hi; o[C] = hi; o[2 * C] = lo; }
+    else if (layout == 2) { o[0] = hi; o[C] = lo; }
+    else if (layout == 3) { o[0] = hi; }
+    else { o[0] = lo; o[C] = hi; }
+  }
+}
+}  // namespace tg
+
+extern "C" int tg_split_tf32(const float* x, long rows, int C, int layout, float* out, void* stream) {
+  using namespace tg;
+  TG_REQUIRE(x && out && rows > 0 && C > 0 && layout >= 0 && layout <= 4, "tg_split_tf32: bad arguments");
+  split_tf32_kernel<<<ls_grid(rows * C, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, rows, C, layout, out);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -35,6 +35,33 @@ __device__ __forceinline__ void rs_store8(__nv_bfloat16* p, const float (&f)[8])
   *reinterpret_cast<uint4*>(p) = raw;
 }
 
+__device__ __forceinline__ void rs_load8(const float* p, float (&f)[8]) { vload8(p, f); }
+__device__ __forceinline__ void rs_store8(float* p, const float (&f)[8]) { vstore8(p, f); }
+// raw 8-element vector of the storage type (held in registers between load and use)
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 v; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void raw_zero(Raw8<__nv_bfloat16>& r) { r.v = make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ void raw_zero(Raw8<float>& r) { r.a = r.b = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void raw_load(Raw8<__nv_bfloat16>& r, const __nv_bfloat16* p) { r.v = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void raw_load(Raw8<float>& r, const float* p) {
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<__nv_bfloat16>& r, float (&f)[8]) {
+  const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&r.v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __bfloat1622float2(hh[e]);
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&f)[8]) {
+  f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
+  f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+
 // PyTorch's upsample_bilinear2d source index for scale 2, align_corners=False:
 // src = max(0, (o + 0.5) / 2 - 0.5); i0 = floor(src); i1 = min(i0 + 1, n - 1); l1 = src - i0.
 __device__ __forceinline__ void bilinear_src(int o, int n, int& i0, int& i1, float& l0, float& l1) {
@@ -50,10 +77,11 @@ __device__ __forceinline__ void bilinear_src(int o, int n, int& i0, int& i1, flo
 // One thread = one 8-channel vector of a 2x2 output block: the four outputs of source pixel (i, j)
 // share its 3x3 neighbourhood (9 loads for 4 outputs instead of 16), index math is 32-bit and
 // amortised over the block. Exact PyTorch weights: 0.75/0.25 with edge clamping.
+template <typename T>
 __global__ void __launch_bounds__(256)
-upsample_concat_kernel(const __nv_bfloat16* __restrict__ up, int B, int h, int w, int Cu,
-                       const __nv_bfloat16* __restrict__ skip, int Cs, const uint8_t* __restrict__ mm,
-                       __nv_bfloat16* __restrict__ out) {
+upsample_concat_kernel(const T* __restrict__ up, int B, int h, int w, int Cu,
+                       const T* __restrict__ skip, int Cs, const uint8_t* __restrict__ mm,
+                       T* __restrict__ out) {
   const int H = 2 * h, W = 2 * w, C = Cu + Cs;
   const unsigned cv = C >> 3;
   const unsigned total = static_cast<unsigned>(B) * h * w * cv;
@@ -74,7 +102,7 @@ upsample_concat_kernel(const __nv_bfloat16* __restrict__ up, int B, int h, int w
       if (on[0] || on[1] || on[2] || on[3]) {
         const int im = ii > 0 ? ii - 1 : 0, ip = ii < h - 1 ? ii + 1 : h - 1;
         const int jm = jj > 0 ? jj - 1 : 0, jp = jj < w - 1 ? jj + 1 : w - 1;
-        const __nv_bfloat16* base = up + static_cast<size_t>(b) * hw * Cu + c;
+        const T* base = up + static_cast<size_t>(b) * hw * Cu + c;
         float t[3][3][8];
         const int rr[3] = {im, ii, ip}, cc[3] = {jm, jj, jp};
 #pragma unroll
@@ -119,9 +147,10 @@ upsample_concat_kernel(const __nv_bfloat16* __restrict__ up, int B, int h, int w
 // shared by the two low-resolution rows that use it (a sliding window of 4 rows in registers), which halves the
 // loads and bf16 unpacks per output of the 4x4-window gather this replaces (measured instruction-bound).
 constexpr int kUbSeg = 16;
+template <typename T>
 __global__ void __launch_bounds__(256)
-upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dm, int B, int h, int w, int Cu, int Ctot,
-                           __nv_bfloat16* __restrict__ dup) {
+upsample_concat_bwd_kernel(const T* __restrict__ dm, int B, int h, int w, int Cu, int Ctot,
+                           T* __restrict__ dup) {
   const int H = 2 * h, W = 2 * w;
   const unsigned cv = Cu >> 3;
   const unsigned segs = (static_cast<unsigned>(h) + kUbSeg - 1) / kUbSeg;
@@ -133,7 +162,7 @@ upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dm, int B, int h, i
     rest /= w;
     const int seg = static_cast<int>(rest % segs);
     const int b = static_cast<int>(rest / segs);
-    const __nv_bfloat16* base = dm + static_cast<size_t>(b) * H * W * Ctot + c;
+    const T* base = dm + static_cast<size_t>(b) * H * W * Ctot + c;
     // source column j feeds output columns 2j-1, 2j, 2j+1, 2j+2 with weights 0.25, 0.75, 0.75, 0.25; at the borders
     // the clamped neighbour folds its weight onto the edge pixel (same along rows)
     float ww[4];
@@ -142,34 +171,31 @@ upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dm, int B, int h, i
     ww[2] = jj < w - 1 ? 0.75f : 1.f;
     ww[3] = jj < w - 1 ? 0.25f : 0.f;
     // rows are fetched one loop iteration ahead of their use (the loop is otherwise one load-latency per output row)
-    auto load_row = [&](int oh, uint4 (&raw)[4]) {
+    auto load_row = [&](int oh, Raw8<T> (&raw)[4]) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) raw[q] = make_uint4(0u, 0u, 0u, 0u);
+      for (int q = 0; q < 4; ++q) raw_zero(raw[q]);
       if (oh < 0 || oh >= H) return;
-      const __nv_bfloat16* rowp = base + static_cast<size_t>(oh) * W * Ctot;
+      const T* rowp = base + static_cast<size_t>(oh) * W * Ctot;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int ow = 2 * jj - 1 + q;
-        if (ww[q] != 0.f) raw[q] = *reinterpret_cast<const uint4*>(rowp + static_cast<size_t>(ow) * Ctot);
+        if (ww[q] != 0.f) raw_load(raw[q], rowp + static_cast<size_t>(ow) * Ctot);
       }
     };
-    auto reduce_row = [&](const uint4 (&raw)[4], float (&out)[8]) {
+    auto reduce_row = [&](const Raw8<T> (&raw)[4], float (&out)[8]) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) out[e] = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw[q]);
+        float t[8];
+        raw_unpack(raw[q], t);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 t = __bfloat1622float2(hh[e]);
-          out[2 * e] += ww[q] * t.x;
-          out[2 * e + 1] += ww[q] * t.y;
-        }
+        for (int e = 0; e < 8; ++e) out[e] += ww[q] * t[e];
       }
     };
     const int i0 = seg * kUbSeg, i1 = min(h, i0 + kUbSeg);
     float r0[8], r1[8], r2[8], r3[8];
-    uint4 ra[4], rb[4];
+    Raw8<T> ra[4], rb[4];
     load_row(2 * i0 - 1, ra);
     load_row(2 * i0, rb);
     reduce_row(ra, r0);
@@ -177,7 +203,7 @@ upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dm, int B, int h, i
     load_row(2 * i0 + 1, ra);
     load_row(2 * i0 + 2, rb);
     for (int ii = i0; ii < i1; ++ii) {
-      uint4 na[4], nb[4];
+      Raw8<T> na[4], nb[4];
       load_row(ii + 1 < i1 ? 2 * ii + 3 : -1, na);
       load_row(ii + 1 < i1 ? 2 * ii + 4 : -1, nb);
       reduce_row(ra, r2);
@@ -202,8 +228,9 @@ upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dm, int B, int h, i
   }
 }
 
-__global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
-                                __nv_bfloat16* __restrict__ y) {
+template <typename T>
+__global__ void maxpool2_kernel(const T* __restrict__ x, int B, int H, int W, int C,
+                                T* __restrict__ y) {
   const int h = H >> 1, w = W >> 1, cv = C >> 3;
   const long total = static_cast<long>(B) * h * w * cv;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -213,7 +240,7 @@ __global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, int B, int 
     const int j = static_cast<int>(p % w);
     const int ii = static_cast<int>((p / w) % h);
     const int b = static_cast<int>(p / (static_cast<long>(w) * h));
-    const __nv_bfloat16* base = x + ((static_cast<long>(b) * H + 2 * ii) * W + 2 * j) * C + c;
+    const T* base = x + ((static_cast<long>(b) * H + 2 * ii) * W + 2 * j) * C + c;
     float a[8], t[8];
     rs_load8(base, a);
     rs_load8(base + C, t);
@@ -231,9 +258,10 @@ __global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, int B, int 
 
 // gx[b][H][W][C]: the pooled gradient goes to the first maximum of each 2x2 window (scan order, as
 // ATen's max_pool2d_with_indices does), times the ReLU gate [x > 0] of the layer that produced x.
-__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy,
+template <typename T>
+__global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy,
                                     int B, int H, int W, int C, int relu_gate,
-                                    __nv_bfloat16* __restrict__ gx) {
+                                    T* __restrict__ gx) {
   const int h = H >> 1, w = W >> 1, cv = C >> 3;
   const long total = static_cast<long>(B) * h * w * cv;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -274,53 +302,69 @@ static int rs_grid(long n, int block) {
   return static_cast<int>(g);
 }
 
-}  // namespace tg
-
-extern "C" int tg_upsample_concat(const void* up, int B, int h, int w, int Cu, const void* skip, int Cs,
-                                  const uint8_t* merged_mask, void* out, void* stream) {
-  using namespace tg;
+template <typename T>
+static int upsample_concat_impl(const void* up, int B, int h, int w, int Cu, const void* skip, int Cs,
+                                const uint8_t* merged_mask, void* out, void* stream) {
   TG_REQUIRE(up && out && Cu > 0 && Cu % 8 == 0 && Cs >= 0 && Cs % 8 == 0, "tg_upsample_concat: bad arguments");
   TG_REQUIRE(Cs == 0 || skip, "tg_upsample_concat: skip missing");
   const long total = static_cast<long>(B) * h * w * ((Cu + Cs) / 8);     // one thread per 2x2 output block
   TG_REQUIRE(total < (1L << 31), "tg_upsample_concat: tensor too large for 32-bit indexing");
-  upsample_concat_kernel<<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(up), B, h, w, Cu, reinterpret_cast<const __nv_bfloat16*>(skip), Cs,
-      merged_mask, reinterpret_cast<__nv_bfloat16*>(out));
+  upsample_concat_kernel<T><<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const T*>(up), B, h, w, Cu, reinterpret_cast<const T*>(skip), Cs, merged_mask,
+      reinterpret_cast<T*>(out));
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int tg_upsample_concat_bwd(const void* d_merged, int B, int h, int w, int Cu, int Ctot, void* d_up,
-                                      void* stream) {
-  using namespace tg;
+template <typename T>
+static int upsample_concat_bwd_impl(const void* d_merged, int B, int h, int w, int Cu, int Ctot, void* d_up,
+                                    void* stream) {
   TG_REQUIRE(d_merged && d_up && Cu > 0 && Cu % 8 == 0 && Ctot >= Cu && Ctot % 8 == 0,
              "tg_upsample_concat_bwd: bad arguments");
-  const long total = static_cast<long>(B) * ((h + tg::kUbSeg - 1) / tg::kUbSeg) * w * (Cu / 8);   // column strips
+  const long total = static_cast<long>(B) * ((h + kUbSeg - 1) / kUbSeg) * w * (Cu / 8);   // column strips
   TG_REQUIRE(total < (1L << 31), "tg_upsample_concat_bwd: tensor too large for 32-bit indexing");
-  upsample_concat_bwd_kernel<<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d_merged), B, h, w, Cu, Ctot, reinterpret_cast<__nv_bfloat16*>(d_up));
+  upsample_concat_bwd_kernel<T><<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const T*>(d_merged), B, h, w, Cu, Ctot, reinterpret_cast<T*>(d_up));
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int tg_maxpool2(const void* x, int B, int H, int W, int C, void* y, void* stream) {
-  using namespace tg;
+template <typename T>
+static int maxpool2_impl(const void* x, int B, int H, int W, int C, void* y, void* stream) {
   TG_REQUIRE(x && y && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "tg_maxpool2: bad arguments");
   const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2_kernel<<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
+  maxpool2_kernel<T><<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const T*>(x), B, H, W, C, reinterpret_cast<T*>(y));
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int tg_maxpool2_bwd(const void* x, const void* gy, int B, int H, int W, int C, int relu_gate, void* gx,
-                               void* stream) {
-  using namespace tg;
+template <typename T>
+static int maxpool2_bwd_impl(const void* x, const void* gy, int B, int H, int W, int C, int relu_gate, void* gx,
+                             void* stream) {
   TG_REQUIRE(x && gy && gx && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "tg_maxpool2_bwd: bad arguments");
   const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2_bwd_kernel<<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gy), B, H, W, C, relu_gate,
-      reinterpret_cast<__nv_bfloat16*>(gx));
+  maxpool2_bwd_kernel<T><<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(gy), B, H, W, C, relu_gate, reinterpret_cast<T*>(gx));
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+}  // namespace tg
+
+#define TG_RS_TWINS(NAME, IMPL, PARAMS, ARGS)                                                   \
+  extern "C" int NAME PARAMS { return tg::IMPL<__nv_bfloat16> ARGS; }                           \
+  extern "C" int NAME##_f32 PARAMS { return tg::IMPL<float> ARGS; }
+
+TG_RS_TWINS(tg_upsample_concat, upsample_concat_impl,
+            (const void* up, int B, int h, int w, int Cu, const void* skip, int Cs, const uint8_t* merged_mask, void* out,
+             void* stream),
+            (up, B, h, w, Cu, skip, Cs, merged_mask, out, stream))
+TG_RS_TWINS(tg_upsample_concat_bwd, upsample_concat_bwd_impl,
+            (const void* d_merged, int B, int h, int w, int Cu, int Ctot, void* d_up, void* stream),
+            (d_merged, B, h, w, Cu, Ctot, d_up, stream))
+TG_RS_TWINS(tg_maxpool2, maxpool2_impl, (const void* x, int B, int H, int W, int C, void* y, void* stream),
+            (x, B, H, W, C, y, stream))
+TG_RS_TWINS(tg_maxpool2_bwd, maxpool2_bwd_impl,
+            (const void* x, const void* gy, int B, int H, int W, int C, int relu_gate, void* gx, void* stream),
+            (x, gy, B, H, W, C, relu_gate, gx, stream))

@@ -70,6 +70,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // Same for fp32 elements (the TF32 verification path: fp32 storage, kind::tf32 MMAs).
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box);
+// fp32 with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks swizzled over 4 rows): the only shared-memory layout
+// MN-major kind::tf32 operands can use (UMMA layout type SWIZZLE_128B_BASE32B) -- the fp32 weight-gradient kernel.
+int make_tmap_f32_atom32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box);
 
 // ----------------------------------------------------------------------------------------------
 // device helpers
@@ -216,6 +220,22 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uin
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::tf32: fp32 words in shared memory, the tensor core reads the upper 19 bits (TF32), fp32 accumulate; K = 8
+// per instruction (32 bytes along K, as for kind::f16). The verification path (fp32 storage) uses it.
+__device__ __forceinline__ void umma_tf32_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(
@@ -246,14 +266,16 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // K-major tile (rows = M/N index, 128 B = 64 bf16 of K per row): SBO = 1024 (8-row atom), LBO unused.
 // MN-major tile (rows = K index, 128 B = 64 bf16 of M/N per row): SBO = 1024 (8 k-rows), LBO =
 // byte distance between consecutive 64-wide M/N blocks.
+// layout_type: 2 = SWIZZLE_128B (16-byte chunks over 8 rows); 1 = SWIZZLE_128B_BASE32B (32-byte chunks over 4 rows:
+// MN-major tf32 operands; SBO is then the distance between 4-row groups).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
+                                                   uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32 (cute::UMMA::InstrDescriptor layout).
@@ -266,6 +288,41 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n, b
          | ((b_mn_major ? 1u : 0u) << 16)  // b_major
          | ((n >> 3) << 17)                // n_dim
          | ((m >> 4) << 24);               // m_dim
+}
+
+// Same for kind::tf32 (a_format = b_format = 2).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t m, uint32_t n, bool a_mn_major,
+                                                       bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// ---- 8-element vectors of the activation storage type (bf16: one 16-byte word; fp32: two) ----
+__device__ __forceinline__ void vload8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void vload8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void vstore8(__nv_bfloat16* p, const float (&f)[8]) {
+  __nv_bfloat162 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(v);
+}
+__device__ __forceinline__ void vstore8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *(reinterpret_cast<float4*>(p) + 1) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
 // ---- misc math ----

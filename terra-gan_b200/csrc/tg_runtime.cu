@@ -115,9 +115,11 @@ static int make_tmap_any(CUtensorMap* out, int dtype_f32, const void* base, int 
     estr[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  // dtype code 2: fp32 with 32-byte swizzle atoms (the layout MN-major kind::tf32 operands need)
   CUresult r = fn(out, dtype_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
                   const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  dtype_f32 == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error(
         "cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
@@ -145,6 +147,11 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   return make_tmap_any(out, 1, base, rank, dims, strides_bytes, box);
 }
 
+int make_tmap_f32_atom32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap_any(out, 2, base, rank, dims, strides_bytes, box);
+}
+
 void tmap_cache_counters(uint64_t* hits, uint64_t* misses) {
   *hits = g_tmap_hits;
   *misses = g_tmap_misses;
@@ -152,7 +159,7 @@ void tmap_cache_counters(uint64_t* hits, uint64_t* misses) {
 
 }  // namespace tg
 
-extern "C" int tg_version(void) { return 1; }
+extern "C" int tg_version(void) { return 2; }
 
 extern "C" size_t tg_last_error(char* buf, size_t cap) {
   size_t n = strlen(tg::g_err);

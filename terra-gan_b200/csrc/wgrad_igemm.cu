@@ -24,23 +24,30 @@ namespace tg {
 constexpr int kWStages = 4;
 constexpr int kBoxBytes = 64 * 128;  // 64 pixels x 64 bf16
 
-template <int BN>
+// kF32 (verification path): fp32 tiles [pixel][32 channels] (the same 128-byte rows), kind::tf32 MMAs with K = 8
+// pixels each; M = 128 rows = FOUR 32-channel blocks of the (tap, channel block) list.
+template <int BN, bool kF32 = false>
 struct WgradSmem {
-  static constexpr int kABytes = 2 * kBoxBytes;
-  static constexpr int kBBytes = (BN / 64) * kBoxBytes;
+  static constexpr int kCB = kF32 ? 32 : 64;                 // channels per TMA box
+  static constexpr int kABoxes = 128 / kCB;
+  static constexpr int kStages = kF32 ? 3 : kWStages;
+  static constexpr int kABytes = kABoxes * kBoxBytes;
+  static constexpr int kBBytes = (BN / kCB) * kBoxBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTiles = kWStages * kStageBytes;
+  static constexpr int kTiles = kStages * kStageBytes;
   static constexpr int kTotal = kTiles + 256 + 1024;
 };
 
-template <int BN>
+template <int BN, bool kF32 = false>
 __global__ void __launch_bounds__(256, 1)
 wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                    const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  using S = WgradSmem<BN>;
+  using S = WgradSmem<BN, kF32>;
+  constexpr int kWStages = S::kStages;     // shadows the namespace constant
+  constexpr int kCB = S::kCB, kABoxes = S::kABoxes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kTiles);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kWStages;
@@ -86,10 +93,10 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const int nt = u % p.n_tiles;
         const int mt = (u / p.n_tiles) % p.m_tiles;
         const int sp = u / (p.n_tiles * p.m_tiles);
-        const int i0 = 2 * mt;
-        const int i1 = (2 * mt + 1 < p.num_blk) ? 2 * mt + 1 : 2 * mt;
-        const WgradBlk e0 = p.blks[i0];
-        const WgradBlk e1 = p.blks[i1];
+        WgradBlk e[kABoxes];
+#pragma unroll
+        for (int j = 0; j < kABoxes; ++j)
+          e[j] = p.blks[(kABoxes * mt + j < p.num_blk) ? kABoxes * mt + j : kABoxes * mt];
         const int kb_begin = sp * per_split;
         const int kb_end = min(kboxes, kb_begin + per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -101,12 +108,13 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-          tma_load_5d(sa, &tmX, &full_bar[stage], e0.cb * 64, w0 + e0.dw, h0 + e0.dh, e0.plane, b0);
-          tma_load_5d(sa + kBoxBytes, &tmX, &full_bar[stage], e1.cb * 64, w0 + e1.dw, h0 + e1.dh,
-                      e1.plane, b0);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_5d(sb + j * kBoxBytes, &tmG, &full_bar[stage], nt * BN + j * 64, w0, h0, 0, b0);
+          for (int j = 0; j < kABoxes; ++j)
+            tma_load_5d(sa + j * kBoxBytes, &tmX, &full_bar[stage], e[j].cb * kCB, w0 + e[j].dw, h0 + e[j].dh,
+                        e[j].plane, b0);
+#pragma unroll
+          for (int j = 0; j < BN / kCB; ++j)
+            tma_load_5d(sb + j * kBoxBytes, &tmG, &full_bar[stage], nt * BN + j * kCB, w0, h0, 0, b0);
           if (++stage == kWStages) {
             stage = 0;
             phase ^= 1;
@@ -116,8 +124,9 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
   } else if (warp == 1) {
     {   // whole warp, warp-uniform addressing; one elected lane issues the tcgen05 instructions
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, true, true);
-      const uint64_t d0 = make_smem_desc(smem_u32(smem), kBoxBytes, 1024);   // both operands MN-major, same strides
+      constexpr uint32_t idesc = kF32 ? make_idesc_tf32(128, BN, true, true) : make_idesc_bf16(128, BN, true, true);
+      // both operands MN-major, same strides; fp32 tiles use 32-byte swizzle atoms over 4-row (512 B) groups
+      const uint64_t d0 = kF32 ? make_smem_desc(smem_u32(smem), kBoxBytes, 512, 1) : make_smem_desc(smem_u32(smem), kBoxBytes, 1024);
       const uint32_t d_lo0 = static_cast<uint32_t>(d0), d_hi = static_cast<uint32_t>(d0 >> 32);
       int stage = 0;
       uint32_t phase = 0;
@@ -137,9 +146,15 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           const uint32_t a_lo = d_lo0 + static_cast<uint32_t>(stage) * (S::kStageBytes >> 4);
           const uint32_t b_lo = a_lo + (S::kABytes >> 4);
           if (elect_one()) {
+            if (kF32) {   // 8 pixels (one 8-row swizzle atom, 1024 B) per MMA
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_lh(d_tmem, a_lo + k * 128, d_hi, b_lo + k * 128, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb > kb_begin));
+              for (int k = 0; k < 8; ++k)
+                umma_tf32_lh(d_tmem, a_lo + k * 64, d_hi, b_lo + k * 64, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb > kb_begin));
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_lh(d_tmem, a_lo + k * 128, d_hi, b_lo + k * 128, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb > kb_begin));
+            }
             umma_commit(&empty_bar[stage]);
           }
           if (++stage == kWStages) {
@@ -163,9 +178,9 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const int mt = (u / p.n_tiles) % p.m_tiles;
       const int sp = u / (p.n_tiles * p.m_tiles);
       const int r = q * 32 + lane;
-      const int bi = 2 * mt + (r >> 6);
+      const int bi = kABoxes * mt + r / kCB;
       const bool valid = bi < p.num_blk;
-      const int row = valid ? p.blks[bi].row + (r & 63) : 0;
+      const int row = valid ? p.blks[bi].row + (r % kCB) : 0;
       float* dst = p.partial + (static_cast<long>(sp) * p.rows + row) * p.Cout + nt * BN;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -247,12 +262,18 @@ static void choose_kbox(int Ho, int Wo, int* Bt, int* Ht, int* Wt) {
 // waves = ceil(units / SMs). The round-1 rule "about 2 units per SM" produced 297 and 299 units on 148 SMs for dec3
 // and enc2 -- a third, almost empty wave (535 / 525 TFLOP/s). Every candidate is now costed and the cheapest
 // taken; ties go to the smaller split (fewer fp32 partial shares for tg_wgrad_reduce to read back).
-static int choose_splits(int B, int Ho, int Wo, int num_blk, int N, int sms) {
+static int wgrad_bn(int N, bool f32) {
+  if (f32) return (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
+  return (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
+}
+
+static int choose_splits(int B, int Ho, int Wo, int num_blk, int N, int sms, bool f32 = false) {
   int Bt, Ht, Wt;
   choose_kbox(Ho, Wo, &Bt, &Ht, &Wt);
   const long kboxes = (long)((B + Bt - 1) / Bt) * ((Ho + Ht - 1) / Ht) * ((Wo + Wt - 1) / Wt);
-  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
-  const long mn = (long)((num_blk + 1) / 2) * (N / BN);
+  const int BN = wgrad_bn(N, f32);
+  const int per_m = f32 ? 4 : 2;
+  const long mn = (long)((num_blk + per_m - 1) / per_m) * (N / BN);
   long max_splits = (kboxes + 3) / 4;            // at least 4 K blocks per unit
   if (max_splits > 256) max_splits = 256;
   if (max_splits < 1) max_splits = 1;
@@ -273,17 +294,22 @@ static int choose_splits(int B, int Ho, int Wo, int num_blk, int N, int sms) {
   return (int)best;
 }
 
-template <int BN>
+template <int BN, bool kF32 = false>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmG, const WgradKParams& kp,
                         int grid, cudaStream_t st) {
-  using S = WgradSmem<BN>;
-  TG_SET_SMEM_ONCE((wgrad_igemm_kernel<BN>), S::kTotal);
-  wgrad_igemm_kernel<BN><<<grid, 256, S::kTotal, st>>>(tmX, tmG, kp);
+  using S = WgradSmem<BN, kF32>;
+  TG_SET_SMEM_ONCE((wgrad_igemm_kernel<BN, kF32>), S::kTotal);
+  wgrad_igemm_kernel<BN, kF32><<<grid, 256, S::kTotal, st>>>(tmX, tmG, kp);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 }  // namespace tg
+
+extern "C" int64_t tg_wgrad_partial_floats_f32(int B, int Ho, int Wo, int num_taps, int C, int N) {
+  const int sms = tg::num_sms() > 0 ? tg::num_sms() : 148;
+  return (int64_t)tg::choose_splits(B, Ho, Wo, num_taps * (C / 32), N, sms, true) * num_taps * C * N;
+}
 
 extern "C" int64_t tg_wgrad_partial_floats(int B, int Ho, int Wo, int num_taps, int C, int N) {
   const int sms = tg::num_sms() > 0 ? tg::num_sms() : 148;
@@ -298,14 +324,17 @@ extern "C" int64_t tg_wgrad_partial_floats(int B, int Ho, int Wo, int num_taps, 
 extern "C" int tg_wgrad_igemm(tg_wgrad_args* a, void* stream) {
   using namespace tg;
   TG_REQUIRE(a != nullptr, "tg_wgrad_igemm: null args");
-  TG_REQUIRE(a->C > 0 && a->C % 64 == 0, "tg_wgrad_igemm: C=%d must be a multiple of 64", a->C);
-  TG_REQUIRE(a->N > 0 && a->N % 64 == 0, "tg_wgrad_igemm: N=%d must be a multiple of 64", a->N);
+  TG_REQUIRE(a->dtype == TG_DTYPE_BF16 || a->dtype == TG_DTYPE_F32, "tg_wgrad_igemm: bad dtype %d", a->dtype);
+  const bool f32 = a->dtype == TG_DTYPE_F32;
+  const int cb_elems = f32 ? 32 : 64, esz = f32 ? 4 : 2;
+  TG_REQUIRE(a->C > 0 && a->C % cb_elems == 0, "tg_wgrad_igemm: C=%d must be a multiple of %d", a->C, cb_elems);
+  TG_REQUIRE(a->N > 0 && a->N % cb_elems == 0, "tg_wgrad_igemm: N=%d must be a multiple of %d", a->N, cb_elems);
   TG_REQUIRE(a->num_taps >= 1 && a->num_taps <= TG_MAX_TAPS, "tg_wgrad_igemm: bad num_taps");
   const int sms = num_sms();
   TG_REQUIRE(sms > 0, "tg_wgrad_igemm: no CUDA device");
-  if (wgrad_halo_enabled() && wgrad_halo_eligible(a)) return wgrad_halo_launch(a, reinterpret_cast<cudaStream_t>(stream));
-  const int BN = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : 64;
-  const int num_blk = a->num_taps * (a->C / 64);
+  if (!f32 && wgrad_halo_enabled() && wgrad_halo_eligible(a)) return wgrad_halo_launch(a, reinterpret_cast<cudaStream_t>(stream));
+  const int BN = wgrad_bn(a->N, f32);
+  const int num_blk = a->num_taps * (a->C / cb_elems);
 
   WgradKParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -315,13 +344,13 @@ extern "C" int tg_wgrad_igemm(tg_wgrad_args* a, void* stream) {
   kp.tiles_b = (a->B + kp.Bt - 1) / kp.Bt;
   kp.n_tiles = a->N / BN;
   kp.num_blk = num_blk;
-  kp.m_tiles = (num_blk + 1) / 2;
-  kp.splits = choose_splits(a->B, a->Ho, a->Wo, num_blk, a->N, sms);
+  kp.m_tiles = f32 ? (num_blk + 3) / 4 : (num_blk + 1) / 2;
+  kp.splits = choose_splits(a->B, a->Ho, a->Wo, num_blk, a->N, sms, f32);
   kp.Cout = a->N;
   kp.rows = a->num_taps * a->C;
   kp.partial = a->partial;
   kp.blks = reinterpret_cast<const WgradBlk*>(a->blks);
-  TG_REQUIRE(a->blks != nullptr && a->num_blk == num_blk, "tg_wgrad_igemm: blks table must hold num_taps*C/64 = %d entries", num_blk);
+  TG_REQUIRE(a->blks != nullptr && a->num_blk == num_blk, "tg_wgrad_igemm: blks table must hold num_taps*C/%d = %d entries", cb_elems, num_blk);
   TG_REQUIRE((int64_t)kp.splits * kp.rows * a->N <= a->partial_cap,
              "tg_wgrad_igemm: partial workspace too small (%lld floats needed)",
              (long long)((int64_t)kp.splits * kp.rows * a->N));
@@ -332,20 +361,25 @@ extern "C" int tg_wgrad_igemm(tg_wgrad_args* a, void* stream) {
   CUtensorMap tmX, tmG;
   {
     uint64_t dims[5] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->P, (uint64_t)a->B};
-    uint64_t str[4] = {(uint64_t)a->C * 2, (uint64_t)a->C * 2 * a->W, (uint64_t)a->C * 2 * a->W * a->H,
-                       (uint64_t)a->C * 2 * a->W * a->H * a->P};
-    uint32_t box[5] = {64, (uint32_t)kp.Wt, (uint32_t)kp.Ht, 1, (uint32_t)kp.Bt};
-    if (make_tmap_bf16(&tmX, a->x, 5, dims, str, box) != 0) return -3;
+    uint64_t str[4] = {(uint64_t)a->C * esz, (uint64_t)a->C * esz * a->W, (uint64_t)a->C * esz * a->W * a->H,
+                       (uint64_t)a->C * esz * a->W * a->H * a->P};
+    uint32_t box[5] = {(uint32_t)cb_elems, (uint32_t)kp.Wt, (uint32_t)kp.Ht, 1, (uint32_t)kp.Bt};
+    if ((f32 ? make_tmap_f32_atom32 : make_tmap_bf16)(&tmX, a->x, 5, dims, str, box) != 0) return -3;
   }
   {
     uint64_t dims[5] = {(uint64_t)a->N, (uint64_t)a->Wo, (uint64_t)a->Ho, 1, (uint64_t)a->B};
-    uint64_t str[4] = {(uint64_t)a->N * 2, (uint64_t)a->N * 2 * a->Wo, (uint64_t)a->N * 2 * a->Wo * a->Ho,
-                       (uint64_t)a->N * 2 * a->Wo * a->Ho};
-    uint32_t box[5] = {64, (uint32_t)kp.Wt, (uint32_t)kp.Ht, 1, (uint32_t)kp.Bt};
-    if (make_tmap_bf16(&tmG, a->g, 5, dims, str, box) != 0) return -3;
+    uint64_t str[4] = {(uint64_t)a->N * esz, (uint64_t)a->N * esz * a->Wo, (uint64_t)a->N * esz * a->Wo * a->Ho,
+                       (uint64_t)a->N * esz * a->Wo * a->Ho};
+    uint32_t box[5] = {(uint32_t)cb_elems, (uint32_t)kp.Wt, (uint32_t)kp.Ht, 1, (uint32_t)kp.Bt};
+    if ((f32 ? make_tmap_f32_atom32 : make_tmap_bf16)(&tmG, a->g, 5, dims, str, box) != 0) return -3;
   }
   const long total_units = (long)kp.m_tiles * kp.n_tiles * kp.splits;
   const int grid = (int)(total_units < sms ? total_units : sms);
+  if (f32) {
+    if (BN == 128) return launch_wgrad<128, true>(tmX, tmG, kp, grid, st);
+    if (BN == 64) return launch_wgrad<64, true>(tmX, tmG, kp, grid, st);
+    return launch_wgrad<32, true>(tmX, tmG, kp, grid, st);
+  }
   if (BN == 256) return launch_wgrad<256>(tmX, tmG, kp, grid, st);
   if (BN == 128) return launch_wgrad<128>(tmX, tmG, kp, grid, st);
   return launch_wgrad<64>(tmX, tmG, kp, grid, st);

@@ -66,4 +66,9 @@ class Discriminator(nn.Module):
 
     def forward(self, img):
         names, tensors = self._param_items()
+        if not torch.is_grad_enabled():      # nothing to save for backward
+            if not img.is_cuda:
+                raise RuntimeError(f"Discriminator: input is on {img.device}; the B200 TERRA-GAN path runs hand-written "
+                                   "sm_100a CUDA kernels only and has no CPU fallback")
+            return self._engine.forward(img, dict(zip(names, tensors)), self._bn_params(), self.training, None)
         return DiscriminatorFn.apply(img, self, tuple(names), *tensors)

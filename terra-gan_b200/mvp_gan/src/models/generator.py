@@ -72,6 +72,14 @@ class PConvUNet(nn.Module):
 
     def forward(self, x, mask):
         names, tensors = self._param_items()
+        if not torch.is_grad_enabled():
+            # inference (evaluate.py:47-50 runs under no_grad): nothing is saved for backward, and in eval mode
+            # the decoder BatchNorm + ReLU fold into the conv epilogues (tg_b200.layers.GeneratorEngine.forward)
+            if not x.is_cuda:
+                raise RuntimeError(f"PConvUNet: input is on {x.device}; the B200 TERRA-GAN path runs hand-written "
+                                   "sm_100a CUDA kernels only and has no CPU fallback")
+            return self._engine.forward(x, mask, dict(zip(names, tensors)), self._bn_params(), self.training, None,
+                                        getattr(self, "_trace", None))
         return GeneratorFn.apply(x, mask, self, tuple(names), *tensors)
 
     # ---- reference helper API (generator.py:66-84), expressed with the stand-alone layers ----

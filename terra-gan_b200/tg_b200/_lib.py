@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libtg_b200.so")
 TG_MAX_TAPS = 64
 TG_MAX_SUB = 4
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+DTYPE_BF16, DTYPE_F32 = 0, 1
 
 c_void_p, c_int, c_long, c_float, c_size_t = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_size_t
 
@@ -40,6 +41,7 @@ class ConvArgs(C.Structure):
         ("act", C.c_int32), ("slope", C.c_float),
         ("stats", c_void_p), ("stats_rows_cap", C.c_int32), ("stats_rows_used", C.c_int32),
         ("gate", c_void_p), ("gate_slope", C.c_float),
+        ("dtype", C.c_int32), ("addend", c_void_p),
     ]
 
 
@@ -57,6 +59,7 @@ class WgradArgs(C.Structure):
         ("tap_dw", C.c_int8 * TG_MAX_TAPS),
         ("partial", c_void_p), ("partial_cap", C.c_int64), ("splits", C.c_int32),
         ("blks", c_void_p), ("num_blk", C.c_int32),
+        ("dtype", C.c_int32),
     ]
 
 
@@ -129,7 +132,21 @@ PROTOTYPES = {
     "tg_l1_bf16_bwd": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]),
     "tg_bce_logits_fwd": (c_int, [c_void_p, c_void_p, c_float, c_long, c_void_p, c_void_p]),
     "tg_bce_logits_bwd": (c_int, [c_void_p, c_void_p, c_float, c_long, c_void_p, c_void_p, c_void_p]),
+    "tg_wgrad_partial_floats_f32": (C.c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "tg_split_tf32": (c_int, [c_void_p, c_long, c_int, c_int, c_void_p, c_void_p]),
+    "tg_conv_to1_fwd_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, C.POINTER(c_int),
+                                    C.POINTER(C.c_int8), C.POINTER(C.c_int8), c_void_p, c_int, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
+# fp32-storage twins with the signature of their bf16 sibling
+for _bf, _f32 in (("tg_bn_apply", "tg_bn_apply_f32"), ("tg_bn_bwd_reduce", "tg_bn_bwd_reduce_f32"),
+                  ("tg_bn_bwd_apply", "tg_bn_bwd_apply_f32"), ("tg_upsample_concat", "tg_upsample_concat_f32"),
+                  ("tg_upsample_concat_bwd", "tg_upsample_concat_bwd_f32"), ("tg_maxpool2", "tg_maxpool2_f32"),
+                  ("tg_maxpool2_bwd", "tg_maxpool2_bwd_f32"), ("tg_conv_c1_fwd", "tg_conv_c1_fwd_f32"),
+                  ("tg_conv_c1_wgrad", "tg_conv_c1_wgrad_f32"), ("tg_conv_to1_bwd_data", "tg_conv_to1_bwd_data_f32"),
+                  ("tg_conv_to1_wgrad", "tg_conv_to1_wgrad_f32"), ("tg_l1_bf16_fwd", "tg_l1_f32_fwd"),
+                  ("tg_l1_bf16_bwd", "tg_l1_f32_bwd")):
+    PROTOTYPES[_f32] = PROTOTYPES[_bf]
 
 _lib: Optional[C.CDLL] = None
 

@@ -10,6 +10,7 @@ import torch
 
 from . import ops
 from . import plan as P
+from . import precision as PR
 from ._lib import ACT_NONE, ACT_RELU
 from .layers import (BN_EPS, BNParams, ConvPack, DiscSave, DiscriminatorEngine, GenSave, GeneratorEngine,
                      VggEngine, bn_coeffs)
@@ -107,13 +108,14 @@ class PerceptualFn(torch.autograd.Function):
             loss = ops.l1_bf16_fwd(fi, ft)
         ctx.engine, ctx.vgg, ctx.saved, ctx.fi, ctx.ft = engine, vgg, saved, fi, ft
         ctx.hw = (inp.shape[2], inp.shape[3])
+        ctx.mode = PR.get_precision()
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, go):
         with torch.no_grad():
             gfeat = ops.l1_bf16_bwd(ctx.fi, ctx.ft, go.reshape(1).float().contiguous(), relu_gate=True)
-            g_img = ctx.engine.backward(gfeat, ctx.vgg, ctx.saved, ctx.hw)
+            g_img = ctx.engine.backward(gfeat, ctx.vgg, ctx.saved, ctx.hw, ctx.mode)
         ctx.saved = ctx.fi = ctx.ft = None
         return g_img, None, None, None
 
@@ -184,6 +186,8 @@ class PConv2dFn(torch.autograd.Function):
         cout = weight.shape[0]
         pk: ConvPack = module._pack
         dev = x.device
+        mode = PR.get_precision()
+        adt = PR.act_dtype(mode)
         with torch.no_grad():
             m8 = ops.mask_from_f32(mask.reshape(B, H, W).contiguous().float())
             ssum, upd, _, m_split = ops.mask_window_sum(m8, k, s, p, want_in_split=(s == 2 and cin > 1))
@@ -197,15 +201,15 @@ class PConv2dFn(torch.autograd.Function):
                                               f"got Cout={cout}, k={k}, s={s}")
                 x3 = x.reshape(B, H, W).contiguous().float()
                 z, stats = ops.conv_c1_fwd(x3, m8, k, s, p, weight.reshape(cout, k * k).contiguous(), bias, code=ssum,
-                                           lut_dev=pk.lut_dev(dev), act=epi_act, want_stats=want_stats)
+                                           lut_dev=pk.lut_dev(dev), act=epi_act, want_stats=want_stats, out_dtype=adt)
                 xin = x3
             else:
                 if cin % 64 or cout % 64 or s not in (1, 2) or (s == 2 and (H % 2 or W % 2)):
                     raise NotImplementedError("PConv2d (B200 path): channels must be multiples of 64 and stride 1 or 2 "
                                               f"(even H, W); got Cin={cin}, Cout={cout}, stride={s}, {H}x{W}")
-                xm = (x * mask).permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+                xm = (x * mask).permute(0, 2, 3, 1).to(adt).contiguous()
                 xin = P.to_parity_split(xm) if s == 2 else xm.unsqueeze(1)
-                z, stats = ops.conv_igemm(xin, pk.w_fprop(weight), pk.fplan, (ho, wo), code=ssum, lut=pk.lut, bias=bias,
+                z, stats = ops.conv_igemm(xin, pk.w_fprop(weight, mode), pk.fplan, (ho, wo), code=ssum, lut=pk.lut, bias=bias,
                                           act=epi_act, want_stats=want_stats)
             if module.batch_norm:
                 bn = module.bn
@@ -221,6 +225,7 @@ class PConv2dFn(torch.autograd.Function):
             out = y.permute(0, 3, 1, 2).float()
             out_mask = ops.mask_to_f32(upd).reshape(B, 1, ho, wo)
         ctx.state = (module, xin, z, scale, shift, mean, invstd, ssum, m8, m_split, (B, cin, H, W), weight)
+        ctx.mode = mode
         ctx.mark_non_differentiable(out_mask)
         return out, out_mask
 
@@ -232,8 +237,9 @@ class PConv2dFn(torch.autograd.Function):
         pk: ConvPack = module._pack
         dev = g_out.device
         cout = weight.shape[0]
+        mode = ctx.mode
         with torch.no_grad():
-            g = g_out.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+            g = g_out.permute(0, 2, 3, 1).to(PR.act_dtype(mode)).contiguous()
             gz, dgam, dbet, dbias = ops.bn_bwd(ops.grad_src(g), None, z, scale, shift, mean, invstd, ACT_RELU, 0.0, ssum,
                                                pk.lut_dev(dev), batch_stats=module.batch_norm and module.training)
             dw = torch.empty_like(weight)
@@ -249,14 +255,14 @@ class PConv2dFn(torch.autograd.Function):
                     gx, _ = ops.conv_to1_fwd(gz[:, 0], False, (ho, wo), wt, counts, taps, None, (H, W))
                     gx = gx.reshape(B, 1, H, W) * ops.mask_to_f32(m8).reshape(B, 1, H, W)
             else:
-                ops.wgrad_igemm(xin, gz, pk.fplan, pk.blks(cin, dev), pk.perm(dev), dw)
+                ops.wgrad_igemm(xin, gz, pk.fplan, pk.blks(cin, dev), pk.perm(dev), dw, x3=mode == "tf32x3")
                 if ctx.needs_input_grad[0]:
                     if s == 1:
-                        dx, _ = ops.conv_igemm(gz, pk.w_dgrad(weight), pk.dplan, (H, W), code=m8.reshape(B, 1, H, W),
+                        dx, _ = ops.conv_igemm(gz, pk.w_dgrad(weight, mode), pk.dplan, (H, W), code=m8.reshape(B, 1, H, W),
                                                lut=[0.0, 1.0])
                         gx = dx[:, 0].permute(0, 3, 1, 2).float()
                     else:
-                        dx, _ = ops.conv_igemm(gz, pk.w_dgrad(weight), pk.dplan, (H // 2, W // 2), code=m_split,
+                        dx, _ = ops.conv_igemm(gz, pk.w_dgrad(weight, mode), pk.dplan, (H // 2, W // 2), code=m_split,
                                                lut=[0.0, 1.0])
                         gx = P.from_parity_split(dx).permute(0, 3, 1, 2).float()
         ctx.state = None

@@ -18,6 +18,7 @@ import torch
 
 from . import ops
 from . import plan as P
+from . import precision as PR
 from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU
 
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
@@ -45,6 +46,7 @@ class ConvPack:
         self.lut = P.ratio_lut(k)
         self._key = None
         self._wf = self._wd = None
+        self._f32: Dict[str, tuple] = {}      # verification modes: mode -> (key, w_fprop, w_dgrad), fp32 operands
         self._blks: Dict[Tuple[int, str], torch.Tensor] = {}
         self._perm: Dict[str, torch.Tensor] = {}
         self._lut_dev: Dict[str, torch.Tensor] = {}
@@ -57,15 +59,29 @@ class ConvPack:
                 self._wd = P.pack_w_dgrad(w, self.dplan)
             self._key = key
 
+    def _refresh_f32(self, w: torch.Tensor, mode: str) -> tuple:
+        key = (w.data_ptr(), w._version, str(w.device))
+        ent = self._f32.get(mode)
+        if ent is None or ent[0] != key:
+            split = ops.split_hi_lo if mode == "tf32x3" else None
+            with torch.no_grad():
+                ent = (key, P.pack_w_fprop_f32(w, split), P.pack_w_dgrad_f32(w, self.dplan, split))
+            self._f32[mode] = ent
+        return ent
+
     def mark_fresh(self, w: torch.Tensor) -> None:
         """The packed copies were just written in place from `w` (tg_b200.optim.Adam): no re-pack needed."""
         self._key = (w.data_ptr(), w._version, str(w.device))
 
-    def w_fprop(self, w: torch.Tensor) -> torch.Tensor:
+    def w_fprop(self, w: torch.Tensor, mode: str = "bf16") -> torch.Tensor:
+        if mode != "bf16":
+            return self._refresh_f32(w, mode)[1]
         self._refresh(w)
         return self._wf
 
-    def w_dgrad(self, w: torch.Tensor) -> torch.Tensor:
+    def w_dgrad(self, w: torch.Tensor, mode: str = "bf16") -> torch.Tensor:
+        if mode != "bf16":
+            return self._refresh_f32(w, mode)[2]
         self._refresh(w)
         return self._wd
 
@@ -180,6 +196,7 @@ class GenSave:
     y_dec1: Optional[torch.Tensor] = None
     sig: Optional[torch.Tensor] = None
     training: bool = True
+    mode: str = "bf16"                      # tg_b200.precision mode of the forward pass
 
 
 class GeneratorEngine:
@@ -202,11 +219,13 @@ class GeneratorEngine:
             raise RuntimeError(f"PConvUNet (B200 path) needs H, W divisible by 128 (7 stride-2 stages), got {H}x{W}; "
                                "the reference always feeds 512x512 tiles (train.py:68, evaluate.py:21)")
         dev = x.device
+        mode = PR.get_precision()
+        adt = PR.act_dtype(mode)
         x3 = x.reshape(B, H, W).contiguous().float()
         m0 = ops.mask_from_f32(mask.reshape(B, H, W).contiguous().float())
         pyr = build_mask_pyramid(m0)
         if save is not None:
-            save.pyr, save.x, save.training = pyr, x3, training
+            save.pyr, save.x, save.training, save.mode = pyr, x3, training, mode
         feats: List[torch.Tensor] = []      # unmasked NHWC outputs of enc1..7
         cur_split = None
         h, w = H, W
@@ -217,11 +236,11 @@ class GeneratorEngine:
             if i == 0:
                 w1 = params[name + ".input_conv.weight"].reshape(cout, k * k).contiguous()
                 z, stats = ops.conv_c1_fwd(x3, m0, k, s, p, w1, params[name + ".input_conv.bias"], code=code,
-                                           lut_dev=pk.lut_dev(dev), want_stats=training)
+                                           lut_dev=pk.lut_dev(dev), want_stats=training, out_dtype=adt)
                 xin = None
             else:
                 xin = cur_split
-                z, stats = ops.conv_igemm(xin, pk.w_fprop(params[name + ".input_conv.weight"]), pk.fplan, (ho, wo),
+                z, stats = ops.conv_igemm(xin, pk.w_fprop(params[name + ".input_conv.weight"], mode), pk.fplan, (ho, wo),
                                           code=code, lut=pk.lut, bias=params[name + ".input_conv.bias"],
                                           want_stats=training)
             scale, shift, mean, invstd = bn_coeffs(stats, B * ho * wo, bns[name], training)
@@ -245,14 +264,14 @@ class GeneratorEngine:
             if not training and save is None:
                 # inference: running-statistics BatchNorm + ReLU folded into the conv epilogue (one pass less per layer)
                 scale, shift, _, _ = bn_coeffs(None, B * hh * ww, bns[name], False)
-                y, _ = ops.conv_igemm(merged, pk.w_fprop(params[name + ".input_conv.weight"]), pk.fplan, (hh, ww),
+                y, _ = ops.conv_igemm(merged, pk.w_fprop(params[name + ".input_conv.weight"], mode), pk.fplan, (hh, ww),
                                       code=code, lut=pk.lut, bias=params[name + ".input_conv.bias"], scale=scale,
                                       shift=shift, act=ACT_RELU)
+                up = y[:, 0]
                 if trace is not None:
-                    trace[name + ".y"] = y
-                up = y
+                    trace[name + ".y"] = up
                 continue
-            z, stats = ops.conv_igemm(merged, pk.w_fprop(params[name + ".input_conv.weight"]), pk.fplan, (hh, ww),
+            z, stats = ops.conv_igemm(merged, pk.w_fprop(params[name + ".input_conv.weight"], mode), pk.fplan, (hh, ww),
                                       code=code, lut=pk.lut, bias=params[name + ".input_conv.bias"],
                                       want_stats=training)
             scale, shift, mean, invstd = bn_coeffs(stats, B * hh * ww, bns[name], training)
@@ -278,6 +297,8 @@ class GeneratorEngine:
         pyr = save.pyr
         B, H, W = save.x.shape
         dev = g_out.device
+        mode = save.mode
+        adt, x3 = PR.act_dtype(mode), mode == "tf32x3"
         grads: Dict[str, torch.Tensor] = {}
 
         def emit(names):
@@ -292,7 +313,7 @@ class GeneratorEngine:
         grads["final.bias"] = torch.empty_like(params["final.bias"])
         ops.conv_to1_wgrad(save.y_dec1, g_pre, self.final_taps, grads["final.weight"], grads["final.bias"])
         emit(["final.weight", "final.bias"])
-        g_y = ops.conv_to1_bwd_data(g_pre, wt, self.final_taps, (H, W), 64)     # grad w.r.t. dec1 output
+        g_y = ops.conv_to1_bwd_data(g_pre, wt, self.final_taps, (H, W), 64, out_dtype=adt)     # grad w.r.t. dec1 output
         g_src = ops.grad_src(g_y)
         skip_grads: Dict[int, object] = {}      # encoder index -> GradSrc of the skip part
         # decoders dec1 .. dec7
@@ -306,11 +327,11 @@ class GeneratorEngine:
                 self.debug[name + ".gz"] = gz
             wkey = name + ".input_conv.weight"
             grads[wkey] = torch.empty_like(params[wkey])
-            ops.wgrad_igemm(ls.xin, gz, pk.fplan, pk.blks(cin, dev), pk.perm(dev), grads[wkey])
+            ops.wgrad_igemm(ls.xin, gz, pk.fplan, pk.blks(cin, dev), pk.perm(dev), grads[wkey], x3=x3)
             grads[name + ".input_conv.bias"], grads[name + ".bn.weight"], grads[name + ".bn.bias"] = dbias, dgam, dbet
             emit([wkey, name + ".input_conv.bias", name + ".bn.weight", name + ".bn.bias"])
             hh, ww = ls.xin.shape[2], ls.xin.shape[3]
-            d_merged, _ = ops.conv_igemm(gz, pk.w_dgrad(params[wkey]), pk.dplan, (hh, ww), code=pyr.dec_mm[i],
+            d_merged, _ = ops.conv_igemm(gz, pk.w_dgrad(params[wkey], mode), pk.dplan, (hh, ww), code=pyr.dec_mm[i],
                                          lut=_MASK01)
             cu = cin if i == 6 else cin - ENC[5 - i][2]
             if i < 6:
@@ -336,12 +357,12 @@ class GeneratorEngine:
             if i == 0:
                 ops.conv_c1_wgrad(save.x, pyr.m0, k, s, p, gz, False, grads[wkey], None)
             else:
-                ops.wgrad_igemm(ls.xin, gz, pk.fplan, pk.blks(cin, dev), pk.perm(dev), grads[wkey])
+                ops.wgrad_igemm(ls.xin, gz, pk.fplan, pk.blks(cin, dev), pk.perm(dev), grads[wkey], x3=x3)
             grads[name + ".input_conv.bias"], grads[name + ".bn.weight"], grads[name + ".bn.bias"] = dbias, dgam, dbet
             emit([wkey, name + ".input_conv.bias", name + ".bn.weight", name + ".bn.bias"])
             if i > 0:
                 hi, wi = ls.xin.shape[2], ls.xin.shape[3]      # half-resolution of the layer input
-                dx, _ = ops.conv_igemm(gz, pk.w_dgrad(params[wkey]), pk.dplan, (hi, wi),
+                dx, _ = ops.conv_igemm(gz, pk.w_dgrad(params[wkey], mode), pk.dplan, (hi, wi),
                                        code=pyr.enc_m_split[i - 1], lut=_MASK01)
                 g_next = ops.grad_src(dx, split=True)
         return grads
@@ -360,10 +381,12 @@ class DiscSave:
     mids: List[LayerSave] = field(default_factory=list)
     y8: Optional[torch.Tensor] = None
     training: bool = True
+    mode: str = "bf16"
 
 
 class DiscriminatorEngine:
     def __init__(self):
+        self.trace = None        # tests may set a list: every forward appends {conv idx: post-activation tensor}
         self.pack = ConvPack(4, 2, 1)
         self.p11 = P.fprop_plan(4, 1, 1)
         self.taps11 = [(dh, dw) for (_, dh, dw) in self.p11.taps]
@@ -380,23 +403,27 @@ class DiscriminatorEngine:
             raise RuntimeError("Discriminator (B200 path) supports input_channels=1 (discriminator.py:7 default)")
         if H % 16 or W % 16:
             raise RuntimeError("Discriminator (B200 path) needs H, W divisible by 16")
+        mode = PR.get_precision()
         x3 = img.reshape(B, H, W).contiguous().float()
         w0 = params["model.0.weight"].reshape(64, 16).contiguous()
         y0, _ = ops.conv_c1_fwd(x3, None, 4, 2, 1, w0, params["model.0.bias"], act=ACT_LEAKY, slope=0.2,
-                                out_split=True)
+                                out_split=True, out_dtype=PR.act_dtype(mode))
         if save is not None:
-            save.img, save.y0, save.training = x3, y0, training
+            save.img, save.y0, save.training, save.mode = x3, y0, training, mode
+        tr = {0: y0} if self.trace is not None else None
         cur = y0
         h, w = H // 2, W // 2
         y8 = None
         for j, (ci, bi, cin, cout) in enumerate(DISC_MID):
             pk = self._packs[ci]
             ho, wo = h // 2, w // 2
-            z, stats = ops.conv_igemm(cur, pk.w_fprop(params[f"model.{ci}.weight"]), pk.fplan, (ho, wo),
+            z, stats = ops.conv_igemm(cur, pk.w_fprop(params[f"model.{ci}.weight"], mode), pk.fplan, (ho, wo),
                                       bias=params[f"model.{ci}.bias"], want_stats=training)
             scale, shift, mean, invstd = bn_coeffs(stats, B * ho * wo, bns[bi], training)
             last = j == 2
             y, ys = ops.bn_apply(z, scale, shift, ACT_LEAKY, 0.2, want_nhwc=last, want_split=not last)
+            if tr is not None:
+                tr[ci] = y if last else ys
             if save is not None:
                 save.mids.append(LayerSave(cur, z, scale, shift, mean, invstd))
             cur = ys if not last else None
@@ -407,12 +434,16 @@ class DiscriminatorEngine:
         logits, _ = ops.conv_to1_fwd(y8, False, (h, w), wt, [16], self.taps11, params["model.11.bias"], (h - 1, w - 1))
         if save is not None:
             save.y8 = y8
+        if tr is not None:
+            self.trace.append(tr)
         return logits.reshape(B, 1, h - 1, w - 1)
 
     def backward(self, g_logits: torch.Tensor, params: Dict[str, torch.Tensor], save: DiscSave, need_input_grad: bool,
                  need_param_grads: bool = True, on_grads=None):
         B, H, W = save.img.shape
         dev = g_logits.device
+        mode = save.mode
+        adt, x3 = PR.act_dtype(mode), mode == "tf32x3"
         grads: Dict[str, torch.Tensor] = {}
 
         def emit(names):
@@ -428,7 +459,7 @@ class DiscriminatorEngine:
             grads["model.11.bias"] = torch.empty_like(params["model.11.bias"])
             ops.conv_to1_wgrad(save.y8, g, self.taps11, grads["model.11.weight"], grads["model.11.bias"])
             emit(["model.11.weight", "model.11.bias"])
-        g_y = ops.conv_to1_bwd_data(g, wt, self.taps11, (h8, w8), 512)
+        g_y = ops.conv_to1_bwd_data(g, wt, self.taps11, (h8, w8), 512, out_dtype=adt)
         g_src = ops.grad_src(g_y)
         for j in range(2, -1, -1):
             ci, bi, cin, cout = DISC_MID[j]
@@ -439,14 +470,15 @@ class DiscriminatorEngine:
             wkey = f"model.{ci}.weight"
             if need_param_grads:
                 grads[wkey] = torch.empty_like(params[wkey])
-                ops.wgrad_igemm(ls.xin, gz, pk.fplan, pk.blks(cin, dev), pk.perm(dev), grads[wkey])
+                ops.wgrad_igemm(ls.xin, gz, pk.fplan, pk.blks(cin, dev), pk.perm(dev), grads[wkey], x3=x3)
                 grads[f"model.{ci}.bias"], grads[f"model.{bi}.weight"], grads[f"model.{bi}.bias"] = dbias, dgam, dbet
                 emit([wkey, f"model.{ci}.bias", f"model.{bi}.weight", f"model.{bi}.bias"])
             hi, wi = ls.xin.shape[2], ls.xin.shape[3]
             if j > 0:
-                dx, _ = ops.conv_igemm(gz, pk.w_dgrad(params[wkey]), pk.dplan, (hi, wi))
+                dx, _ = ops.conv_igemm(gz, pk.w_dgrad(params[wkey], mode), pk.dplan, (hi, wi))
             else:   # into model[0]'s LeakyReLU output: fold the activation derivative (discriminator.py:14)
-                dx, _ = ops.conv_igemm(gz, pk.w_dgrad(params[wkey]), pk.dplan, (hi, wi), gate=save.y0, gate_slope=0.2)
+                dx, _ = ops.conv_igemm(gz, pk.w_dgrad(params[wkey], mode), pk.dplan, (hi, wi), gate=save.y0,
+                                       gate_slope=0.2)
             g_src = ops.grad_src(dx, split=True)
             gz0 = dx
         if need_param_grads:
@@ -475,6 +507,7 @@ class VggEngine:
     losses.py:79): conv0's three identical input channels are folded into one (weights summed)."""
 
     def __init__(self):
+        self.trace = None        # tests may set a list: every features() call appends {conv idx: post-ReLU tensor}
         self.pack = {idx: ConvPack(3, 1, 1) for idx, _, _ in VGG_CONVS[1:]}
         d = P.dgrad_plan(3, 1, 1)
         self.d_taps = [(dh, dw) for (_, dh, dw) in d.taps]
@@ -492,23 +525,31 @@ class VggEngine:
     def features(self, img: torch.Tensor, vgg: Dict[str, torch.Tensor], save: Optional[list]):
         """img fp32 [B,1,H,W] -> bf16 [B,H/4,W/4,256]; `save` collects the post-ReLU activations."""
         B, _, H, W = img.shape
+        mode = PR.get_precision()
         x3 = img.reshape(B, H, W).contiguous().float()
-        y, _ = ops.conv_c1_fwd(x3, None, 3, 1, 1, self._w0_folded(vgg["0.weight"]), vgg["0.bias"], act=ACT_RELU)
+        y, _ = ops.conv_c1_fwd(x3, None, 3, 1, 1, self._w0_folded(vgg["0.weight"]), vgg["0.bias"], act=ACT_RELU,
+                               out_dtype=PR.act_dtype(mode))
         if save is not None:
             save.append(y)
+        tr = {0: y} if self.trace is not None else None
         h, w = H, W
         for idx, cin, cout in VGG_CONVS[1:]:
             pk = self.pack[idx]
-            y, _ = ops.conv_igemm(y, pk.w_fprop(vgg[f"{idx}.weight"]), pk.fplan, (h, w), bias=vgg[f"{idx}.bias"],
+            y, _ = ops.conv_igemm(y, pk.w_fprop(vgg[f"{idx}.weight"], mode), pk.fplan, (h, w), bias=vgg[f"{idx}.bias"],
                                   act=ACT_RELU)
             if save is not None:
                 save.append(y)
+            if tr is not None:
+                tr[idx] = y
             if idx in VGG_POOL_AFTER:
                 y = ops.maxpool2(y[:, 0]).unsqueeze(1)
                 h, w = h // 2, w // 2
+        if tr is not None:
+            self.trace.append(tr)
         return y
 
-    def backward(self, g_feat: torch.Tensor, vgg: Dict[str, torch.Tensor], saved: list, hw) -> torch.Tensor:
+    def backward(self, g_feat: torch.Tensor, vgg: Dict[str, torch.Tensor], saved: list, hw,
+                 mode: str = "bf16") -> torch.Tensor:
         """g_feat: gradient w.r.t. the pre-ReLU output of conv14 (bf16 [B,1,h,w,256]) -> fp32 [B,1,H,W]."""
         H, W = hw
         ys = {idx: saved[i] for i, (idx, _, _) in enumerate(VGG_CONVS)}
@@ -517,7 +558,7 @@ class VggEngine:
         prev = {14: 12, 12: 10, 10: 7, 7: 5, 5: 2, 2: 0}
         for idx in order:
             pk = self.pack[idx]
-            wd = pk.w_dgrad(vgg[f"{idx}.weight"])
+            wd = pk.w_dgrad(vgg[f"{idx}.weight"], mode)
             h, w = gz.shape[2], gz.shape[3]
             pi = prev[idx]
             if pi in VGG_POOL_AFTER:     # this conv reads pool(y_prev): route through the pool, then y_prev's ReLU

@@ -15,6 +15,42 @@ from ._lib import ConvArgs, WgradArgs, check, lib, ptr, stream_ptr
 from .plan import TapPlan
 
 BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _act_dtype(t: torch.Tensor, name: str):
+    """Activation tensors are bf16 (product path) or fp32 (verification path, tg_b200.precision)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor — the TERRA-GAN hot path has no CPU fallback")
+    if t.dtype not in (BF16, F32):
+        raise RuntimeError(f"{name}: expected a bf16 or fp32 activation tensor, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+    return t.dtype
+
+
+def _fn(name: str, dtype):
+    """Entry point of the storage type: tg_x for bf16, tg_x_f32 for fp32."""
+    return getattr(lib(), name if dtype == BF16 else name + "_f32"), (name if dtype == BF16 else name + "_f32")
+
+
+def split_tf32(x: torch.Tensor, layout: int) -> torch.Tensor:
+    """Two-term TF32 split along the last dim (tg_split_tf32): layout 0 [hi|lo|hi], 1 [hi|hi|lo], 2 [hi|lo], 3 [hi],
+    4 [lo|hi]."""
+    _req(x, F32, "x")
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    parts = {0: 3, 1: 3, 2: 2, 3: 1, 4: 2}[layout]
+    out = torch.empty(x.shape[:-1] + (Cc * parts,), dtype=F32, device=x.device)
+    check(lib().tg_split_tf32(ptr(x), rows, Cc, layout, ptr(out), stream_ptr()), "tg_split_tf32")
+    return out
+
+
+def split_hi_lo(w: torch.Tensor):
+    """(tf32(w), tf32(w - tf32(w))) with the shape of w."""
+    flat = split_tf32(w.detach().float().contiguous().reshape(1, -1), 2)
+    n = w.numel()
+    return flat[0, :n].reshape(w.shape), flat[0, n:].reshape(w.shape)
 
 # bench.py sets PROFILE = [] to time every tensor-core launch with CUDA events on the launching stream:
 # entries are (kind, algorithmic FLOPs, start event, end event). Events come from a pool created up front
@@ -80,8 +116,18 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
 
     x: bf16 [B, P, H, W, C];  w_packed: bf16 [N, Ktot];  plan: fprop_plan / dgrad_plan.
     Returns (out, stats) where stats is None or fp32 [rows, 2, N] per-CTA partial sums."""
-    _req(x, BF16, "x")
-    _req(w_packed, BF16, "w_packed")
+    dt = _act_dtype(x, "x")
+    addend = None
+    if isinstance(w_packed, tuple):
+        # tf32x3: (main, cross) operand matrices = (w_hi, [w_hi | w_lo] per tap). A first launch forms the cross terms
+        # x_lo*w_hi + x_hi*w_lo on its own (small) accumulator; the main launch adds them to x_hi*w_hi before the
+        # epilogue, so the tensor core's long accumulation chain carries the main term only.
+        if dt != F32:
+            raise RuntimeError("conv_igemm: split operands are an fp32-path feature")
+        w_packed, w_cross = w_packed
+        addend, _ = conv_igemm(split_tf32(x, 4), w_cross, plan, out_hw)
+        x = split_tf32(x, 3)
+    _req(w_packed, dt, "w_packed")
     B, P, H, W, Cc = x.shape
     N, Ktot = w_packed.shape
     Ho, Wo = out_hw
@@ -89,9 +135,9 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
     if P != plan.in_planes:
         raise RuntimeError(f"conv_igemm: input has {P} planes, plan expects {plan.in_planes}")
     if out is None:
-        out = torch.empty((B, Po, Ho, Wo, N), dtype=BF16, device=x.device)
+        out = torch.empty((B, Po, Ho, Wo, N), dtype=dt, device=x.device)
     else:
-        _req(out, BF16, "out")
+        _req(out, dt, "out")
     a = ConvArgs()
     a.x, a.B, a.P, a.H, a.W, a.C = ptr(x), B, P, H, W, Cc
     a.w, a.N, a.Ktot = ptr(w_packed), N, Ktot
@@ -116,8 +162,10 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
                 raise RuntimeError(f"conv_igemm: {name} must have N={N} entries")
         setattr(a, name, ptr(t))
     a.act, a.slope = act, slope
+    a.dtype = _lib.DTYPE_BF16 if dt == BF16 else _lib.DTYPE_F32
+    a.addend = ptr(addend)
     if gate is not None:
-        _req(gate, BF16, "gate")
+        _req(gate, dt, "gate")
         if gate.numel() != out.numel():
             raise RuntimeError("conv_igemm: gate must have the shape of the output")
         a.gate, a.gate_slope = ptr(gate), gate_slope
@@ -138,40 +186,65 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
 _BLK_DTYPE = None
 
 
-def wgrad_blk_table(plan: TapPlan, Cin: int, device) -> torch.Tensor:
-    """Device table of tg_wgrad_blk {int8 plane, dh, dw, pad; int32 cb; int32 row}, tap-major."""
+def wgrad_blk_table(plan: TapPlan, Cin: int, device, gran: int = 64) -> torch.Tensor:
+    """Device table of tg_wgrad_blk {int8 plane, dh, dw, pad; int32 cb; int32 row}, tap-major. `gran` = channels
+    per block: 64 (bf16 storage) or 32 (fp32 storage)."""
     import numpy as np
     dt = np.dtype([("plane", "i1"), ("dh", "i1"), ("dw", "i1"), ("pad", "i1"), ("cb", "<i4"), ("row", "<i4")])
     rows = []
     for t, (pl, dh, dw) in enumerate(plan.taps):
-        for cb in range(Cin // 64):
-            rows.append((pl, dh, dw, 0, cb, t * Cin + cb * 64))
+        for cb in range(Cin // gran):
+            rows.append((pl, dh, dw, 0, cb, t * Cin + cb * gran))
     arr = np.array(rows, dtype=dt)
     return torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(device)
 
 
-def wgrad_igemm(x: torch.Tensor, g: torch.Tensor, plan: TapPlan, blks: torch.Tensor,
-                tap_perm: torch.Tensor, dw: torch.Tensor, accumulate: bool = False) -> None:
+_F32_BLKS: dict = {}
+
+
+def wgrad_igemm(x: torch.Tensor, g: torch.Tensor, plan: TapPlan, blks: Optional[torch.Tensor],
+                tap_perm: torch.Tensor, dw: torch.Tensor, accumulate: bool = False, x3: bool = False) -> None:
     """dw[N][C][kh][kw] (+)= sum_pixels x[pix (+) tap][c] * g[pix][n]   (tg_wgrad_igemm + reduce).
 
     x: bf16 [B, P, H, W, C] (forward input, masked); g: bf16 [B, 1, Ho, Wo, N];
-    plan: the layer's *fprop* plan; dw: fp32 [N, C, k, k] contiguous."""
-    _req(x, BF16, "x")
-    _req(g, BF16, "g")
+    plan: the layer's *fprop* plan; dw: fp32 [N, C, k, k] contiguous.
+    fp32 x / g select the verification path (kind::tf32; `blks` is built here at 32-channel granularity); with
+    x3 the product is evaluated on two-term TF32 splits: [x_hi | x_lo] against [g_hi | g_lo] in one launch, of
+    which the hi*hi, lo*hi and hi*lo blocks are summed."""
+    dt = _act_dtype(x, "x")
+    _req(g, dt, "g")
     _req(dw, torch.float32, "dw")
+    if dt == F32 and x3:
+        N0, C0 = g.shape[-1], x.shape[-1]
+        dw2 = torch.empty((2 * N0, 2 * C0) + tuple(dw.shape[2:]), dtype=torch.float32, device=dw.device)
+        wgrad_igemm(split_tf32(x, 2), split_tf32(g, 2), plan, None, tap_perm, dw2)
+        tot = dw2[:N0, :C0] + dw2[:N0, C0:] + dw2[N0:, :C0]
+        if accumulate:
+            dw.add_(tot)
+        else:
+            dw.copy_(tot)
+        return
     B, P, H, W, Cc = x.shape
     _, _, Ho, Wo, N = g.shape
     T = len(plan.taps)
-    need = lib().tg_wgrad_partial_floats(B, Ho, Wo, T, Cc, N)
+    if dt == F32:
+        key = (id(plan), Cc, str(x.device))
+        if key not in _F32_BLKS:
+            _F32_BLKS[key] = (plan, wgrad_blk_table(plan, Cc, x.device, 32))
+        blks = _F32_BLKS[key][1]
+        need = lib().tg_wgrad_partial_floats_f32(B, Ho, Wo, T, Cc, N)
+    else:
+        need = lib().tg_wgrad_partial_floats(B, Ho, Wo, T, Cc, N)
     partial = torch.empty((need,), dtype=torch.float32, device=x.device)
     a = WgradArgs()
+    a.dtype = _lib.DTYPE_BF16 if dt == BF16 else _lib.DTYPE_F32
     a.x, a.B, a.P, a.H, a.W, a.C = ptr(x), B, P, H, W, Cc
     a.g, a.Ho, a.Wo, a.N = ptr(g), Ho, Wo, N
     a.num_taps = T
     for i, (pl, dh, dw_) in enumerate(plan.taps):
         a.tap_plane[i], a.tap_dh[i], a.tap_dw[i] = pl, dh, dw_
     a.partial, a.partial_cap = ptr(partial), need
-    a.blks, a.num_blk = ptr(blks), T * (Cc // 64)
+    a.blks, a.num_blk = ptr(blks), T * (Cc // (64 if dt == BF16 else 32))
     ev0 = _prof_begin()
     check(lib().tg_wgrad_igemm(C.byref(a), stream_ptr()), "tg_wgrad_igemm")
     _prof_end("wgrad", 2.0 * B * Ho * Wo * N * T * Cc, ev0, f"B{B} x {H}x{W}x{Cc}(P{P}) g {Ho}x{Wo}x{N} taps{T} splits{a.splits}")
@@ -244,24 +317,27 @@ def bn_eval_coeff(gamma, beta, running_mean, running_var, eps):
 
 def bn_apply(z, scale, shift, act, slope=0.0, code=None, want_nhwc=True, want_split=False, mask_split=False):
     """z bf16 [B,1,H,W,C] or [B,H,W,C] -> (y_nhwc [B,H,W,C] | None, y_split [B,4,H/2,W/2,C] | None)."""
-    _req(z, BF16, "z")
+    dt = _act_dtype(z, "z")
     if z.dim() == 5:
         z = z[:, 0]
     B, H, W, Cc = z.shape
-    y = torch.empty((B, H, W, Cc), dtype=BF16, device=z.device) if want_nhwc else None
-    ys = torch.empty((B, 4, H // 2, W // 2, Cc), dtype=BF16, device=z.device) if want_split else None
-    check(lib().tg_bn_apply(ptr(z), B, H, W, Cc, ptr(scale), ptr(shift), act, slope, ptr(code), ptr(y), ptr(ys),
-                            1 if mask_split else 0, stream_ptr()), "tg_bn_apply")
+    y = torch.empty((B, H, W, Cc), dtype=dt, device=z.device) if want_nhwc else None
+    ys = torch.empty((B, 4, H // 2, W // 2, Cc), dtype=dt, device=z.device) if want_split else None
+    fn, name = _fn("tg_bn_apply", dt)
+    check(fn(ptr(z), B, H, W, Cc, ptr(scale), ptr(shift), act, slope, ptr(code), ptr(y), ptr(ys),
+             1 if mask_split else 0, stream_ptr()), name)
     return y, ys
 
 
 def grad_src(t: Optional[torch.Tensor], chan_off: int = 0, split: bool = False) -> _lib.GradSrc:
-    """Describe a bf16 gradient tensor whose last dim is the channel dim (pixel stride = last dim)."""
+    """Describe a gradient tensor (bf16, or fp32 on the verification path) whose last dim is the channel dim
+    (pixel stride = last dim)."""
     s = _lib.GradSrc()
     if t is None:
         s.ptr, s.pix_stride, s.chan_off, s.split = None, 0, 0, 0
+        s._dtype = None
     else:
-        _req(t, BF16, "grad")
+        s._dtype = _act_dtype(t, "grad")
         s.ptr, s.pix_stride, s.chan_off, s.split = ptr(t), t.shape[-1], chan_off, 1 if split else 0
         s._keep = t  # the descriptor only holds a raw pointer: keep the tensor alive with it
     return s
@@ -270,6 +346,10 @@ def grad_src(t: Optional[torch.Tensor], chan_off: int = 0, split: bool = False) 
 def bn_bwd(g0: _lib.GradSrc, g1: Optional[_lib.GradSrc], z, scale, shift, mean, invstd, act, slope, code,
            lut_dev, want_dbias=True, batch_stats=True):
     """BN(+act, +mask ratio) backward. Returns (gz bf16 [B,1,H,W,C], dgamma, dbeta, dbias)."""
+    dt = _act_dtype(z, "z")
+    for s_ in (g0, g1):
+        if s_ is not None and getattr(s_, "_dtype", dt) not in (None, dt):
+            raise RuntimeError(f"bn_bwd: gradient source is {s_._dtype}, z is {dt}")
     if z.dim() == 5:
         z = z[:, 0]
     B, H, W, Cc = z.shape
@@ -278,17 +358,18 @@ def bn_bwd(g0: _lib.GradSrc, g1: Optional[_lib.GradSrc], z, scale, shift, mean, 
     partial = torch.empty((rows_cap, 5, Cc), dtype=torch.float32, device=dev)
     used = C.c_int(0)
     g1p = C.byref(g1) if g1 is not None else None
-    check(lib().tg_bn_bwd_reduce(C.byref(g0), g1p, ptr(z), B, H, W, Cc, ptr(scale), ptr(shift), act, slope,
-                                 ptr(code), ptr(lut_dev), ptr(partial), rows_cap, C.byref(used), stream_ptr()),
-          "tg_bn_bwd_reduce")
+    fn_r, name_r = _fn("tg_bn_bwd_reduce", dt)
+    fn_a, name_a = _fn("tg_bn_bwd_apply", dt)
+    check(fn_r(C.byref(g0), g1p, ptr(z), B, H, W, Cc, ptr(scale), ptr(shift), act, slope,
+               ptr(code), ptr(lut_dev), ptr(partial), rows_cap, C.byref(used), stream_ptr()), name_r)
     outs = torch.empty((8, Cc), dtype=torch.float32, device=dev)  # coeff[5], dgamma, dbeta, dbias
     check(lib().tg_bn_bwd_finalize(ptr(partial), used.value, Cc, float(B * H * W), ptr(scale), ptr(mean),
                                    ptr(invstd), ptr(outs), ptr(outs[5]), ptr(outs[6]),
                                    ptr(outs[7]) if want_dbias else None, 0, 1 if batch_stats else 0, stream_ptr()),
           "tg_bn_bwd_finalize")
-    gz = torch.empty((B, 1, H, W, Cc), dtype=BF16, device=dev)
-    check(lib().tg_bn_bwd_apply(C.byref(g0), g1p, ptr(z), B, H, W, Cc, ptr(shift), ptr(outs), act, slope, ptr(code),
-                                ptr(lut_dev), ptr(gz), stream_ptr()), "tg_bn_bwd_apply")
+    gz = torch.empty((B, 1, H, W, Cc), dtype=dt, device=dev)
+    check(fn_a(C.byref(g0), g1p, ptr(z), B, H, W, Cc, ptr(shift), ptr(outs), act, slope, ptr(code),
+               ptr(lut_dev), ptr(gz), stream_ptr()), name_a)
     return gz, outs[5], outs[6], outs[7]
 
 
@@ -297,43 +378,44 @@ def bn_bwd(g0: _lib.GradSrc, g1: Optional[_lib.GradSrc], z, scale, shift, mean, 
 # ------------------------------------------------------------------------------------------------
 def upsample_concat(up, skip, merged_mask):
     """up bf16 [B,h,w,Cu], skip bf16 [B,2h,2w,Cs] | None, merged_mask u8 [B,2h,2w] -> [B,1,2h,2w,Cu+Cs]."""
-    _req(up, BF16, "up")
+    dt = _act_dtype(up, "up")
     B, h, w, Cu = up.shape
     Cs = 0
     if skip is not None:
-        _req(skip, BF16, "skip")
+        _req(skip, dt, "skip")
         Cs = skip.shape[-1]
-    out = torch.empty((B, 1, 2 * h, 2 * w, Cu + Cs), dtype=BF16, device=up.device)
-    check(lib().tg_upsample_concat(ptr(up), B, h, w, Cu, ptr(skip), Cs, ptr(merged_mask), ptr(out), stream_ptr()),
-          "tg_upsample_concat")
+    out = torch.empty((B, 1, 2 * h, 2 * w, Cu + Cs), dtype=dt, device=up.device)
+    fn, name = _fn("tg_upsample_concat", dt)
+    check(fn(ptr(up), B, h, w, Cu, ptr(skip), Cs, ptr(merged_mask), ptr(out), stream_ptr()), name)
     return out
 
 
 def upsample_concat_bwd(d_merged, Cu):
     """d_merged bf16 [B,1,2h,2w,Ctot] -> d_up bf16 [B,h,w,Cu]."""
-    _req(d_merged, BF16, "d_merged")
+    dt = _act_dtype(d_merged, "d_merged")
     B, _, H, W, Ct = d_merged.shape
-    out = torch.empty((B, H // 2, W // 2, Cu), dtype=BF16, device=d_merged.device)
-    check(lib().tg_upsample_concat_bwd(ptr(d_merged), B, H // 2, W // 2, Cu, Ct, ptr(out), stream_ptr()),
-          "tg_upsample_concat_bwd")
+    out = torch.empty((B, H // 2, W // 2, Cu), dtype=dt, device=d_merged.device)
+    fn, name = _fn("tg_upsample_concat_bwd", dt)
+    check(fn(ptr(d_merged), B, H // 2, W // 2, Cu, Ct, ptr(out), stream_ptr()), name)
     return out
 
 
 def maxpool2(x):
-    _req(x, BF16, "x")
+    dt = _act_dtype(x, "x")
     B, H, W, Cc = x.shape
-    y = torch.empty((B, H // 2, W // 2, Cc), dtype=BF16, device=x.device)
-    check(lib().tg_maxpool2(ptr(x), B, H, W, Cc, ptr(y), stream_ptr()), "tg_maxpool2")
+    y = torch.empty((B, H // 2, W // 2, Cc), dtype=dt, device=x.device)
+    fn, name = _fn("tg_maxpool2", dt)
+    check(fn(ptr(x), B, H, W, Cc, ptr(y), stream_ptr()), name)
     return y
 
 
 def maxpool2_bwd(x, gy, relu_gate=True):
-    _req(x, BF16, "x")
-    _req(gy, BF16, "gy")
+    dt = _act_dtype(x, "x")
+    _req(gy, dt, "gy")
     B, H, W, Cc = x.shape
     gx = torch.empty_like(x)
-    check(lib().tg_maxpool2_bwd(ptr(x), ptr(gy), B, H, W, Cc, 1 if relu_gate else 0, ptr(gx), stream_ptr()),
-          "tg_maxpool2_bwd")
+    fn, name = _fn("tg_maxpool2_bwd", dt)
+    check(fn(ptr(x), ptr(gy), B, H, W, Cc, 1 if relu_gate else 0, ptr(gx), stream_ptr()), name)
     return gx
 
 
@@ -341,22 +423,22 @@ def maxpool2_bwd(x, gy, relu_gate=True):
 # bandwidth-bound convolutions
 # ------------------------------------------------------------------------------------------------
 def conv_c1_fwd(x, xmask, k, s, pad, wgt, bias, code=None, lut_dev=None, act=0, slope=0.0, out_split=False,
-                want_stats=False):
-    """x fp32 [B,H,W] -> bf16 [B,1,Ho,Wo,64] (or [B,4,Ho/2,Wo/2,64] if out_split), stats|None."""
+                want_stats=False, out_dtype=BF16):
+    """x fp32 [B,H,W] -> bf16 (or fp32: out_dtype) [B,1,Ho,Wo,64] (or [B,4,Ho/2,Wo/2,64] if out_split), stats|None."""
     _req(x, torch.float32, "x")
     _req(wgt, torch.float32, "wgt")
     B, H, W = x.shape
     Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
     shape = (B, 4, Ho // 2, Wo // 2, 64) if out_split else (B, 1, Ho, Wo, 64)
-    out = torch.empty(shape, dtype=BF16, device=x.device)
+    out = torch.empty(shape, dtype=out_dtype, device=x.device)
     stats, used = None, C.c_int(0)
     rows = 0
     if want_stats:
         rows = num_sms() * 4
         stats = torch.empty((rows, 2, 64), dtype=torch.float32, device=x.device)
-    check(lib().tg_conv_c1_fwd(ptr(x), ptr(xmask), B, H, W, k, s, pad, ptr(wgt), ptr(bias), ptr(code), ptr(lut_dev),
-                               act, slope, ptr(out), 1 if out_split else 0, ptr(stats), rows, C.byref(used),
-                               stream_ptr()), "tg_conv_c1_fwd")
+    fn, name = _fn("tg_conv_c1_fwd", out_dtype)
+    check(fn(ptr(x), ptr(xmask), B, H, W, k, s, pad, ptr(wgt), ptr(bias), ptr(code), ptr(lut_dev),
+             act, slope, ptr(out), 1 if out_split else 0, ptr(stats), rows, C.byref(used), stream_ptr()), name)
     if stats is not None:
         stats = stats[: used.value]
     return out, stats
@@ -364,12 +446,13 @@ def conv_c1_fwd(x, xmask, k, s, pad, wgt, bias, code=None, lut_dev=None, act=0, 
 
 def conv_c1_wgrad(x, xmask, k, s, pad, g, g_split, dw, db=None, accumulate=False):
     _req(x, torch.float32, "x")
-    _req(g, BF16, "g")
+    dt = _act_dtype(g, "g")
     B, H, W = x.shape
     rows = lib().tg_conv_c1_wgrad_rows()
     partial = torch.empty((rows * 64 * (k * k + 1),), dtype=torch.float32, device=x.device)
-    check(lib().tg_conv_c1_wgrad(ptr(x), ptr(xmask), B, H, W, k, s, pad, ptr(g), 1 if g_split else 0, ptr(partial),
-                                 rows, ptr(dw), ptr(db), 1 if accumulate else 0, stream_ptr()), "tg_conv_c1_wgrad")
+    fn, name = _fn("tg_conv_c1_wgrad", dt)
+    check(fn(ptr(x), ptr(xmask), B, H, W, k, s, pad, ptr(g), 1 if g_split else 0, ptr(partial),
+             rows, ptr(dw), ptr(db), 1 if accumulate else 0, stream_ptr()), name)
 
 
 def _tap_arrays(taps):
@@ -381,7 +464,7 @@ def _tap_arrays(taps):
 
 def conv_to1_fwd(x, x_split, hw, wgt, cls_counts, taps, bias, out_hw, mode=0, mask=None, xin=None, want_sig=False):
     """x bf16 [B,H,W,C] (or parity-split of it), wgt fp32 [ntaps,C], taps [(dh,dw)] -> fp32 [B,Ho,Wo]."""
-    _req(x, BF16, "x")
+    dt = _act_dtype(x, "x")
     _req(wgt, torch.float32, "wgt")
     B = x.shape[0]
     Cc = x.shape[-1]
@@ -391,6 +474,11 @@ def conv_to1_fwd(x, x_split, hw, wgt, cls_counts, taps, bias, out_hw, mode=0, ma
     sig = torch.empty((B, Ho, Wo), dtype=torch.float32, device=x.device) if want_sig else None
     dh, dw = _tap_arrays(taps)
     cc = (C.c_int * len(cls_counts))(*cls_counts)
+    if dt == F32:
+        check(lib().tg_conv_to1_fwd_f32(ptr(x), 1 if x_split else 0, B, H, W, Cc, ptr(wgt), len(cls_counts), cc, dh, dw,
+                                        ptr(bias), Ho, Wo, mode, ptr(mask), ptr(xin), ptr(out), ptr(sig), stream_ptr()),
+              "tg_conv_to1_fwd_f32")
+        return out, sig
     nscr = lib().tg_conv_to1_fwd_scratch_floats(B, H, W, Cc, len(taps))
     scratch = torch.empty((nscr,), dtype=torch.float32, device=x.device) if nscr else None
     check(lib().tg_conv_to1_fwd(ptr(x), 1 if x_split else 0, B, H, W, Cc, ptr(wgt), len(cls_counts), cc, dh, dw,
@@ -402,21 +490,21 @@ def conv_to1_fwd(x, x_split, hw, wgt, cls_counts, taps, bias, out_hw, mode=0, ma
     return out, sig
 
 
-def conv_to1_bwd_data(g, wgt, taps, hw, Cc):
-    """g fp32 [B,Ho,Wo], wgt fp32 [ntaps,C] -> dx bf16 [B,H,W,C]."""
+def conv_to1_bwd_data(g, wgt, taps, hw, Cc, out_dtype=BF16):
+    """g fp32 [B,Ho,Wo], wgt fp32 [ntaps,C] -> dx bf16 (or fp32: out_dtype) [B,H,W,C]."""
     _req(g, torch.float32, "g")
     B, Ho, Wo = g.shape
     H, W = hw
-    dx = torch.empty((B, H, W, Cc), dtype=BF16, device=g.device)
+    dx = torch.empty((B, H, W, Cc), dtype=out_dtype, device=g.device)
     dh, dw = _tap_arrays(taps)
-    check(lib().tg_conv_to1_bwd_data(ptr(g), B, Ho, Wo, ptr(wgt), len(taps), dh, dw, H, W, Cc, ptr(dx),
-                                     stream_ptr()), "tg_conv_to1_bwd_data")
+    fn, name = _fn("tg_conv_to1_bwd_data", out_dtype)
+    check(fn(ptr(g), B, Ho, Wo, ptr(wgt), len(taps), dh, dw, H, W, Cc, ptr(dx), stream_ptr()), name)
     return dx
 
 
 def conv_to1_wgrad(x, g, taps, dw, db=None, accumulate=False):
     """x bf16 [B,H,W,C], g fp32 [B,Ho,Wo] -> dw fp32 [1,C,k,k] (+)=, db fp32 [1] (+)=."""
-    _req(x, BF16, "x")
+    dt = _act_dtype(x, "x")
     _req(g, torch.float32, "g")
     B, H, W, Cc = x.shape
     _, Ho, Wo = g.shape
@@ -424,9 +512,9 @@ def conv_to1_wgrad(x, g, taps, dw, db=None, accumulate=False):
     partial = torch.empty((rows * len(taps) * Cc,), dtype=torch.float32, device=x.device)
     partial_b = torch.empty((rows,), dtype=torch.float32, device=x.device)
     dh, dww = _tap_arrays(taps)
-    check(lib().tg_conv_to1_wgrad(ptr(x), B, H, W, Cc, ptr(g), Ho, Wo, len(taps), dh, dww, ptr(partial),
-                                  ptr(partial_b), rows, ptr(dw), ptr(db), 1 if accumulate else 0, stream_ptr()),
-          "tg_conv_to1_wgrad")
+    fn, name = _fn("tg_conv_to1_wgrad", dt)
+    check(fn(ptr(x), B, H, W, Cc, ptr(g), Ho, Wo, len(taps), dh, dww, ptr(partial),
+             ptr(partial_b), rows, ptr(dw), ptr(db), 1 if accumulate else 0, stream_ptr()), name)
 
 
 def final_bwd_pre(g_out, sig, mask_u8):
@@ -466,21 +554,23 @@ def inpaint_loss_bwd(pred, target, mask, terms, grad_terms, flags=0, eps=1e-6):
 
 
 def l1_bf16_fwd(a, b):
-    _req(a, BF16, "a")
-    _req(b, BF16, "b")
+    """mean |a - b| of two activation tensors (bf16, or fp32 on the verification path)."""
+    dt = _act_dtype(a, "a")
+    _req(b, dt, "b")
     rows = lib().tg_loss_rows()
     partial = torch.empty((rows,), dtype=torch.float32, device=a.device)
     out = torch.empty((1,), dtype=torch.float32, device=a.device)
-    check(lib().tg_l1_bf16_fwd(ptr(a), ptr(b), a.numel(), ptr(partial), rows, ptr(out), stream_ptr()),
-          "tg_l1_bf16_fwd")
+    fn, name = (lib().tg_l1_bf16_fwd, "tg_l1_bf16_fwd") if dt == BF16 else (lib().tg_l1_f32_fwd, "tg_l1_f32_fwd")
+    check(fn(ptr(a), ptr(b), a.numel(), ptr(partial), rows, ptr(out), stream_ptr()), name)
     return out
 
 
 def l1_bf16_bwd(a, b, grad_out, relu_gate=True):
+    dt = _act_dtype(a, "a")
     _req(grad_out, torch.float32, "grad_out")
     ga = torch.empty_like(a)
-    check(lib().tg_l1_bf16_bwd(ptr(a), ptr(b), a.numel(), ptr(grad_out), 1 if relu_gate else 0, ptr(ga),
-                               stream_ptr()), "tg_l1_bf16_bwd")
+    fn, name = (lib().tg_l1_bf16_bwd, "tg_l1_bf16_bwd") if dt == BF16 else (lib().tg_l1_f32_bwd, "tg_l1_f32_bwd")
+    check(fn(ptr(a), ptr(b), a.numel(), ptr(grad_out), 1 if relu_gate else 0, ptr(ga), stream_ptr()), name)
     return ga
 
 

@@ -100,6 +100,26 @@ def pack_w_dgrad(w: torch.Tensor, plan: TapPlan) -> torch.Tensor:
     return _arrange_dgrad(w.detach(), plan).to(torch.bfloat16).contiguous()
 
 
+def pack_w_fprop_f32(w: torch.Tensor, split=None):
+    """fp32 operand matrix of the verification path. `split(w) -> (hi, lo)` (two-term TF32 split) selects the
+    tf32x3 form, a (main, cross) pair: w_hi for activations x_hi, and input channels [w_hi | w_lo] for activations
+    laid out [x_lo | x_hi] (the cross terms)."""
+    w = w.detach().float()
+    if split is None:
+        return _arrange_fprop(w).contiguous()
+    hi, lo = split(w)
+    return _arrange_fprop(hi).contiguous(), _arrange_fprop(torch.cat([hi, lo], dim=1)).contiguous()
+
+
+def pack_w_dgrad_f32(w: torch.Tensor, plan: TapPlan, split=None):
+    """Same for the data-gradient operand: the contraction runs over Cout, so the split goes along dim 0."""
+    w = w.detach().float()
+    if split is None:
+        return _arrange_dgrad(w, plan).contiguous()
+    hi, lo = split(w)
+    return _arrange_dgrad(hi, plan).contiguous(), _arrange_dgrad(torch.cat([hi, lo], dim=0), plan).contiguous()
+
+
 def pack_scatter_index(shape, plan: Optional[TapPlan], device) -> torch.Tensor:
     """int32 [numel]: position in the packed matrix (fprop layout if plan is None, else the dgrad layout of
     `plan`) of every element of a [Cout, Cin, kh, kw] weight in its natural order. Both packings are

@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/terragan_b200.h but not exported"
     assert declared == set(_lib.PROTOTYPES), "ctypes prototypes and header declarations differ"
-    assert _lib.lib().tg_version() == 1
+    assert _lib.lib().tg_version() == 2
 
 
 def test_error_reporting_without_gpu_compute():
