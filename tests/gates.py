@@ -59,3 +59,29 @@ def summarize(tape) -> str:
     total = sum(v[1] for v in tape.report.values())
     worst = max((v[2] for v in tape.report.values()), default=0.0)
     return f"{flips} of {total} branch decisions differ ({flips / max(total, 1):.1e}); largest |pre|/std among them {worst:.1e}"
+
+
+def run_adversarial(G, D, criterion, real_c, masks_c, lr=2e-4, optimizers=None):
+    """One iteration of train.py:179-219 with the drop-in modules, written out as the reference loop does it;
+    returns outputs, losses and gradient snapshots (taken before each optimizer step)."""
+    bce = torch.nn.BCEWithLogitsLoss()
+    opt_G, opt_D = optimizers or (torch.optim.Adam(G.parameters(), lr=lr), torch.optim.Adam(D.parameters(), lr=lr))
+    masked = real_c * masks_c
+    opt_G.zero_grad()
+    gen = G(masked, masks_c)
+    g_loss = criterion(gen, real_c, masks_c)
+    fake = D(gen)
+    g_adv = bce(fake, torch.ones_like(fake))
+    g_total = g_loss + g_adv
+    g_total.backward()
+    g_grads = {k: p.grad.detach().clone() for k, p in G.named_parameters() if p.grad is not None}
+    opt_G.step()
+    opt_D.zero_grad()
+    real_validity = D(real_c)
+    fake_validity = D(gen.detach())
+    d_loss = 0.5 * (bce(real_validity, torch.ones_like(real_validity)) + bce(fake_validity, torch.zeros_like(fake_validity)))
+    d_loss.backward()
+    d_grads = {k: p.grad.detach().clone() for k, p in D.named_parameters() if p.grad is not None}
+    opt_D.step()
+    return dict(gen=gen.detach(), g_loss=g_loss.detach(), g_adv=g_adv.detach(), g_total=g_total.detach(),
+                d_loss=d_loss.detach(), g_grads=g_grads, d_grads=d_grads)

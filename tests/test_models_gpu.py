@@ -36,29 +36,42 @@ def rel_l2(a, b, scale=0.0):
     return ((a - b).norm() / max(b.norm().item(), scale * b.numel() ** 0.5, 1e-30)).item()
 
 
-def grad_ok(got, ref32, refq, name="", scale=0.0):
-    """Gradient criterion.
-
-    bf16 storage of z / y flips ReLU gates of elements whose pre-activation is within one bf16 ulp of
-    zero (tools/diag_grad.py shows the largest per-element deviations are exactly those), so the
-    max-norm error of a gradient tensor on small test tiles is dominated by a handful of flipped
-    elements — for ANY bf16 implementation: `floor` below is the same error measured between the fp32
-    oracle and the fp32 oracle with bf16 rounding emulated at the CUDA path's storage points.
-    A tensor passes if its max-norm error vs the fp32 oracle is <= 1e-2 (the north-star bound), or if
-    it is within 1e-2 + 4x the bf16-storage floor in BOTH max-norm and relative L2 norm."""
-    e32, floor, eq = rel_err(got, ref32, scale), rel_err(refq, ref32, scale), rel_err(got, refq, scale)
-    l32, lfloor = rel_l2(got, ref32, scale), rel_l2(refq, ref32, scale)
-    ok = e32 <= TOL or (e32 <= TOL + 4 * floor and l32 <= TOL + 4 * lfloor)
-    if scale > 0.0:
-        # conv bias feeding train-mode BatchNorm: its true gradient is ~0 (BN removes any constant shift; only
-        # the per-pixel mask ratio leaves a residue) and the reference's own value is rounding noise, so it is
-        # only required to stay small relative to the BN-bias gradient of the same layer
-        ok = ok or e32 <= 0.25
-    return ok, (name, round(e32, 4), round(floor, 4), round(eq, 4), "L2", round(l32, 4), round(lfloor, 4))
-
-
 def vgg_seq_state(vgg):
     return {k: v for k, v in vgg.items()}
+
+
+# Sharp criterion (round 2). The bf16 path is compared with the oracle that emulates bf16 rounding at the path's
+# storage points (O.rounding(O.bf16_ste)) AND replays the path's own branch decisions (O.gate_tape: ReLU / LeakyReLU
+# gates, max-pool routing, L1 signs — see the comment at oracle.gate_tape). What is left is backward arithmetic:
+# a dgrad / wgrad / BN-backward / upsample-backward kernel that is wrong by a few per cent fails these bounds.
+REPLAY_MAX, REPLAY_L2 = 1e-2, 6e-3            # single layers: one or two bf16 roundings deep (measured <= 4e-3 / 3e-3)
+STEP_MAX, STEP_L2 = 6e-2, 3e-2                # whole train step: bf16 rounding noise through 15 BN layers + D + VGG
+
+
+def replay_table(got: dict, ref: dict):
+    rows = []
+    for k, g in got.items():
+        if k not in ref:
+            continue
+        comp = _bn_companion(k)
+        scale = ref[comp].abs().max().item() if comp is not None and comp in ref else 0.0
+        rows.append((k, rel_err(g, ref[k], scale), rel_l2(g, ref[k], scale)))
+    rows.sort(key=lambda r: -r[1])
+    return rows
+
+
+def assert_replay(rows, what, n_expected=None, tol_max=REPLAY_MAX, tol_l2=REPLAY_L2):
+    print(what, "vs rounding oracle on the same branch decisions (name, max-norm, rel-L2), worst 5:",
+          [(n, f"{a:.1e}", f"{b:.1e}") for n, a, b in rows[:5]])
+    if n_expected is not None:
+        assert len(rows) == n_expected, (len(rows), n_expected)
+    # a conv bias in front of train-mode BatchNorm has a mathematically ~zero gradient (BN removes any constant shift;
+    # only the per-pixel mask ratio leaves a residue): what is computed is cancellation noise, measured against the
+    # scale of the BN-bias gradient of the same layer (replay_table) and held to 0.1 of it
+    def lim(name):
+        return 0.1 if _bn_companion(name) is not None else tol_max
+    bad = [r for r in rows if r[1] > lim(r[0]) or r[2] > max(tol_l2, lim(r[0]) if _bn_companion(r[0]) else 0)]
+    assert not bad, bad
 
 
 # ---------------------------------------------------------------------------------------------
@@ -103,9 +116,10 @@ def test_generator_forward_parity(kind, mode):
     errs = {n: rel_err(nchw(G._trace[n + ".y"]), trace[n + ".y"]) for n, *_r in O.ENC + O.DEC}
     print(mode, kind, {k: f"{v:.2e}" for k, v in errs.items()}, "out", rel_err(out, ref))
     assert out.shape == ref.shape and out.dtype == torch.float32
-    ok, info = grad_ok(out, ref, refq, "out")
-    print(info)
-    assert ok, info
+    # train-mode BN at batch 2: relative L2 far below 1e-2; the max over 131 k sigmoid outputs sits at the
+    # bf16-storage floor, which the rounding-emulating oracle shows too (printed)
+    print("out: max", rel_err(out, ref), "L2", rel_l2(out, ref), "bf16-storage floor (rounding oracle vs fp32)", rel_err(refq, ref))
+    assert rel_l2(out, ref) < 0.5 * TOL and rel_err(out, ref) < 3 * TOL
     if mode == "eval":
         assert rel_err(out, ref) < TOL
         for n, e in errs.items():
@@ -125,26 +139,29 @@ PCONV_CASES = [(1, 64, 7, 2, 3, 1, 64, "iid"), (64, 128, 5, 2, 2, 2, 16, "rect")
 @pytest.mark.parametrize("case", PCONV_CASES)
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_pconv2d_layer_parity(case, mode):
-    """BASELINE.json config 1 (PConv2d(1,64,7,2,3) fwd+bwd) and the other window shapes, stand-alone."""
+    """BASELINE.json config 1 (PConv2d(1,64,7,2,3) fwd+bwd) and the other window shapes, stand-alone: output within
+    1e-2 of the fp32 oracle, updated mask bit-exact, and dx / dw / db / dgamma / dbeta within (2e-2 max, 1e-2 L2) of
+    the rounding-emulating oracle on the layer's own ReLU gates."""
     cin, cout, k, s, p, B, H, kind = case
     sd = O.make_pconv_state(100, cin, cout, k)
     x = torch.randn((B, cin, H, H), generator=torch.Generator().manual_seed(200))
     mask = O.make_mask(300, B, H, kind)
     names = ["input_conv.weight", "input_conv.bias", "bn.weight", "bn.bias"]
+    gy = None
 
     def run_oracle(xin):
+        nonlocal gy
         osd = {k_: v.clone() for k_, v in sd.items()}
         for n in names:
             osd[n] = osd[n].requires_grad_(True)
         xr = xin.clone().requires_grad_(True)
         y_ref, m_ref = O.pconv2d(xr, mask, osd, "", s, p, mode == "train")
-        gy = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(400))
+        if gy is None:
+            gy = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(400))
         g = torch.autograd.grad(y_ref, [xr] + [osd[n] for n in names], gy)
-        return y_ref.detach(), m_ref, gy, g, osd
+        return y_ref.detach(), m_ref, g, osd
 
-    y_ref, m_ref, gy, g_ref, osd = run_oracle(x)
-    with O.rounding(O.bf16_ste):
-        y_q, _, _, g_q, _ = run_oracle(x.bfloat16().float() if cin > 1 else x)
+    y_ref, m_ref, g_ref, osd = run_oracle(x)
     layer = PConv2d(cin, cout, k, s, p)
     layer.load_state_dict(sd)
     layer.to(DEV).train(mode == "train")
@@ -153,13 +170,18 @@ def test_pconv2d_layer_parity(case, mode):
     assert torch.equal(m.cpu(), m_ref)                                   # updated mask: bit-exact
     assert rel_err(y, y_ref) < TOL
     y.backward(gy.to(DEV))
-    got = [xc.grad, layer.input_conv.weight.grad, layer.input_conv.bias.grad, layer.bn.weight.grad, layer.bn.bias.grad]
-    report = []
-    for gname, a_, r32, rq in zip(["dx", "dw", "db", "dgamma", "dbeta"], got, g_ref, g_q):
-        ok, info = grad_ok(a_, r32, rq, gname)
-        report.append(info)
-        assert ok, info
-    print(case[:5], mode, report)
+    with O.rounding(O.bf16_ste), O.gate_tape({"": (y.detach() > 0).cpu()}) as tape:
+        y_q, _, g_q, _ = run_oracle(x.bfloat16().float() if cin > 1 else x)
+    got = dict(zip(["dx", "dw", "db", "dgamma", "dbeta"],
+                   [xc.grad, layer.input_conv.weight.grad, layer.input_conv.bias.grad, layer.bn.weight.grad, layer.bn.bias.grad]))
+    ref = dict(zip(["dx", "dw", "db", "dgamma", "dbeta"], g_q))
+    rows = []
+    for n in got:
+        scale = ref["dbeta"].abs().max().item() if (n == "db" and mode == "train") else 0.0   # conv bias before train BN: ~0
+        rows.append((n, rel_err(got[n], ref[n], scale), rel_l2(got[n], ref[n], scale)))
+    print(case[:5], mode, tape.report.get(""), [(n, f"{a:.1e}", f"{b:.1e}") for n, a, b in rows])
+    bad = [r for r in rows if r[1] > REPLAY_MAX or r[2] > REPLAY_L2]
+    assert not bad, bad
     if mode == "train":
         assert rel_err(layer.bn.running_var, osd["bn.running_var"]) < TOL
 
@@ -182,28 +204,8 @@ def _bn_companion(k):
     return None
 
 
-def _check_grads(named_params, ref, refq, what=""):
-    rows, bad = [], []
-    for k, p in named_params:
-        if k not in ref:
-            continue
-        assert p.grad is not None, k
-        # a conv bias in front of train-mode BN has (mathematically) zero gradient: measure it against
-        # the scale of the BN bias gradient of the same layer instead of its own ~1e-9 noise
-        scale = 0.0
-        comp = _bn_companion(k)
-        if comp is not None and comp in ref:
-            scale = ref[comp].abs().max().item()
-        ok, info = grad_ok(p.grad, ref[k], refq[k], k, scale)
-        rows.append(info)
-        if not ok:
-            bad.append(info)
-    rows.sort(key=lambda r: -r[1])
-    print(what, "grads (name, max-err vs fp32 oracle, bf16 floor, vs rounding oracle, L2 err, L2 floor), worst 6:", rows[:6])
-    assert not bad, bad
-
-
 def test_discriminator_parity():
+    import gates as GT
     H, B = 128, 2
     img = O.make_tiles(50, B, H)
     d_sd = O.make_discriminator_state(2)
@@ -211,23 +213,27 @@ def test_discriminator_parity():
     D.load_state_dict(O.make_discriminator_state(2))
     D.to(DEV).train()
     osd = O._require_grad(d_sd)
-    xr = img.clone().requires_grad_(True)
-    ref = O.discriminator(xr, osd, True)
+    ref = O.discriminator(img, osd, True).detach()
     g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(51))
     names = O._leaf_params(d_sd)
-    gr = torch.autograd.grad(ref, [xr] + [osd[k] for k in names], g)
-    with O.rounding(O.bf16_ste):
-        osd_q = O._require_grad(O.make_discriminator_state(2))
-        xq = img.clone().requires_grad_(True)
-        gq = torch.autograd.grad(O.discriminator(xq, osd_q, True), [xq] + [osd_q[k] for k in names], g)
+    GT.arm(None, D, None)
     xc = img.to(DEV).requires_grad_(True)
     out = D(xc)
     assert out.shape == ref.shape
     assert rel_err(out, ref) < TOL
     out.backward(g.to(DEV))
-    ok, info = grad_ok(xc.grad, gr[0], gq[0], "d_img")
-    assert ok, info
-    _check_grads(D.named_parameters(), dict(zip(names, gr[1:])), dict(zip(names, gq[1:])), what="D")
+    gates = GT.collect(None, D, None)
+    GT.disarm(None, D, None)
+    with O.rounding(O.bf16_ste), O.gate_tape(gates) as tape:
+        osd_q = O._require_grad(O.make_discriminator_state(2))
+        xq = img.clone().requires_grad_(True)
+        gq = torch.autograd.grad(O.discriminator(xq, osd_q, True), [xq] + [osd_q[k] for k in names], g)
+    print(GT.summarize(tape))
+    got = {k: p.grad for k, p in D.named_parameters()}
+    got["d_img"] = xc.grad
+    ref_q = dict(zip(names, gq[1:]))
+    ref_q["d_img"] = gq[0]
+    assert_replay(replay_table(got, ref_q), "D", 17, STEP_MAX, STEP_L2)
     for bi in (3, 6, 9):
         assert rel_err(D.model[bi].running_var, osd[f"model.{bi}.running_var"]) < TOL
 
@@ -242,91 +248,96 @@ def test_inpainting_loss_parity():
     terms = {}
     ref = O.inpainting_loss(pr, target, mask, vgg, 0.1, 0.1, 0.5, terms)
     (g_ref,) = torch.autograd.grad(ref, pr)
-    with O.rounding(O.bf16_ste):
-        pq = pred.clone().requires_grad_(True)
-        (g_q,) = torch.autograd.grad(O.inpainting_loss(pq, target, mask, vgg, 0.1, 0.1, 0.5), pq)
+    import gates as GT
     crit = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=torch.device(DEV), vgg_state_dict=vgg)
+    GT.arm(None, None, crit)
     pc = pred.to(DEV).requires_grad_(True)
     loss = crit(pc, target.to(DEV), mask.to(DEV))
     loss.backward()
-    print("loss", loss.item(), ref.item(), {k: v.item() for k, v in terms.items()})
+    gates = GT.collect(None, None, crit)
+    GT.disarm(None, None, crit)
+    with O.rounding(O.bf16_ste), O.gate_tape(gates) as tape:
+        pq = pred.clone().requires_grad_(True)
+        (g_q,) = torch.autograd.grad(O.inpainting_loss(pq, target, mask, vgg, 0.1, 0.1, 0.5), pq)
+    print("loss", loss.item(), ref.item(), {k: v.item() for k, v in terms.items()}, GT.summarize(tape))
     assert abs(loss.item() - ref.item()) < TOL * abs(ref.item())
-    ok, info = grad_ok(pc.grad, g_ref, g_q, "d_pred")
-    print(info)
-    assert ok, info
+    e, l2 = rel_err(pc.grad, g_q), rel_l2(pc.grad, g_q)
+    print("d_pred vs rounding oracle on the same branch decisions: max", e, "L2", l2, "| vs plain fp32 oracle L2", rel_l2(pc.grad, g_ref))
+    assert e < STEP_MAX and l2 < STEP_L2
     b = crit.boundary_loss(pc.detach(), target.to(DEV), mask.to(DEV))
     assert abs(b.item() - terms["boundary"].item()) < 1e-5
 
 
-def test_adversarial_step_parity():
-    """One iteration of the reference hot loop (train.py:179-225) with the drop-in modules."""
-    H, B = 256, 2
-    real = O.make_tiles(30, B, H)
-    masks = O.make_mask(31, B, H, "rect")
-    g_sd, d_sd, vgg = O.make_generator_state(1), O.make_discriminator_state(2), O.make_vgg_state(3)
-    r = O.adversarial_step(real, masks, g_sd, d_sd, vgg, lr=2e-4, opt_state={})
-    with O.rounding(O.bf16_ste):
-        rq = O.adversarial_step(real, masks, O.make_generator_state(1), O.make_discriminator_state(2), vgg)
+def _adversarial_case(H, B, kind, seed_t=30, seed_m=31, fp32_grad_report=True):
+    """One iteration of the reference hot loop (train.py:179-225) with the drop-in modules in bf16, against
+    (1) the plain fp32 oracle: outputs, losses, BN statistics (north-star 1e-2 bounds), and
+    (2) the rounding-emulating oracle replaying the path's branch decisions: every gradient, parameters after Adam."""
+    import gates as GT
+    real = O.make_tiles(seed_t, B, H)
+    masks = O.make_mask(seed_m, B, H, kind)
+    vgg = O.make_vgg_state(3)
     G, D, _ = _make_modules()
     criterion = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=torch.device(DEV), vgg_state_dict=vgg)
-    adversarial_loss = torch.nn.BCEWithLogitsLoss()
-    optimizer_G = torch.optim.Adam(G.parameters(), lr=2e-4)
-    optimizer_D = torch.optim.Adam(D.parameters(), lr=2e-4)
-    real_imgs, masks_c = real.to(DEV), masks.to(DEV)
-    # ---- train.py:179-219 ----
-    masked_imgs = real_imgs * masks_c
-    optimizer_G.zero_grad()
-    gen_imgs = G(masked_imgs, masks_c)
-    g_loss = criterion(gen_imgs, real_imgs, masks_c)
-    fake_validity = D(gen_imgs)
-    g_adv_loss = adversarial_loss(fake_validity, torch.ones_like(fake_validity, device=DEV))
-    g_total_loss = g_loss + g_adv_loss
-    g_total_loss.backward()
-    ok, info = grad_ok(gen_imgs, r["gen"], rq["gen"], "gen")
-    print(info, {k_: (v.item(), r[k_].item()) for k_, v in (("g_loss", g_loss), ("g_adv", g_adv_loss))})
-    assert ok, info
-    for got, key in ((g_loss, "g_loss"), (g_adv_loss, "g_adv"), (g_total_loss, "g_total")):
-        assert abs(got.item() - r[key].item()) < TOL * abs(r[key].item()), key
-    _check_grads(G.named_parameters(), r["g_grads"], rq["g_grads"], what="G")
-    optimizer_G.step()
-    optimizer_D.zero_grad()
-    real_validity = D(real_imgs)
-    fake_validity = D(gen_imgs.detach())
-    real_loss = adversarial_loss(real_validity, torch.ones_like(real_validity, device=DEV))
-    fake_loss = adversarial_loss(fake_validity, torch.zeros_like(fake_validity, device=DEV))
-    d_loss = 0.5 * (real_loss + fake_loss)
-    d_loss.backward()
-    assert abs(d_loss.item() - r["d_loss"].item()) < TOL * abs(r["d_loss"].item())
-    _check_grads(D.named_parameters(), r["d_grads"], rq["d_grads"], what="D")
-    optimizer_D.step()
-    # BN running statistics (D's advance three times per step) and parameters after Adam
-    for k, v in G.state_dict().items():
-        if "running_" in k:
-            assert rel_err(v, g_sd[k]) < 2 * TOL, k
-    for k, v in D.state_dict().items():
-        if "running_" in k:
-            assert rel_err(v, d_sd[k]) < 2 * TOL, k
-    # parameters after one Adam step (first step = -lr * g / (|g| + eps): compare the update direction)
-    g0 = O.make_generator_state(1)
-    agree = tot = 0
-    for k, p in G.named_parameters():
-        if p.requires_grad and p.numel() > 1000:
-            du, dr = (p.detach().cpu() - g0[k]), (g_sd[k] - g0[k])
-            agree += int((torch.sign(du) == torch.sign(dr)).sum())
-            tot += du.numel()
-    print("Adam update sign agreement", agree / tot)
-    assert agree / tot > 0.9
+    GT.arm(G, D, criterion)
+    got = GT.run_adversarial(G, D, criterion, real.to(DEV), masks.to(DEV))
+    gates = GT.collect(G, D, criterion)
+    gates["sign.pixel"] = torch.sign(got["gen"].cpu() - real)
+    GT.disarm(G, D, criterion)
+    g_sd, d_sd = O.make_generator_state(1), O.make_discriminator_state(2)
+    r = O.adversarial_step(real, masks, g_sd, d_sd, vgg, lr=2e-4, opt_state={})
+    gq_sd, dq_sd = O.make_generator_state(1), O.make_discriminator_state(2)
+    with O.rounding(O.bf16_ste), O.gate_tape(gates) as tape:
+        rq = O.adversarial_step(real, masks, gq_sd, dq_sd, vgg, lr=2e-4, opt_state={})
+    e_gen, l2_gen = rel_err(got["gen"], r["gen"]), rel_l2(got["gen"], r["gen"])
+    print(f"{H}x{H} B={B} {kind}: gen vs fp32 oracle max {e_gen:.2e} L2 {l2_gen:.2e}, vs rounding oracle "
+          f"{rel_err(got['gen'], rq['gen']):.2e};", GT.summarize(tape))
+    # (1) fp32 oracle: the north-star bf16 bound. Train-mode BN output: L2 far below it; the max-norm over 0.5-2 M
+    # sigmoid outputs sits at the bf16-storage floor (the reference's own modules under bf16 autocast differ from
+    # fp32 by 1.06e-2 in train mode, BASELINE.md §2)
+    assert l2_gen < 0.5 * TOL
+    assert e_gen < 3 * TOL
+    for key in ("g_loss", "g_adv", "g_total", "d_loss"):
+        assert abs(got[key].item() - r[key].item()) < TOL * abs(r[key].item()), key
+    for sd_ref, mod in ((g_sd, G), (d_sd, D)):
+        for k, v in mod.state_dict().items():
+            if "running_" in k:
+                assert rel_err(v, sd_ref[k]) < 2 * TOL, k
+    # (2) every gradient, sharp
+    assert rel_l2(got["gen"], rq["gen"]) < 0.5 * TOL
+    assert_replay(replay_table(got["g_grads"], rq["g_grads"]), f"G {H}x{H}", 58, STEP_MAX, STEP_L2)
+    assert_replay(replay_table(got["d_grads"], rq["d_grads"]), f"D {H}x{H}", 16, STEP_MAX, STEP_L2)
+    if fp32_grad_report:
+        rows = replay_table(got["g_grads"], r["g_grads"])
+        print("  (for the record) vs the plain fp32 oracle, own branch decisions, worst 4:",
+              [(n, f"{a:.1e}", f"{b:.1e}") for n, a, b in rows[:4]])
+    # parameters after one Adam step (~ -lr * sign(g) on the first step): where the gradient is clearly non-zero the
+    # update must agree to a few per cent of lr
+    worst = 0.0
+    for k, p in list(G.named_parameters()) + list(D.named_parameters()):
+        ref_g = rq["g_grads"].get(k, rq["d_grads"].get(k))
+        ref_p = gq_sd.get(k, dq_sd.get(k))
+        if ref_g is None or not p.requires_grad:
+            continue
+        gr = ref_g.abs()
+        big = (gr > 0.1 * gr.max()) & (gr > 1e-6)
+        if big.any():
+            worst = max(worst, ((p.detach().cpu() - ref_p).abs()[big].max() / 2e-4).item())
+    print("  Adam: worst parameter deviation in units of lr:", worst)
+    assert worst < 0.05
+
+
+def test_adversarial_step_parity():
+    _adversarial_case(256, 2, "rect")
 
 
 def test_human_guided_step_parity():
+    """human_guided_trainer.py:101-153: G -> HumanGuidedLoss (0.7 / 0.3, boundary 0.5) -> backward -> Adam(1e-4)."""
+    import gates as GT
     H, B = 256, 2
     images = O.make_tiles(40, B, H)
     masks = O.make_mask(41, B, H, "large")
     human = 1 - O.make_mask(42, B, H, "rect")
-    g_sd, vgg = O.make_generator_state(1), O.make_vgg_state(3)
-    r = O.human_guided_step(images, masks, human, g_sd, vgg, lr=1e-4, opt_state={})
-    with O.rounding(O.bf16_ste):
-        rq = O.human_guided_step(images, masks, human, O.make_generator_state(1), vgg)
+    vgg = O.make_vgg_state(3)
     G, _, _ = _make_modules()
     config = {"training": {"loss_weights": {"perceptual": 0.1, "tv": 0.1, "boundary": 0.5},
                            "modes": {"human_guided": {"human_feedback_weight": 0.3, "base_loss_weight": 0.7,
@@ -334,16 +345,24 @@ def test_human_guided_step_parity():
     criterion = HumanGuidedLoss(config, device=torch.device(DEV), vgg_state_dict=vgg)
     optimizer = torch.optim.Adam(G.parameters(), lr=1e-4)
     ic, mc, hc = images.to(DEV), masks.to(DEV), human.to(DEV)
+    GT.arm(G, None, criterion)
     generated = G(ic * mc, mc)
     loss = criterion(generated, ic, mc, {"mask": hc})
     optimizer.zero_grad()
     loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in G.named_parameters() if p.grad is not None}
     optimizer.step()
-    ok, info = grad_ok(generated, r["gen"], rq["gen"], "gen")
-    print(info, loss.item(), r["loss"].item())
-    assert ok, info
+    gates = GT.collect(G, None, criterion)
+    gates["sign.pixel"] = torch.sign(generated.detach().cpu() - images)
+    GT.disarm(G, None, criterion)
+    r = O.human_guided_step(images, masks, human, O.make_generator_state(1), vgg, lr=1e-4, opt_state={})
+    with O.rounding(O.bf16_ste), O.gate_tape(gates) as tape:
+        rq = O.human_guided_step(images, masks, human, O.make_generator_state(1), vgg)
+    print("H-G: gen vs fp32 oracle", rel_err(generated, r["gen"]), "L2", rel_l2(generated, r["gen"]), GT.summarize(tape))
+    assert rel_l2(generated, r["gen"]) < 0.5 * TOL
+    assert rel_err(generated, r["gen"]) < 3 * TOL
     assert abs(loss.item() - r["loss"].item()) < TOL * abs(r["loss"].item())
-    _check_grads(G.named_parameters(), r["g_grads"], rq["g_grads"], what="G(hg)")
+    assert_replay(replay_table(grads, rq["g_grads"]), "G (H-G step)", 58, STEP_MAX, STEP_L2)
 
 
 def _smooth(sd, shift):
@@ -370,27 +389,30 @@ def test_generator_gradients_smooth_regime(mode):
         l = ((o - target) ** 2).mean()
         return o.detach(), l.detach(), dict(zip(names, torch.autograd.grad(l, [sd[k] for k in names])))
 
+    import gates as GT
     out_ref, loss_ref, g_ref = run_oracle()
-    with O.rounding(O.bf16_ste):
-        _, _, g_q = run_oracle()
     G = PConvUNet()
     G.load_state_dict(_smooth(O.make_generator_state(1), 3.0))
     G.to(DEV).train(mode == "train")
+    GT.arm(G)
     out = G((x * mask).to(DEV), mask.to(DEV))
     loss = ((out - target.to(DEV)) ** 2).mean()
     loss.backward()
+    gates = GT.collect(G)
+    GT.disarm(G)
     assert rel_err(out, out_ref) < TOL
     assert abs(loss.item() - loss_ref.item()) < TOL * abs(loss_ref.item())
-    rows = []
-    for k, p in G.named_parameters():
-        if k in g_ref:
-            comp = _bn_companion(k)
-            scale = g_ref[comp].abs().max().item() if (comp in g_ref and mode == "train") else 0.0
-            ok, info = grad_ok(p.grad, g_ref[k], g_q[k], k, scale)
-            rows.append(info + (ok,))
-    rows.sort(key=lambda r: -r[1])
-    print(mode, "grads (name, max-err vs fp32 oracle, bf16 floor, vs rounding oracle, L2 err, L2 floor), worst 8:", rows[:8])
-    assert all(r[-1] for r in rows), [r for r in rows if not r[-1]]
+    # most gates are wide open (a +3 shift leaves ~1e-3 of them closed): the gradient flows through every element of
+    # every layer; the few gate decisions are replayed like everywhere else
+    with O.rounding(O.bf16_ste), O.gate_tape(gates) as tape:
+        _, _, g_q = run_oracle()
+    print(GT.summarize(tape))
+    got = {k: p.grad for k, p in G.named_parameters() if p.grad is not None}
+    if mode == "eval":       # a conv bias feeds an affine BN: no near-zero gradient to floor
+        rows = sorted(((k, rel_err(g, g_q[k]), rel_l2(g, g_q[k])) for k, g in got.items()), key=lambda r: -r[1])
+    else:
+        rows = replay_table(got, g_q)
+    assert_replay(rows, f"G smooth regime ({mode})", 58, STEP_MAX, STEP_L2)
 
 
 def test_discriminator_gradients_smooth_regime():
@@ -403,22 +425,28 @@ def test_discriminator_gradients_smooth_regime():
     g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(51))
     names = O._leaf_params(d_sd)
     gr = torch.autograd.grad(ref, [xr] + [osd[k] for k in names], g)
+    import gates as GT
     D = Discriminator()
     D.load_state_dict(_smooth(O.make_discriminator_state(2), 3.0))
     D.to(DEV).train()
+    GT.arm(None, D, None)
     xc = img.to(DEV).requires_grad_(True)
     out = D(xc)
     out.backward(g.to(DEV))
+    gates = GT.collect(None, D, None)
+    GT.disarm(None, D, None)
     assert rel_err(out, ref) < TOL
-    ref_g = dict(zip(names, gr[1:]))
-    rows = [("d_img", round(rel_err(xc.grad, gr[0]), 4))]
-    for k, p in D.named_parameters():
-        comp = _bn_companion(k)
-        scale = ref_g[comp].abs().max().item() if comp in ref_g else 0.0
-        rows.append((k, round(rel_err(p.grad, ref_g[k], scale), 4)))
-    rows.sort(key=lambda r: -r[1])
-    print("D smooth-regime grads, worst 8:", rows[:8])
-    assert rows[0][1] < 0.15, rows[:6]      # gate flips at |pre| < 1 bf16 ulp dominate (see grad_ok)
+    # BN shifts of +3 keep the three BN-fed LeakyReLUs open; model[0]'s LeakyReLU (no BN) still gates, so the
+    # path's decisions are replayed
+    with O.rounding(O.bf16_ste), O.gate_tape(gates):
+        osd_q = O._require_grad(_smooth(O.make_discriminator_state(2), 3.0))
+        xq = img.clone().requires_grad_(True)
+        gq = torch.autograd.grad(O.discriminator(xq, osd_q, True), [xq] + [osd_q[k] for k in names], g)
+    got = {k: p.grad for k, p in D.named_parameters()}
+    got["d_img"] = xc.grad
+    ref_q = dict(zip(names, gq[1:]))
+    ref_q["d_img"] = gq[0]
+    assert_replay(replay_table(got, ref_q), "D smooth regime", 17, STEP_MAX, STEP_L2)
 
 
 def test_no_cpu_fallback():
@@ -469,35 +497,14 @@ def test_train_step_odd_batch_nonsquare():
 
 
 def test_adversarial_step_full_size_tiles():
-    """The real tile shape (1x512x512, train.py:68) at batch 2: generator output and every loss term of the
-    adversarial step within 1e-2 of the fp32 oracle; gradients by the bf16-floor criterion (grad_ok)."""
-    H, B = 512, 2
-    real = O.make_tiles(30, B, H)
-    masks = O.make_mask(31, B, H, "rect")
-    vgg = O.make_vgg_state(3)
-    r = O.adversarial_step(real, masks, O.make_generator_state(1), O.make_discriminator_state(2), vgg)
-    with O.rounding(O.bf16_ste):
-        rq = O.adversarial_step(real, masks, O.make_generator_state(1), O.make_discriminator_state(2), vgg)
-    G, D, _ = _make_modules()
-    criterion = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=torch.device(DEV), vgg_state_dict=vgg)
-    bce = torch.nn.BCEWithLogitsLoss()
-    real_c, masks_c = real.to(DEV), masks.to(DEV)
-    gen = G(real_c * masks_c, masks_c)
-    g_loss = criterion(gen, real_c, masks_c)
-    fake = D(gen)
-    g_adv = bce(fake, torch.ones_like(fake))
-    (g_loss + g_adv).backward()
-    ok, info = grad_ok(gen, r["gen"], rq["gen"], "gen")
-    l2 = rel_l2(gen, r["gen"])
-    print("512x512 gen (max-err vs fp32 oracle, bf16 floor, vs rounding oracle):", info, "rel-L2", l2,
-          "g_loss", g_loss.item(), r["g_loss"].item(), "g_adv", g_adv.item(), r["g_adv"].item())
-    # train-mode BatchNorm in bf16: the reference's own modules under bf16 autocast differ from fp32 by 1.06e-2
-    # (SURVEY.md / BASELINE.md); the max-norm is met up to the bf16-storage floor, the L2 error is far below 1e-2
-    assert ok, info
-    assert l2 < TOL
-    assert abs(g_loss.item() - r["g_loss"].item()) < TOL * abs(r["g_loss"].item())
-    assert abs(g_adv.item() - r["g_adv"].item()) < TOL * abs(r["g_adv"].item())
-    _check_grads(G.named_parameters(), r["g_grads"], rq["g_grads"], what="G 512x512")
+    """The real tile shape (1x512x512, train.py:68) at batch 2."""
+    _adversarial_case(512, 2, "rect")
+
+
+def test_adversarial_step_well_sampled_large_masks():
+    """Batch 8 of 512x512 tiles with structured `large` hole masks (50-80 % hole, so that holes survive to enc6/enc7
+    and every mask-dependent path of the deep layers is live) — the well-sampled case."""
+    _adversarial_case(512, 8, "large", fp32_grad_report=False)
 
 
 @pytest.mark.gpu

@@ -53,14 +53,12 @@ def _w(mode, w, plan=None):
 # kernel level
 # ---------------------------------------------------------------------------------------------------------------
 FPROP = [(64, 64, 3, 1, 1, 32, 2), (192, 64, 3, 1, 1, 16, 2), (1024, 512, 3, 1, 1, 8, 3), (64, 128, 5, 2, 2, 32, 2),
-         (256, 512, 3, 2, 1, 16, 2), (512, 512, 3, 2, 1, 2, 5), (64, 128, 4, 2, 1, 32, 2), (32, 96, 3, 1, 1, 16, 1)]
+         (256, 512, 3, 2, 1, 16, 2), (512, 512, 3, 2, 1, 2, 5), (64, 128, 4, 2, 1, 32, 2), (32, 128, 3, 1, 1, 16, 1)]
 
 
 @pytest.mark.parametrize("mode,tol", [("tf32", 2e-3), ("tf32x3", 1e-4)])
 @pytest.mark.parametrize("Cin,Cout,k,s,p,H,B", FPROP)
 def test_fprop_f32(mode, tol, Cin, Cout, k, s, p, H, B):
-    if Cout % 64:
-        pytest.skip("N must be a multiple of 64")
     torch.manual_seed(0)
     x = torch.randn(B, Cin, H, H, device=DEV)
     w = torch.randn(Cout, Cin, k, k, device=DEV) / (Cin * k * k) ** 0.5
@@ -281,24 +279,8 @@ def _modules():
 
 
 def _run_adversarial(G, D, criterion, real_c, masks_c, lr=2e-4):
-    """train.py:179-219 with the drop-in modules; returns tensors and gradient snapshots."""
-    bce = torch.nn.BCEWithLogitsLoss()
-    opt_G, opt_D = torch.optim.Adam(G.parameters(), lr=lr), torch.optim.Adam(D.parameters(), lr=lr)
-    opt_G.zero_grad()
-    gen = G(real_c * masks_c, masks_c)
-    g_loss = criterion(gen, real_c, masks_c)
-    fake = D(gen)
-    g_adv = bce(fake, torch.ones_like(fake))
-    (g_loss + g_adv).backward()
-    g_grads = {k: p.grad.detach().clone() for k, p in G.named_parameters() if p.grad is not None}
-    opt_G.step()
-    opt_D.zero_grad()
-    d_loss = 0.5 * (bce(D(real_c), torch.ones_like(fake)) + bce(D(gen.detach()), torch.zeros_like(fake)))
-    d_loss.backward()
-    d_grads = {k: p.grad.detach().clone() for k, p in D.named_parameters() if p.grad is not None}
-    opt_D.step()
-    return dict(gen=gen.detach(), g_loss=g_loss.detach(), g_adv=g_adv.detach(), d_loss=d_loss.detach(), g_grads=g_grads,
-                d_grads=d_grads)
+    import gates as GT
+    return GT.run_adversarial(G, D, criterion, real_c, masks_c, lr)
 
 
 def _table(got: dict, ref: dict):
