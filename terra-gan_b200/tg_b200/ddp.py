@@ -94,7 +94,10 @@ class BucketedGradReducer:
         inv = 1.0 / self.world
 
         def scatter_back():
+            # one multi-tensor copy (and one add for parameters that received several contributions) per step
+            # instead of one tiny kernel per parameter: round 1 spent ~78 launches on the comm stream here
             seen = set()
+            copy_dst, copy_src, add_dst, add_src = [], [], [], []
             for work, flat, keys, sizes, _src in inflight:
                 work.wait()
                 flat.mul_(inv)
@@ -106,11 +109,17 @@ class BucketedGradReducer:
                                            "after backward() and before optimizer.step()")
                     src = flat[off:off + n].view_as(p.grad)
                     if (id(module), name) in seen:
-                        p.grad.add_(src)
+                        add_dst.append(p.grad)
+                        add_src.append(src)
                     else:
-                        p.grad.copy_(src)
+                        copy_dst.append(p.grad)
+                        copy_src.append(src)
                         seen.add((id(module), name))
                     off += n
+            if copy_dst:
+                torch._foreach_copy_(copy_dst, copy_src)
+            if add_dst:
+                torch._foreach_add_(add_dst, add_src)
 
         if cuda:
             after_bwd = torch.cuda.Event()
