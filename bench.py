@@ -36,7 +36,10 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 GFLOP_PER_TILE_STEP = 690.163          # algorithmic work of one adversarial step per tile
-GFLOP_PER_TILE = {"train": 690.163, "infer": 93.634, "hg": 573.118}
+# train: 690.163 GF per tile as the reference graph computes it; 13.035 GF of that is the D weight gradient of the
+# generator step, which train.py:210 zeroes unused and this path skips by default (--ref-graph computes it): 677.128
+GFLOP_PER_TILE = {"train": 690.163, "train_skip_d_wgrad": 677.128, "infer": 93.634, "hg": 573.118}
+PCONV_GFLOP_PER_TILE = {"train": 280.490, "hg": 280.490, "infer": 93.634}   # the 14 PConv layers + final conv
 TILE = 512
 METRIC = "gan_train_step_dsm_tiles_per_sec"
 METRICS = {"train": METRIC, "infer": "generator_inference_dsm_tiles_per_sec", "hg": "hg_finetune_step_dsm_tiles_per_sec"}
@@ -46,8 +49,71 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1383.8), d.get("hbm_gbs", 6551.4), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return d.get("bf16_tflops_sustained", 1383.8), d.get("hbm_gbs", 6551.4), "measured", d.get("bf16_tflops", 1632.5)
+    return 1400.0, 6650.0, "fallback", 1650.0
+
+
+def make_masks(kind: str, B: int, gen: "torch.Generator"):
+    """Synthetic hole masks (1 = valid), SURVEY.md §8d. rect: 1-4 axis-aligned holes of side 32-256 px (M_rect).
+    large: union of big rectangles and blobs to 50-80 % hole so that holes survive to enc6 / enc7 (M_large, the
+    "large-mask irregular holes at high mask density" of BASELINE.json configs[4])."""
+    m = torch.ones(B, 1, TILE, TILE)
+    if kind == "rect":
+        for b in range(B):
+            for _ in range(int(torch.randint(1, 5, (1,), generator=gen))):
+                hh, ww = (int(torch.randint(32, 257, (1,), generator=gen)) for _ in range(2))
+                y0 = int(torch.randint(0, TILE - hh + 1, (1,), generator=gen))
+                x0 = int(torch.randint(0, TILE - ww + 1, (1,), generator=gen))
+                m[b, 0, y0:y0 + hh, x0:x0 + ww] = 0
+        return m
+    for b in range(B):
+        target = 0.5 + 0.3 * float(torch.rand((1,), generator=gen))
+        # irregular blobs: threshold a smooth random field (low-resolution noise, bilinearly up-sampled) ...
+        field = torch.nn.functional.interpolate(torch.rand((1, 1, 16, 16), generator=gen), size=(TILE, TILE),
+                                                mode="bicubic", align_corners=False)[0, 0]
+        thr = torch.quantile(field.flatten(), target * 0.8)
+        m[b, 0][field < thr] = 0
+        # ... plus rectangles until the target hole density is reached
+        while float(1 - m[b].mean()) < target:
+            hh, ww = (int(torch.randint(64, 257, (1,), generator=gen)) for _ in range(2))
+            y0 = int(torch.randint(0, TILE - hh + 1, (1,), generator=gen))
+            x0 = int(torch.randint(0, TILE - ww + 1, (1,), generator=gen))
+            m[b, 0, y0:y0 + hh, x0:x0 + ww] = 0
+    return m
+
+
+def stock_torch_gpu_baseline(dev, batch: int, steps: int):
+    """Informational bar (SURVEY.md §2.2 / BASELINE.md §4): the reference's own ATen ops on this GPU, i.e. what
+    stock PyTorch + cuDNN does with the unmodified algorithm — the oracle port with every tensor on the device, in
+    fp32 and with TF32 convolutions allowed. (/root/reference does not exist on the GPU box; the port is verified
+    bit-identical to the reference modules on CPU by tests/test_oracle_golden.py.)"""
+    from oracle import terra_oracle as O
+    to = lambda sd: {k: v.to(dev) for k, v in sd.items()}
+    out = {}
+    real, masks = O.make_tiles(5, batch, TILE).to(dev), O.make_mask(6, batch, TILE, "rect").to(dev)
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        g_sd, d_sd, vgg, opt = to(O.make_generator_state(1)), to(O.make_discriminator_state(2)), to(O.make_vgg_state(3)), {}
+        try:
+            for _ in range(2):
+                O.adversarial_step(real, masks, g_sd, d_sd, vgg, lr=2e-4, opt_state=opt)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                O.adversarial_step(real, masks, g_sd, d_sd, vgg, lr=2e-4, opt_state=opt)
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = batch / (e0.elapsed_time(e1) / steps * 1e-3)
+        except Exception as exc:          # never let the informational leg take the bench line down
+            out[name] = f"failed: {type(exc).__name__}: {exc}"[:200]
+        del g_sd, d_sd, vgg, opt
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = True
+    return {"unit": "tiles/s", "batch": batch, "steps": steps, "tiles_per_s": out,
+            "what": "oracle port of train.py:179-225 (the reference's own ATen ops, torch.autograd, cuDNN/cuBLAS) on this "
+                    "GPU; informational, not the reference arm"}
 
 
 class ClockSampler:
@@ -154,7 +220,14 @@ def run_ours(args):
     from mvp_gan.src.models.discriminator import Discriminator
     from mvp_gan.src.utils.losses import InpaintingLoss
 
-    B = args.batch
+    if args.global_batch:
+        if args.global_batch % world:
+            raise RuntimeError(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        B = args.global_batch // world          # strong scaling (configs[4]) / fixed global batch (configs[3])
+    else:
+        B = args.batch
+    scaling = "strong" if args.global_batch else "weak"
+    mask_kind = args.masks or ("large" if args.workload == "hg" else "rect")
     torch.manual_seed(1)                               # random-init weights (default PyTorch init), same on every rank
     G, D = PConvUNet(), Discriminator()
     G.to(dev).train()
@@ -188,14 +261,8 @@ def run_ours(args):
     # synthetic DSM tiles + rectangular hole masks, a different shard per rank; pinned host copies for e2e
     gen = torch.Generator().manual_seed(1234 + rank)
     real_h = torch.rand((B, 1, TILE, TILE), generator=gen).pin_memory()
-    mask_h = torch.ones(B, 1, TILE, TILE)
-    for b in range(B):
-        for _ in range(int(torch.randint(1, 5, (1,), generator=gen))):
-            hh, ww = (int(torch.randint(32, 257, (1,), generator=gen)) for _ in range(2))
-            y0 = int(torch.randint(0, TILE - hh + 1, (1,), generator=gen))
-            x0 = int(torch.randint(0, TILE - ww + 1, (1,), generator=gen))
-            mask_h[b, 0, y0:y0 + hh, x0:x0 + ww] = 0
-    mask_h = mask_h.pin_memory()
+    mask_h = make_masks(mask_kind, B, gen).pin_memory()
+    human_h = (1 - make_masks("rect", B, gen)).pin_memory()      # human-flagged regions (1 = flagged), configs[4]
     real_d, mask_d = real_h.to(dev), mask_h.to(dev)
 
     def barrier():
@@ -218,31 +285,65 @@ def run_ours(args):
             ms = float(t.item())
         return ms / steps
 
-    human_d = (torch.rand((B, 1, TILE, TILE), generator=gen) < 0.1).float().to(dev)
+    human_d = human_h.to(dev)
+    graphed = None
+    if args.workload == "infer" and not args.no_graph:
+        from tg_b200.graphs import GraphedGenerator
+        graphed = GraphedGenerator(G, B, TILE, TILE)     # one cudaGraphLaunch per forward (small batches are launch-bound)
 
-    def run_step(r, m):
+    def run_step(r, m, h=None):
         if args.workload == "infer":
-            with torch.no_grad():
-                out = G(r * m, m)
-            return {"g_total_loss": out.mean(), "d_loss": out.mean()}
+            if graphed is not None:
+                out = graphed(r * m, m)
+            else:
+                with torch.no_grad():
+                    out = G(r * m, m)
+            return {"g_total_loss": out.mean(), "d_loss": out.mean(), "out": out}
         if args.workload == "hg":
-            o = hg_stepper.run(r, m, human_d)
+            o = hg_stepper.run(r, m, human_d if h is None else h)
             return {"g_total_loss": o["loss"], "d_loss": o["loss"]}
         return stepper.run(r, m)
 
     def step_resident():
         run_step(real_d, mask_d)
 
+    # ---- end to end: every step's inputs come from pinned host memory. Like a DataLoader(pin_memory=True) feeding
+    # `.to(device, non_blocking=True)`, the copy of step i+1 is issued on a copy stream while step i computes; the
+    # compute stream waits for its own batch's copy event. Results are read back every step: the two loss scalars
+    # (train.py:222-225) for the training workloads, the inpainted tiles (evaluate.py:53) for inference.
+    copy_stream = torch.cuda.Stream()
+    n_in = 3 if args.workload == "hg" else 2
+    host_in = [real_h, mask_h, human_h][:n_in]
+    bufs = [[torch.empty_like(t, device=dev) for t in host_in] for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"i": 0}
     loss_host = torch.empty(2, pin_memory=True)
+    out_host = torch.empty((B, 1, TILE, TILE), pin_memory=True) if args.workload == "infer" else None
+
+    def prefetch(slot):
+        copy_stream.wait_event(consumed[slot])           # the previous user of this slot is done with it
+        with torch.cuda.stream(copy_stream):
+            for dst, src in zip(bufs[slot], host_in):
+                dst.copy_(src, non_blocking=True)
+            ready[slot].record()
 
     def step_e2e():
-        r = real_h.to(dev, non_blocking=True)
-        m = mask_h.to(dev, non_blocking=True)
-        out = run_step(r, m)
-        loss_host.copy_(torch.stack([out["g_total_loss"], out["d_loss"]]), non_blocking=True)
-        torch.cuda.current_stream().synchronize()     # the user reads the losses every step (train.py:222-225)
+        slot = state["i"] & 1
+        if state["i"] == 0:
+            prefetch(0)
+        prefetch(slot ^ 1)                               # next step's inputs travel while this step computes
+        torch.cuda.current_stream().wait_event(ready[slot])
+        out = run_step(*bufs[slot])
+        consumed[slot].record()
+        if out_host is not None:
+            out_host.copy_(out["out"], non_blocking=True)
+        else:
+            loss_host.copy_(torch.stack([out["g_total_loss"], out["d_loss"]]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the caller reads the result of every step
+        state["i"] += 1
 
-    ops.profile_pool(2 * 100 * args.steps + 64)      # timing events for every tensor-core launch of the timed steps
+    ops.profile_pool(2 * 130 * args.steps + 64)      # timing events for every tensor-core launch of the timed steps
     for _ in range(args.warmup):
         step_resident()
     # ---- timed region 1: resident inputs; tensor-core launches timed with CUDA events ----
@@ -250,8 +351,20 @@ def run_ours(args):
     sampler.start()
     _lib.CALLS.clear()
     ops.PROFILE = []
-    ms_step = timed(step_resident, args.steps)
-    prof, ops.PROFILE = ops.PROFILE, None
+    if graphed is not None:
+        ms_step = timed(step_resident, args.steps)      # replayed graph: launches are not individually timed
+        prof = []
+        ops.PROFILE = None
+        with torch.no_grad():                            # per-launch profile + launch count from one eager forward each
+            ops.PROFILE = []
+            _lib.CALLS.clear()
+            for _ in range(args.steps):
+                G(real_d * mask_d, mask_d)
+            torch.cuda.synchronize()
+            prof, ops.PROFILE = ops.PROFILE, None
+    else:
+        ms_step = timed(step_resident, args.steps)
+        prof, ops.PROFILE = ops.PROFILE, None
     launches = _lib.kernel_launches()
     calls = dict(_lib.CALLS)
     # ---- timed region 2: end to end from host buffers ----
@@ -263,27 +376,44 @@ def run_ours(args):
     if args.per_launch and rank == 0:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", args.per_launch), "w") as f:
-            for kind, flops, a, b, shape in prof[: len(prof) // max(args.steps, 1)]:
+            for kind, flops, a, b, shape, tag in prof[: len(prof) // max(args.steps, 1)]:
                 ms = a.elapsed_time(b)
-                f.write(f"{kind:6s} {ms*1e3:9.1f} us {flops/ms/1e9:8.1f} TFLOP/s  {flops/1e9:9.1f} GF  {shape}\n")
-    for kind, flops, a, b, _shape in prof:
+                f.write(f"{tag:3s} {kind:10s} {ms*1e3:9.1f} us {flops/ms/1e9:8.1f} TFLOP/s  {flops/1e9:9.1f} GF  {shape}\n")
+    pconv = {}                                           # the generator's 14 PConv layers + final conv, incl. enc1 / final
+    for kind, flops, a, b, _shape, tag in prof:
+        ms = a.elapsed_time(b)
+        if tag == "G":
+            t = pconv.setdefault(kind, [0.0, 0.0, 0])
+            t[0] += flops
+            t[1] += ms
+            t[2] += 1
+        if kind.startswith("thin_"):
+            continue                                     # bandwidth-bound 1<->64-channel convs: not part of the GEMM family
         t = tc.setdefault(kind, [0.0, 0.0, 0])
         t[0] += flops
-        t[1] += a.elapsed_time(b)
+        t[1] += ms
         t[2] += 1
     tc_flops = sum(v[0] for v in tc.values())
     tc_ms = sum(v[1] for v in tc.values())
-    peak_tf, peak_bw, peak_src = load_peaks()
+    peak_tf, peak_bw, peak_src, peak_burst = load_peaks()
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    pc_flops = sum(v[0] for v in pconv.values())
+    pc_ms = sum(v[1] for v in pconv.values())
+    pc_tf = pc_flops / (pc_ms * 1e-3) / 1e12 if pc_ms > 0 else 0.0
+    pc_gemm = {k: v for k, v in pconv.items() if not k.startswith("thin_")}
+    pcg_flops, pcg_ms = sum(v[0] for v in pc_gemm.values()), sum(v[1] for v in pc_gemm.values())
+    pcg_tf = pcg_flops / (pcg_ms * 1e-3) / 1e12 if pcg_ms > 0 else 0.0
 
     # DRAM traffic of the same kernel family from the committed ncu --set full capture (one B=64 train step)
     traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_tensorcore_step_summary.json")
-    if os.path.exists(tpath) and B == 64 and args.workload == "train":
-        t = json.load(open(tpath))
-        traffic = t["dram_gbytes"] * 1e9 / t["launches"]
-        traffic_note = (f"dram__bytes_read+write: {t['dram_gbytes']:.1f} GB over the {t['launches']} tensor-core launches of one "
-                        f"B=64 step (profiles/r01_ncu_tensorcore_step_metrics.csv); bytes per launch (mean)")
+    for tname in ("r02_ncu_tensorcore_step_summary.json", "r01_ncu_tensorcore_step_summary.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath) and B == 64 and args.workload == "train":
+            t = json.load(open(tpath))
+            traffic = t["dram_gbytes"] * 1e9 / t["launches"]
+            traffic_note = (f"dram__bytes_read+write: {t['dram_gbytes']:.1f} GB over the {t['launches']} tensor-core launches of "
+                            f"one B=64 step (ncu --set full capture summarised in profiles/{tname}); bytes per launch (mean)")
+            break
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -292,30 +422,40 @@ def run_ours(args):
     value = tiles_per_step / (ms_step * 1e-3)
     e2e = tiles_per_step / (ms_e2e * 1e-3)
     cpu = None
+    stock = None
     if world == 1 and not args.no_cpu_baseline:
+        if args.workload == "train":
+            stock = stock_torch_gpu_baseline(dev, 16, 3)
         dt, threads = cpu_reference_step_time(4, 4, 1)
         cpu = {"value": 4 / dt, "unit": "tiles/s", "cores": threads, "kind": "port",
                "sample": "1 warm-up + 4 timed adversarial steps at batch 4 (oracle/terra_oracle.py: the reference's "
                          "own ATen/oneDNN ops, fp32, all host threads)"}
+    wl_key = "train_skip_d_wgrad" if (args.workload == "train" and not args.ref_graph) else args.workload
+    step_gf = GFLOP_PER_TILE[wl_key]
     line = {
         "metric": METRICS[args.workload], "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": {"train": "adversarial train step (train.py:179-225): PConvUNet + Discriminator + "
                                          "InpaintingLoss (perceptual 0.1, tv 0.1, boundary 0.5) + Adam x2, 1x512x512 DSM "
-                                         "tiles, rect hole masks",
-                                "infer": "generator inference, eval mode, no_grad (evaluate.py:47-50), 1x512x512 DSM tiles",
+                                         "tiles",
+                                "infer": "generator inference, eval mode, no_grad (evaluate.py:47-50), 1x512x512 DSM tiles"
+                                         + ("" if args.no_graph else ", one CUDA-graph launch per forward"),
                                 "hg": "human-guided fine-tune step (human_guided_trainer.py:101-153): PConvUNet + "
-                                      "HumanGuidedLoss (0.7/0.3, boundary 0.5) + Adam 1e-4, 1x512x512 DSM tiles"}[args.workload],
+                                      "HumanGuidedLoss (0.7/0.3, boundary 0.5, human masks) + Adam 1e-4, 1x512x512 DSM "
+                                      "tiles"}[args.workload],
+                   "masks": {"rect": "M_rect: 1-4 rectangular holes of side 32-256 px",
+                             "large": "M_large: irregular blobs + rectangles, 50-80 % hole"}[mask_kind],
                    "tile": TILE, "batch_per_gpu": B, "global_batch": tiles_per_step,
                    "parallelism": f"dp{world}", "l2": "working set per step (>10 GB) exceeds the 126 MB L2",
                    "d_wgrad_in_g_step": "computed (reference graph)" if args.ref_graph else
                                         "skipped (zeroed unused by train.py:210; output-equivalent)",
-                   "step_gflop_per_tile": GFLOP_PER_TILE[args.workload],
-                   "step_frac_of_bf16_peak": value / world * GFLOP_PER_TILE[args.workload] * 1e9 / (peak_tf * 1e12)},
+                   "step_gflop_per_tile": step_gf,
+                   "step_frac_of_bf16_peak": value / world * step_gf * 1e9 / (peak_tf * 1e12)},
         "e2e": {"value": e2e, "unit": "tiles/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(real_h.numel() * 4 + mask_h.numel() * 4) * world,
-                "d2h_bytes_per_step": 8 * world},
+                "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host_in)) * world,
+                "d2h_bytes_per_step": (int(out_host.numel() * 4) if out_host is not None else 8) * world,
+                "input_pipeline": "double-buffered: step i+1's pinned-host -> device copy runs on a copy stream during step i"},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel + wgrad_igemm_kernel (tcgen05 implicit GEMM)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
@@ -324,8 +464,24 @@ def run_ours(args):
                      "share_of_step": tc_ms / (ms_step * args.steps) if ms_step > 0 else None,
                      "by_kind": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0,
                                      "ms_per_step": v[1] / args.steps, "launches_per_step": v[2] / args.steps}
-                                 for k, v in tc.items()}},
+                                 for k, v in tc.items()},
+                     # BASELINE.json's second half: "PConv tensor-pipe % of peak" = the generator's PConv layers alone
+                     # (enc1..enc7, dec7..dec1 and the final conv; fprop + dgrad + wgrad launches issued by the
+                     # generator engine), algorithmic FLOPs / summed CUDA-event time of those launches
+                     "pconv_only": {
+                         "tflops": pc_tf, "ms_per_step": pc_ms / args.steps,
+                         "gflop_per_tile": pc_flops / args.steps / B / 1e9,
+                         "frac_of_sustained_peak": pc_tf / peak_tf, "frac_of_burst_peak": pc_tf / peak_burst,
+                         "tensor_core_layers": {"tflops": pcg_tf, "ms_per_step": pcg_ms / args.steps,
+                                                "frac_of_sustained_peak": pcg_tf / peak_tf,
+                                                "frac_of_burst_peak": pcg_tf / peak_burst,
+                                                "note": "enc2..enc7, dec7..dec1 (implicit GEMM); enc1 and the final conv are "
+                                                        "bandwidth-bound 1<->64-channel kernels, included in the line above"},
+                         "peaks": {"sustained": peak_tf, "burst": peak_burst},
+                         "by_kind": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0,
+                                         "ms_per_step": v[1] / args.steps} for k, v in pconv.items()}}},
         "cpu_baseline": cpu,
+        "stock_pytorch_on_this_gpu": stock,
         "clocks": clocks,
         "calls_per_step": {k: v / args.steps for k, v in sorted(calls.items())},
     }
@@ -348,6 +504,11 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "infer", "hg"],
                     help="train: adversarial step (headline, configs[2]); infer: generator inference (configs[1]); "
                          "hg: human-guided fine-tune step (configs[4])")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="fix the GLOBAL batch (tiles per step over all ranks): strong scaling (configs[4]: 256) or the "
+                         "fixed 512 of configs[3]; per-GPU batch = global / ranks. Default: --batch per GPU (weak scaling)")
+    ap.add_argument("--masks", default="", choices=["", "rect", "large"], help="hole-mask family (default: rect; large for hg)")
+    ap.add_argument("--no-graph", action="store_true", help="infer workload: eager launches instead of one CUDA graph")
     ap.add_argument("--per-launch", default="", help="write a per-launch table of the tensor-core kernels to gpurun_out/<name>")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -23,6 +23,20 @@ from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU
 
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
+
+def _tagged(tag):
+    """Label every launch made inside the call with the network it belongs to (bench.py's per-network roofline)."""
+    def deco(fn):
+        def wrapper(*a, **k):
+            prev, ops.TAG = ops.TAG, tag
+            try:
+                return fn(*a, **k)
+            finally:
+                ops.TAG = prev
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
 # (name, Cin, Cout, k, stride, pad) — generator.py:13-28
 ENC = [("enc1", 1, 64, 7, 2, 3), ("enc2", 64, 128, 5, 2, 2), ("enc3", 128, 256, 5, 2, 2),
        ("enc4", 256, 512, 3, 2, 1), ("enc5", 512, 512, 3, 2, 1), ("enc6", 512, 512, 3, 2, 1),
@@ -209,6 +223,7 @@ class GeneratorEngine:
         self.final_taps = [(dh, dw) for (_, dh, dw) in self.final_plan.taps]
 
     # ---- forward ----
+    @_tagged("G")
     def forward(self, x: torch.Tensor, mask: torch.Tensor, params: Dict[str, torch.Tensor],
                 bns: Dict[str, BNParams], training: bool, save: Optional[GenSave],
                 trace: Optional[dict] = None) -> torch.Tensor:
@@ -290,6 +305,7 @@ class GeneratorEngine:
         return out.reshape(B, 1, H, W)
 
     # ---- backward ----
+    @_tagged("G")
     def backward(self, g_out: torch.Tensor, params: Dict[str, torch.Tensor], save: GenSave,
                  on_grads=None) -> Dict[str, torch.Tensor]:
         """Returns {param name: fp32 gradient}. `on_grads(names, tensors)` is called as soon as a layer's
@@ -396,6 +412,7 @@ class DiscriminatorEngine:
         self.d0_counts = [c for (_, c, _, _) in d0.subs]
         self._packs = {idx: ConvPack(4, 2, 1) for idx, _, _, _ in DISC_MID}
 
+    @_tagged("D")
     def forward(self, img: torch.Tensor, params: Dict[str, torch.Tensor], bns: Dict[int, BNParams], training: bool,
                 save: Optional[DiscSave]) -> torch.Tensor:
         B, C1, H, W = img.shape
@@ -438,6 +455,7 @@ class DiscriminatorEngine:
             self.trace.append(tr)
         return logits.reshape(B, 1, h - 1, w - 1)
 
+    @_tagged("D")
     def backward(self, g_logits: torch.Tensor, params: Dict[str, torch.Tensor], save: DiscSave, need_input_grad: bool,
                  need_param_grads: bool = True, on_grads=None):
         B, H, W = save.img.shape
@@ -522,6 +540,7 @@ class VggEngine:
             self._w0_key = key
         return self._w0
 
+    @_tagged("VGG")
     def features(self, img: torch.Tensor, vgg: Dict[str, torch.Tensor], save: Optional[list]):
         """img fp32 [B,1,H,W] -> bf16 [B,H/4,W/4,256]; `save` collects the post-ReLU activations."""
         B, _, H, W = img.shape
@@ -548,6 +567,7 @@ class VggEngine:
             self.trace.append(tr)
         return y
 
+    @_tagged("VGG")
     def backward(self, g_feat: torch.Tensor, vgg: Dict[str, torch.Tensor], saved: list, hw,
                  mode: str = "bf16") -> torch.Tensor:
         """g_feat: gradient w.r.t. the pre-ReLU output of conv14 (bf16 [B,1,h,w,256]) -> fp32 [B,1,H,W]."""

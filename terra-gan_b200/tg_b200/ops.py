@@ -56,6 +56,7 @@ def split_hi_lo(w: torch.Tensor):
 # entries are (kind, algorithmic FLOPs, start event, end event). Events come from a pool created up front
 # (profile_pool): creating a timing event costs ~100 us of host time, which made the timed region CPU-bound.
 PROFILE = None
+TAG = ""            # which network the engines are running ("G", "D", "VGG"): recorded with every profiled launch
 _POOL: list = []
 
 
@@ -84,7 +85,7 @@ def _prof_end(kind: str, flops: float, ev0, shape: str = "") -> None:
         return
     ev1 = _event()
     ev1.record()
-    PROFILE.append((kind, flops, ev0, ev1, shape))
+    PROFILE.append((kind, flops, ev0, ev1, shape, TAG))
 
 
 def _req(t: torch.Tensor, dtype, name: str) -> None:
@@ -437,8 +438,10 @@ def conv_c1_fwd(x, xmask, k, s, pad, wgt, bias, code=None, lut_dev=None, act=0, 
         rows = num_sms() * 4
         stats = torch.empty((rows, 2, 64), dtype=torch.float32, device=x.device)
     fn, name = _fn("tg_conv_c1_fwd", out_dtype)
+    ev0 = _prof_begin()
     check(fn(ptr(x), ptr(xmask), B, H, W, k, s, pad, ptr(wgt), ptr(bias), ptr(code), ptr(lut_dev),
              act, slope, ptr(out), 1 if out_split else 0, ptr(stats), rows, C.byref(used), stream_ptr()), name)
+    _prof_end("thin_fprop", 2.0 * B * Ho * Wo * 64 * k * k, ev0, f"B{B} {H}x{W}x1 -> {Ho}x{Wo}x64 k{k}s{s}")
     if stats is not None:
         stats = stats[: used.value]
     return out, stats
@@ -451,8 +454,10 @@ def conv_c1_wgrad(x, xmask, k, s, pad, g, g_split, dw, db=None, accumulate=False
     rows = lib().tg_conv_c1_wgrad_rows()
     partial = torch.empty((rows * 64 * (k * k + 1),), dtype=torch.float32, device=x.device)
     fn, name = _fn("tg_conv_c1_wgrad", dt)
+    ev0 = _prof_begin()
     check(fn(ptr(x), ptr(xmask), B, H, W, k, s, pad, ptr(g), 1 if g_split else 0, ptr(partial),
              rows, ptr(dw), ptr(db), 1 if accumulate else 0, stream_ptr()), name)
+    _prof_end("thin_wgrad", 2.0 * g.numel() * k * k, ev0, f"B{B} {H}x{W}x1 k{k}s{s} g{tuple(g.shape)}")
 
 
 def _tap_arrays(taps):
@@ -481,9 +486,12 @@ def conv_to1_fwd(x, x_split, hw, wgt, cls_counts, taps, bias, out_hw, mode=0, ma
         return out, sig
     nscr = lib().tg_conv_to1_fwd_scratch_floats(B, H, W, Cc, len(taps))
     scratch = torch.empty((nscr,), dtype=torch.float32, device=x.device) if nscr else None
+    ev0 = _prof_begin()
     check(lib().tg_conv_to1_fwd(ptr(x), 1 if x_split else 0, B, H, W, Cc, ptr(wgt), len(cls_counts), cc, dh, dw,
                                 ptr(bias), Ho, Wo, mode, ptr(mask), ptr(xin), ptr(out), ptr(sig), ptr(scratch), nscr,
                                 stream_ptr()), "tg_conv_to1_fwd")
+    _prof_end("thin_fprop" if mode == 1 or bias is not None else "thin_dgrad",
+              2.0 * B * Ho * Wo * Cc * (len(taps) / len(cls_counts)), ev0, f"B{B} {H}x{W}x{Cc} -> {Ho}x{Wo}x1 taps{len(taps)}")
     if nscr:    # the C = 64 cases run two kernels (tap dot products, shifted sum): keep the launch count exact
         from . import _lib
         _lib.CALLS["tg_conv_to1_fwd+tapsum"] = _lib.CALLS.get("tg_conv_to1_fwd+tapsum", 0) + 1
@@ -498,7 +506,9 @@ def conv_to1_bwd_data(g, wgt, taps, hw, Cc, out_dtype=BF16):
     dx = torch.empty((B, H, W, Cc), dtype=out_dtype, device=g.device)
     dh, dw = _tap_arrays(taps)
     fn, name = _fn("tg_conv_to1_bwd_data", out_dtype)
+    ev0 = _prof_begin()
     check(fn(ptr(g), B, Ho, Wo, ptr(wgt), len(taps), dh, dw, H, W, Cc, ptr(dx), stream_ptr()), name)
+    _prof_end("thin_dgrad", 2.0 * B * Ho * Wo * Cc * len(taps), ev0, f"B{B} {Ho}x{Wo}x1 -> {H}x{W}x{Cc} taps{len(taps)}")
     return dx
 
 
@@ -513,8 +523,10 @@ def conv_to1_wgrad(x, g, taps, dw, db=None, accumulate=False):
     partial_b = torch.empty((rows,), dtype=torch.float32, device=x.device)
     dh, dww = _tap_arrays(taps)
     fn, name = _fn("tg_conv_to1_wgrad", dt)
+    ev0 = _prof_begin()
     check(fn(ptr(x), B, H, W, Cc, ptr(g), Ho, Wo, len(taps), dh, dww, ptr(partial),
              ptr(partial_b), rows, ptr(dw), ptr(db), 1 if accumulate else 0, stream_ptr()), name)
+    _prof_end("thin_wgrad", 2.0 * B * Ho * Wo * Cc * len(taps), ev0, f"B{B} x {H}x{W}x{Cc} g {Ho}x{Wo}x1 taps{len(taps)}")
 
 
 def final_bwd_pre(g_out, sig, mask_u8):

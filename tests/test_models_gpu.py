@@ -545,3 +545,21 @@ def test_fused_adam_matches_torch_adam_and_keeps_packed_weights_current():
     # state_dict layout is torch.optim.Adam's
     sd = ours[0].state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_graphed_generator_matches_eager_inference():
+    """tg_b200.graphs.GraphedGenerator: one cudaGraphLaunch per call, bit-identical to the eager eval forward."""
+    from tg_b200.graphs import GraphedGenerator
+    B, H = 3, 128
+    G = PConvUNet()
+    G.load_state_dict(O.make_generator_state(1))
+    G.to(DEV).eval()
+    gg = GraphedGenerator(G, B, H, H)
+    for seed, kind in ((80, "rect"), (81, "large")):
+        x, mask = O.make_tiles(seed, B, H).to(DEV), O.make_mask(seed + 5, B, H, kind).to(DEV)
+        with torch.no_grad():
+            eager = G(x * mask, mask)
+        out = gg(x * mask, mask)
+        assert torch.equal(out, eager)
+    with pytest.raises(RuntimeError, match="captured for"):
+        gg(torch.zeros(1, 1, H, H, device=DEV), torch.ones(1, 1, H, H, device=DEV))
