@@ -279,6 +279,40 @@ int tg_bce_logits_fwd(const float* logits, const float* target, float target_con
 int tg_bce_logits_bwd(const float* logits, const float* target, float target_const, long n,
                       const float* grad_out, float* grad_logits, void* stream);
 
+/* ---- logging-interval image-quality metrics (metrics_kernels.cu) ------------------------
+ * One fused reduction replacing ExperimentTracker._calculate_psnr/_calculate_ssim/_calculate_l1_l2
+ * (utils/experiment_tracking.py:196-231, called from :678-695), PerformanceMetrics (mvp_gan/src/utils/metrics.py:12-46)
+ * and calculate_boundary_quality (mvp_gan/src/evaluation/metrics.py:79-133), which the loops call every
+ * log_interval batches (train.py:229-266) with ~40 ATen kernels and 8 .item() host syncs.
+ * pred / target / mask: fp32 [B][1][H][W] (mask may be NULL: no boundary metrics). partial: rows_cap * 10 doubles.
+ * out[9] (device) = psnr, ssim, l1_distance, l2_distance, mse, boundary_mse, boundary_psnr, boundary_gradient_diff,
+ * boundary pixel count. No host synchronisation. */
+int tg_quality_metrics_rows(void);
+int tg_quality_metrics(const float* pred, const float* target, const float* mask, int B, int H, int W,
+                       double* partial, int rows_cap, float* out, void* stream);
+
+/* ---- batched inference I/O and DSM normalisation (image_io.cu) ----------------
+ * The byte-level ends of the inference path, per batch on the device instead of per tile through PIL / numpy:
+ *   tg_u8_prepare          uint8 tile + uint8 mask -> masked fp32 image (u8/255 * [mask>0]) and fp32 {0,1} mask
+ *                          (mvp_gan/src/evaluate.py:28-33)
+ *   tg_resize_bilinear_u8  PIL.Image.resize(..., BILINEAR) on 8-bit images, bit-exact with Pillow's Resample.c
+ *                          (evaluate.py:58-59 512->500; the Resize((512,512)) of evaluate.py:21-25;
+ *                          utils/data_extraction.py:106-107). src may be fp32, quantised on the fly as
+ *                          (x*255).astype(uint8) (evaluate.py:54-55). tmp: B*Hin*Wout bytes.
+ *   tg_resize_ksize / tg_resize_coeffs   HOST helpers building Pillow's fixed-point coefficient tables
+ *                          (bounds [out][2], kk [out][ksize] int32) that the caller uploads once per (in, out) size
+ *   tg_quantize_u8         (x * 255).astype(uint8)
+ *   tg_dsm_normalize       NaN-aware per-tile min-max normalisation of float64 DSM tiles [B][H][W] to uint8
+ *                          (utils/data_extraction.py:80-103); minmax: B*2 doubles of workspace / output. */
+int tg_u8_prepare(const uint8_t* img, const uint8_t* mask, long n, float* masked, float* mask_out, void* stream);
+int tg_resize_ksize(int in_size, int out_size);
+int tg_resize_coeffs(int in_size, int out_size, int32_t* bounds, int32_t* kk, int ksize);
+int tg_resize_bilinear_u8(const void* src, int src_is_f32, int B, int Hin, int Win, int Hout, int Wout,
+                          const int32_t* bounds_w, const int32_t* kk_w, int ksize_w, const int32_t* bounds_h,
+                          const int32_t* kk_h, int ksize_h, uint8_t* tmp, uint8_t* dst, void* stream);
+int tg_quantize_u8(const float* src, long n, uint8_t* dst, void* stream);
+int tg_dsm_normalize(const double* data, int B, int H, int W, double* minmax, uint8_t* out, void* stream);
+
 /* ---- fp32-storage verification path ("TF32 path <= 1e-3", BASELINE.json north star) ---------------------------
  * Twins of the entry points above with fp32 activations instead of bf16 (same argument meaning; every `void*`
  * activation / gradient pointer is a float tensor). The implicit-GEMM entry points take `dtype = TG_DTYPE_F32` in

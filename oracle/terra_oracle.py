@@ -516,6 +516,39 @@ def human_guided_loss(inp: Tensor, target: Tensor, mask: Tensor, human_mask: Opt
 
 
 # --------------------------------------------------------------------------------------------------
+# logging-interval metrics — mvp_gan/src/utils/metrics.py:12-46, utils/experiment_tracking.py:196-231,
+# mvp_gan/src/evaluation/metrics.py:79-133
+# --------------------------------------------------------------------------------------------------
+def quality_metrics(pred: Tensor, target: Tensor, mask: Optional[Tensor] = None) -> dict:
+    mse = F.mse_loss(pred, target)                                     # metrics.py:14
+    out = {"mse": mse.item(), "psnr": float("inf") if mse == 0 else (20 * torch.log10(1.0 / torch.sqrt(mse))).item()}
+    C1, C2, ws = (0.01 * 1.0) ** 2, (0.03 * 1.0) ** 2, 11                # :24-39
+    mu1 = F.avg_pool2d(pred, ws, stride=1, padding=ws // 2)
+    mu2 = F.avg_pool2d(target, ws, stride=1, padding=ws // 2)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.avg_pool2d(pred * pred, ws, stride=1, padding=ws // 2) - mu1_sq
+    s2 = F.avg_pool2d(target * target, ws, stride=1, padding=ws // 2) - mu2_sq
+    s12 = F.avg_pool2d(pred * target, ws, stride=1, padding=ws // 2) - mu1_mu2
+    out["ssim"] = (((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))).mean().item()
+    out["l1_distance"] = F.l1_loss(pred, target).item()                # :44-45
+    out["l2_distance"] = F.mse_loss(pred, target, reduction="mean").sqrt().item()
+    if mask is not None:                                               # evaluation/metrics.py:88-120
+        dil = F.max_pool2d(mask, kernel_size=3, stride=1, padding=1)
+        ero = 1 - F.max_pool2d(1 - mask, kernel_size=3, stride=1, padding=1)
+        bd = torch.clamp(dil - ero, 0.0, 1.0)
+        out["boundary_pixels"] = bd.sum().item()
+        if torch.sum(bd) < 1e-6:
+            out.update(boundary_mse=0.0, boundary_psnr=0.0, boundary_gradient_diff=0.0)
+        else:
+            bmse = torch.mean(((pred - target) * bd) ** 2)
+            pd = torch.abs(pred[:, :, 1:, :] - pred[:, :, :-1, :]).mean() + torch.abs(pred[:, :, :, 1:] - pred[:, :, :, :-1]).mean()
+            td = torch.abs(target[:, :, 1:, :] - target[:, :, :-1, :]).mean() + torch.abs(target[:, :, :, 1:] - target[:, :, :, :-1]).mean()
+            out.update(boundary_mse=bmse.item(), boundary_psnr=(10 * torch.log10(1.0 / (bmse + 1e-6))).item(),
+                       boundary_gradient_diff=torch.abs(pd - td).item())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # train-step bodies
 # --------------------------------------------------------------------------------------------------
 def _leaf_params(sd: SD) -> List[str]:

@@ -132,6 +132,15 @@ PROTOTYPES = {
     "tg_l1_bf16_bwd": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]),
     "tg_bce_logits_fwd": (c_int, [c_void_p, c_void_p, c_float, c_long, c_void_p, c_void_p]),
     "tg_bce_logits_bwd": (c_int, [c_void_p, c_void_p, c_float, c_long, c_void_p, c_void_p, c_void_p]),
+    "tg_u8_prepare": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p]),
+    "tg_resize_ksize": (c_int, [c_int, c_int]),
+    "tg_resize_coeffs": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int]),
+    "tg_resize_bilinear_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "tg_quantize_u8": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
+    "tg_dsm_normalize": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tg_quality_metrics_rows": (c_int, []),
+    "tg_quality_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "tg_wgrad_partial_floats_f32": (C.c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "tg_split_tf32": (c_int, [c_void_p, c_long, c_int, c_int, c_void_p, c_void_p]),
     "tg_conv_to1_fwd_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, C.POINTER(c_int),

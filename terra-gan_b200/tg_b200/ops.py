@@ -605,3 +605,95 @@ def bce_logits_bwd(logits, grad_out, target=None, target_const=0.0):
     check(lib().tg_bce_logits_bwd(ptr(logits), ptr(target), float(target_const), logits.numel(), ptr(grad_out),
                                   ptr(gx), stream_ptr()), "tg_bce_logits_bwd")
     return gx
+
+
+# ------------------------------------------------------------------------------------------------
+# logging-interval quality metrics
+# ------------------------------------------------------------------------------------------------
+QUALITY_FIELDS = ("psnr", "ssim", "l1_distance", "l2_distance", "mse", "boundary_mse", "boundary_psnr",
+                  "boundary_gradient_diff", "boundary_pixels")
+
+
+def quality_metrics(pred, target, mask=None) -> torch.Tensor:
+    """fp32 [B,1,H,W] x2 (+ mask) -> device fp32 [9] in the order of QUALITY_FIELDS (tg_quality_metrics); no host sync."""
+    for n, t in (("pred", pred), ("target", target)) + ((("mask", mask),) if mask is not None else ()):
+        _req(t, torch.float32, n)
+    if pred.dim() != 4 or pred.shape[1] != 1 or target.shape != pred.shape or (mask is not None and mask.shape != pred.shape):
+        raise RuntimeError("quality_metrics: pred / target / mask must all be [B,1,H,W] (single-channel DSM tiles)")
+    B, _, H, W = pred.shape
+    rows = lib().tg_quality_metrics_rows()
+    partial = torch.empty((rows * 10,), dtype=torch.float64, device=pred.device)
+    out = torch.empty((9,), dtype=torch.float32, device=pred.device)
+    check(lib().tg_quality_metrics(ptr(pred), ptr(target), ptr(mask), B, H, W, ptr(partial), rows, ptr(out), stream_ptr()),
+          "tg_quality_metrics")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# batched inference I/O and DSM normalisation (SURVEY.md §8f rank 3 / 4)
+# ------------------------------------------------------------------------------------------------
+_RESIZE_TABLES: dict = {}
+
+
+def resize_tables(in_size: int, out_size: int, device):
+    """Device copies of Pillow's fixed-point bilinear coefficient tables for one axis: (bounds, kk, ksize)."""
+    key = (in_size, out_size, str(device))
+    if key not in _RESIZE_TABLES:
+        ks = lib().tg_resize_ksize(in_size, out_size)
+        if ks <= 0:
+            raise RuntimeError("resize_tables: bad sizes")
+        bounds = torch.empty((out_size, 2), dtype=torch.int32)
+        kk = torch.empty((out_size, ks), dtype=torch.int32)
+        check(lib().tg_resize_coeffs(in_size, out_size, bounds.data_ptr(), kk.data_ptr(), ks), "tg_resize_coeffs")
+        _RESIZE_TABLES[key] = (bounds.to(device), kk.to(device), ks)
+    return _RESIZE_TABLES[key]
+
+
+def u8_prepare(img_u8: torch.Tensor, mask_u8: torch.Tensor):
+    """uint8 [B,H,W] x2 -> (masked fp32 [B,1,H,W], mask fp32 [B,1,H,W]) — evaluate.py:28-33."""
+    _req(img_u8, torch.uint8, "img")
+    _req(mask_u8, torch.uint8, "mask")
+    if img_u8.shape != mask_u8.shape or img_u8.dim() != 3:
+        raise RuntimeError("u8_prepare: image and mask must both be uint8 [B,H,W]")
+    B, H, W = img_u8.shape
+    masked = torch.empty((B, 1, H, W), dtype=torch.float32, device=img_u8.device)
+    mask = torch.empty_like(masked)
+    check(lib().tg_u8_prepare(ptr(img_u8), ptr(mask_u8), img_u8.numel(), ptr(masked), ptr(mask), stream_ptr()), "tg_u8_prepare")
+    return masked, mask
+
+
+def resize_bilinear_u8(src: torch.Tensor, out_hw, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """PIL.Image.resize(BILINEAR) of a batch of 8-bit images [B,H,W] (uint8, or fp32 quantised as (x*255).astype(uint8))."""
+    if src.dtype not in (torch.uint8, torch.float32):
+        raise RuntimeError("resize_bilinear_u8: src must be uint8 or fp32")
+    _req(src, src.dtype, "src")
+    if src.dim() == 4 and src.shape[1] == 1:
+        src = src[:, 0]
+    B, Hin, Win = src.shape
+    Hout, Wout = out_hw
+    dev = src.device
+    bw, kw, ksw = resize_tables(Win, Wout, dev)
+    bh, kh, ksh = resize_tables(Hin, Hout, dev)
+    tmp = torch.empty((B, Hin, Wout), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((B, Hout, Wout), dtype=torch.uint8, device=dev)
+    check(lib().tg_resize_bilinear_u8(ptr(src), 1 if src.dtype == torch.float32 else 0, B, Hin, Win, Hout, Wout, ptr(bw), ptr(kw),
+                                      ksw, ptr(bh), ptr(kh), ksh, ptr(tmp), ptr(out), stream_ptr()), "tg_resize_bilinear_u8")
+    return out
+
+
+def quantize_u8(x: torch.Tensor) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    check(lib().tg_quantize_u8(ptr(x), x.numel(), ptr(out), stream_ptr()), "tg_quantize_u8")
+    return out
+
+
+def dsm_normalize(data: torch.Tensor):
+    """float64 [B,H,W] (NaN = no data) -> (uint8 [B,H,W], minmax float64 [B,2]) — data_extraction.py:80-103."""
+    _req(data, torch.float64, "data")
+    B, H, W = data.shape
+    mm = torch.empty((B, 2), dtype=torch.float64, device=data.device)
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=data.device)
+    check(lib().tg_dsm_normalize(ptr(data), B, H, W, ptr(mm), ptr(out), stream_ptr()), "tg_dsm_normalize")
+    return out, mm

@@ -249,10 +249,85 @@ def gen_hg_step(ref):
     print("hg_step.npz", len(out), "arrays, loss", float(out["loss"]))
 
 
+def load_reference_metrics():
+    """mvp_gan/src/utils/metrics.py (imports GPUtil / psutil, stubbed) and mvp_gan/src/evaluation/metrics.py by path."""
+    for stub in ("GPUtil", "psutil"):
+        if stub not in sys.modules:
+            try:
+                __import__(stub)
+            except ImportError:
+                sys.modules[stub] = types.ModuleType(stub)
+    mods = {}
+    for tag, rel in (("utils_metrics", "mvp_gan/src/utils/metrics.py"), ("eval_metrics", "mvp_gan/src/evaluation/metrics.py")):
+        spec = importlib.util.spec_from_file_location("ref_" + tag, os.path.join(REF, rel))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        mods[tag] = m
+    return mods
+
+
+def gen_metrics():
+    """Logging-interval metrics: PerformanceMetrics.calculate_psnr / _ssim / _l1_l2 and
+    calculate_boundary_quality of the reference on seeded tiles."""
+    ref = load_reference_metrics()
+    PM, cbq = ref["utils_metrics"].PerformanceMetrics, ref["eval_metrics"].calculate_boundary_quality
+    out = {}
+    cases = [("rect", 2, 128, 128), ("large", 3, 96, 160), ("ones", 1, 64, 64), ("iid", 2, 64, 64)]
+    for i, (kind, B, H, W) in enumerate(cases):
+        target = O.make_tiles(500 + i, B, H, W)
+        mask = O.make_mask(510 + i, B, H, kind, W)
+        noise = torch.rand((B, 1, H, W), generator=torch.Generator().manual_seed(520 + i))
+        pred = target * mask + (0.8 * target + 0.2 * noise) * (1 - mask)
+        l1, l2 = PM.calculate_l1_l2(pred, target)
+        bq = cbq(pred, target, mask)
+        out[f"{i}/values"] = np.array([PM.calculate_psnr(pred, target), PM.calculate_ssim(pred, target), l1, l2,
+                                       torch.nn.functional.mse_loss(pred, target).item(), bq["boundary_mse"],
+                                       bq["boundary_psnr"], bq["boundary_gradient_diff"]], dtype=np.float64)
+        out[f"{i}/case"] = np.array([B, H, W])
+    out["kinds"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
+    print("metrics.npz", {k: v for k, v in out.items() if k.endswith("values")})
+
+
+def gen_image_io():
+    """Batched inference I/O and DSM normalisation (rank 4): Pillow's own
+    Image.resize(..., BILINEAR) on uint8 'L' images (evaluate.py:21-25,53-59, data_extraction.py:105-107) and the
+    reference's numpy normalisation (data_extraction.py:80-103) on seeded arrays."""
+    from PIL import Image
+    rng = np.random.RandomState(7)
+    out = {}
+    for i, (hin, win, hout, wout) in enumerate([(512, 512, 500, 500), (500, 500, 512, 512), (64, 96, 50, 70), (37, 41, 512, 512)]):
+        a = rng.randint(0, 256, (hin, win)).astype(np.uint8)
+        if i == 0:
+            a[:100] = np.arange(win, dtype=np.uint8)[None, :]       # smooth ramp: rounding ties
+        r = np.asarray(Image.fromarray(a, mode="L").resize((wout, hout), Image.BILINEAR))
+        out[f"resize/{i}/in"], out[f"resize/{i}/out"] = a, r
+    # evaluate.py:53-55: (output * 255).astype('uint8')
+    f = rng.rand(64, 64).astype(np.float32)
+    f[0, :4] = [0.0, 1.0, 0.999999, 0.5]
+    out["quant/in"], out["quant/out"] = f, (f * 255).astype("uint8")
+    # data_extraction.py:80-103
+    for i, (h, w) in enumerate([(200, 200), (50, 80)]):
+        d = rng.uniform(-20, 300, (h, w))
+        d[rng.rand(h, w) < 0.05] = np.nan
+        dmin, dmax = np.nanmin(d), np.nanmax(d)
+        n = np.nan_to_num(255 * (d - dmin) / (dmax - dmin), nan=0).astype(np.uint8)
+        png = np.asarray(Image.fromarray(n, mode="L").resize((512, 512), Image.BILINEAR))
+        out[f"dsm/{i}/in"], out[f"dsm/{i}/norm"], out[f"dsm/{i}/png"] = d, n, png
+    np.savez_compressed(os.path.join(HERE, "image_io.npz"), **out)
+    print("image_io.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
+    if len(sys.argv) > 1 and sys.argv[1] == "aux":      # the round-2 fixtures only
+        gen_metrics()
+        gen_image_io()
+        sys.exit(0)
     ref = load_reference()
     gen_pconv_layers(ref)
     gen_generator(ref)
     gen_adv_step(ref)
     gen_hg_step(ref)
+    gen_metrics()
+    gen_image_io()

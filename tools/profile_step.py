@@ -17,7 +17,9 @@ G, D = PConvUNet(), Discriminator()
 G.to(dev).train(); D.to(dev).train()
 os.environ.setdefault("TERRA_VGG_SEED", "3")
 crit = InpaintingLoss(perceptual_weight=0.1, tv_weight=0.1, device=dev)
-st = AdversarialStep(G, D, crit, torch.optim.Adam(G.parameters(), lr=2e-4), torch.optim.Adam(D.parameters(), lr=2e-4))
+from tg_b200 import optim as tg_optim
+st = AdversarialStep(G, D, crit, tg_optim.Adam(G.parameters(), lr=2e-4, modules=[G]),
+                     tg_optim.Adam(D.parameters(), lr=2e-4, modules=[D]))     # the bench default: fused Adam + re-pack
 gen = torch.Generator().manual_seed(0)
 real = torch.rand((B, 1, 512, 512), generator=gen).to(dev)
 mask = torch.ones(B, 1, 512, 512)
