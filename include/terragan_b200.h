@@ -313,6 +313,21 @@ int tg_resize_bilinear_u8(const void* src, int src_is_f32, int B, int Hin, int W
 int tg_quantize_u8(const float* src, long n, uint8_t* dst, void* stream);
 int tg_dsm_normalize(const double* data, int B, int H, int W, double* minmax, uint8_t* out, void* stream);
 
+/* ---- synthetic irregular hole masks (maskgen.cu) ---------------------------------------
+ * The dense image operations of generate_dem_random_mask (random__annotation_mask_generator.py:33-148): scipy.ndimage
+ * binary morphology with the default cross structuring element and border value 0, the separable float64 Gaussian
+ * filter (mode 'reflect', scipy's summation order) and the threshold / distance tests, on [H][W] arrays. The random
+ * draws stay on the host in the reference's order (tg_b200/maskgen.py): seeded runs reproduce the reference's masks.
+ *   tg_morph_cross  one iteration of binary_dilation (erode = 0) or binary_erosion (erode = 1); out != in
+ *   tg_gauss1d_f64  correlate1d of float64 data with a symmetric kernel weights[2*radius+1] along axis 0 / 1; out != in
+ *   tg_mask_shape   mode 0: out = field > p0; 1: out |= dist <= p0 + field*p1; 2: out |= x^2/p0^2 + y^2/p1^2 <= 1;
+ *                   3: out |= (x^2+y^2 <= p0^2) & (field > p1), with x = col - cx, y = row - cy */
+int tg_morph_cross(const uint8_t* in, int H, int W, int erode, uint8_t* out, void* stream);
+int tg_gauss1d_f64(const double* in, int H, int W, int axis, const double* weights, int radius, double* out,
+                   void* stream);
+int tg_mask_shape(const double* field, int H, int W, int mode, int cx, int cy, double p0, double p1, uint8_t* out,
+                  void* stream);
+
 /* ---- fp32-storage verification path ("TF32 path <= 1e-3", BASELINE.json north star) ---------------------------
  * Twins of the entry points above with fp32 activations instead of bf16 (same argument meaning; every `void*`
  * activation / gradient pointer is a float tensor). The implicit-GEMM entry points take `dtype = TG_DTYPE_F32` in

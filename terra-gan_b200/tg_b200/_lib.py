@@ -139,6 +139,9 @@ PROTOTYPES = {
                                       c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "tg_quantize_u8": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
     "tg_dsm_normalize": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tg_morph_cross": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tg_gauss1d_f64": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "tg_mask_shape": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, C.c_double, C.c_double, c_void_p, c_void_p]),
     "tg_quality_metrics_rows": (c_int, []),
     "tg_quality_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "tg_wgrad_partial_floats_f32": (C.c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),

@@ -318,11 +318,39 @@ def gen_image_io():
     print("image_io.npz", len(out), "arrays")
 
 
+MASK_CASES = [(42, "edge", 500), (43, "patch", 500), (44, "region", 500), (45, "region", 500), (46, "region", 500),
+              (47, None, 500), (48, "edge", 512), (49, "patch", 256)]
+
+
+def gen_masks():
+    """Synthetic irregular hole masks: the reference's generate_dem_random_mask under
+    np.random.seed(s) (random__annotation_mask_generator.py:33-148; matplotlib, which that file imports for its
+    plotting helpers, is stubbed). Stored bit-packed."""
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    spec = importlib.util.spec_from_file_location("ref_maskgen", os.path.join(REF, "random__annotation_mask_generator.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    out = {}
+    for i, (seed, approach, size) in enumerate(MASK_CASES):
+        np.random.seed(seed)
+        mask = m.generate_dem_random_mask(size=size, approach=approach)
+        out[f"{i}/bits"] = np.packbits(mask)
+        out[f"{i}/meta"] = np.array([seed, size, int(mask.sum())])
+        out[f"{i}/approach"] = np.array(approach or "none")
+        print("mask", i, seed, approach, size, "valid fraction", float(mask.mean()))
+    np.savez_compressed(os.path.join(HERE, "masks.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
+    if len(sys.argv) > 1 and sys.argv[1] == "masks":
+        gen_masks()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "aux":      # the round-2 fixtures only
         gen_metrics()
         gen_image_io()
+        gen_masks()
         sys.exit(0)
     ref = load_reference()
     gen_pconv_layers(ref)

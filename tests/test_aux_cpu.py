@@ -62,3 +62,19 @@ def test_library_resize_tables_equal_pillow(in_size, out_size):
     assert rc == 0
     rb, rk = IO._coeffs(in_size, out_size)
     assert ks == rk.shape[1] and np.array_equal(bounds, rb) and np.array_equal(kk, rk)
+
+
+MASK_CASES = 8
+
+
+@pytest.mark.parametrize("i", range(MASK_CASES))
+def test_oracle_mask_generator_matches_reference(i):
+    """oracle.maskgen reproduces the reference's generate_dem_random_mask under the same seed bit for bit."""
+    from oracle import maskgen as MG
+    z = np.load(os.path.join(G, "masks.npz"))
+    seed, size, count = (int(v) for v in z[f"{i}/meta"])
+    approach = str(z[f"{i}/approach"])
+    np.random.seed(seed)
+    m = MG.generate_dem_random_mask(size, None if approach == "none" else approach)
+    ref = np.unpackbits(z[f"{i}/bits"])[: size * size].reshape(size, size).astype(bool)
+    assert m.sum() == count and np.array_equal(m, ref)

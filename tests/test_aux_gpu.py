@@ -144,3 +144,25 @@ def test_evaluate_drop_in_writes_the_reference_png(tmp_path):
     Gm.to(DEV)
     out2 = inpaint_with_gan(ip, mp, tmp_path / "inpainted", Gm)           # a model instance is accepted too (:36)
     assert np.array_equal(np.asarray(Image.open(out2)), got) and out2.name == "tile_inpainted.png"
+
+
+@pytest.mark.parametrize("i", range(8))
+def test_device_mask_generator_bit_exact_with_reference(i):
+    """tg_b200.maskgen: same seed -> the reference's mask, bit for bit (golden fixture from the reference function),
+    with the dense scipy.ndimage work done by csrc/maskgen.cu."""
+    from tg_b200 import maskgen
+    z = np.load(os.path.join(G, "masks.npz"))
+    seed, size, count = (int(v) for v in z[f"{i}/meta"])
+    approach = str(z[f"{i}/approach"])
+    np.random.seed(seed)
+    m = maskgen.generate_dem_random_mask(size, None if approach == "none" else approach).cpu().numpy()
+    ref = np.unpackbits(z[f"{i}/bits"])[: size * size].reshape(size, size).astype(bool)
+    print(i, approach, size, "pixels differing:", int((m != ref).sum()))
+    assert np.array_equal(m, ref)
+
+
+def test_hole_mask_batch_feeds_the_generator():
+    from tg_b200 import maskgen
+    masks = maskgen.hole_masks(3, 512, seed=123)
+    assert masks.shape == (3, 1, 512, 512) and masks.dtype == torch.float32 and masks.is_cuda
+    assert set(masks.unique().tolist()) <= {0.0, 1.0} and 0.3 < masks.mean().item() < 1.0
