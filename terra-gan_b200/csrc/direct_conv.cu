@@ -10,6 +10,8 @@
 //   VGG16 features[0] on input.repeat(1,3,1,1)              mvp_gan/src/utils/losses.py:79-89
 //   final conv + sigmoid + `out*(1-mask) + x*mask`          mvp_gan/src/models/generator.py:56-62
 // and the autograd backward of each.
+#include <stdlib.h>
+
 #include "tg_common.cuh"
 #include "../../include/terragan_b200.h"
 #include "thin_mma.cuh"
@@ -758,22 +760,225 @@ conv_to1_wgrad_kernel(const TX* __restrict__ x, int B, int H, int W, int C, cons
 }
 
 // dw_out[c][perm[t]] (+)= sum_rows partial[row][t][c]   (PyTorch layout [1][C][kh][kw]);  db (+)= sum partial_b
-__global__ void conv_to1_wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_b,
-                                             int rows, int T, int C, float* __restrict__ dw, float* __restrict__ db,
-                                             int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < T * C) {
+// Block = 32 outputs x 8 row lanes: the rows are summed 8-way in parallel (one serial chain over several hundred
+// rows was latency-bound: 160 us for 592 rows), then combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+conv_to1_wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_b,
+                             int rows, int T, int C, float* __restrict__ dw, float* __restrict__ db,
+                             int accumulate) {
+  __shared__ double s_sum[8][32];
+  const int ol = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + ol;
+  double s = 0.0;
+  if (i < T * C)
+    for (int r = rl; r < rows; r += 8) s += partial[static_cast<long>(r) * T * C + i];
+  s_sum[rl][ol] = s;
+  __syncthreads();
+  if (rl == 0 && i < T * C) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) s += s_sum[q][ol];
     const int t = i / C, c = i % C;
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += partial[(static_cast<long>(r) * T + t) * C + c];
     float* d = dw + static_cast<long>(c) * T + t;
     *d = (accumulate ? *d : 0.f) + static_cast<float>(s);
   }
-  if (i == 0 && db != nullptr && partial_b != nullptr) {
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += partial_b[r];
-    db[0] = (accumulate ? db[0] : 0.f) + static_cast<float>(s);
+  if (blockIdx.x == 0 && db != nullptr && partial_b != nullptr) {
+    __syncthreads();
+    double b = 0.0;
+    for (int r = threadIdx.x; r < rows; r += 256) b += partial_b[r];
+    // fixed-order block reduction
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (ol == 0) s_sum[rl][0] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tot += s_sum[q][0];
+      db[0] = (accumulate ? db[0] : 0.f) + static_cast<float>(tot);
+    }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 512 -> 1 channels with a 4x4 window (Discriminator model[11], discriminator.py:22): forward, data- and weight-
+// gradient. 1 GFLOP per call at batch 64 — far too small for a 128-row tensor-core tile to matter — but the generic
+// kernels above re-read every activation row once per tap through L2 and spent 0.17 / 0.15 / 0.48 ms per launch
+// (1.9 ms of the step). These read or write each activation exactly once:
+//   forward   per-pixel tap dot products T[t][q] = <x[q][:], w[t][:]> (a warp owns 4 pixels, a lane 16 channels; the 64
+//             sums of a warp are reduced by two transposing butterflies), then tg::to1_tapsum_launch does the shifted sum
+//   dgrad     a thread keeps the 16 x 8 weights of its 8 channels in registers and walks over pixels
+//   wgrad     a thread keeps the 16 x 8 accumulators of its 8 channels in registers; the four pixel lanes of a block and
+//             then the blocks are summed in a fixed order (deterministic)
+// ------------------------------------------------------------------------------------------------
+constexpr int kWideC = 512, kWideT = 16;
+
+__global__ void __launch_bounds__(256)
+to1_wide_tapdot_kernel(const __nv_bfloat16* __restrict__ x, long total, const float* __restrict__ wgt /*[16][512]*/,
+                       float* __restrict__ T /*[16][total]*/) {
+  __shared__ float4 s_w[kWideT * 4 * 32];                 // [t][i][lane]: float4 i of the lane's 16 channels, conflict-free
+  for (int i = threadIdx.x; i < kWideT * kWideC / 4; i += 256) {
+    const int t = i / (kWideC / 4), c4 = i % (kWideC / 4);      // channels 4*c4 .. 4*c4+3
+    const int lane = c4 / 4, q = c4 % 4;
+    s_w[(t * 4 + q) * 32 + lane] = *reinterpret_cast<const float4*>(wgt + t * kWideC + 4 * c4);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long warp_id = (blockIdx.x * 256L + threadIdx.x) >> 5, n_warps = (gridDim.x * 256L) >> 5;
+  for (long p0 = warp_id * 4; p0 < total; p0 += n_warps * 4) {
+    float xv[4][16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (p0 + j < total) {
+        float a[8], b[8];
+        vload8(x + (p0 + j) * kWideC + lane * 16, a);
+        vload8(x + (p0 + j) * kWideC + lane * 16 + 8, b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { xv[j][e] = a[e]; xv[j][8 + e] = b[e]; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) xv[j][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float v[32];                                         // v[(t - 8 half) * 4 + pixel]
+#pragma unroll
+      for (int tt = 0; tt < 8; ++tt) {
+        const int t = half * 8 + tt;
+        float wv[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = s_w[(t * 4 + q) * 32 + lane];
+          wv[4 * q] = w4.x; wv[4 * q + 1] = w4.y; wv[4 * q + 2] = w4.z; wv[4 * q + 3] = w4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float acc = 0.f;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc = fmaf(xv[j][e], wv[e], acc);
+          v[tt * 4 + j] = acc;
+        }
+      }
+      const float tot = warp_transpose_sum32(v);           // lane l now holds the warp total of v[l]
+      const int t = half * 8 + (lane >> 2), j = lane & 3;
+      if (p0 + j < total) T[static_cast<long>(t) * total + p0 + j] = tot;
+    }
+  }
+}
+
+// dx[q][c] = sum_t g[q - d_t] * w[t][c].  Block = 64 channel groups (8 channels each) x 4 pixel lanes; a thread produces 4
+// pixels per iteration so that every pair of 16-byte weight reads from shared memory feeds 32 FMAs (with the 128
+// weights of a thread held in registers the kernel ran one block per SM and was latency-bound: 155 us).
+__global__ void __launch_bounds__(256)
+to1_wide_bwd_data_kernel(const float* __restrict__ g, int B, int Ho, int Wo, const float* __restrict__ wgt, To1Taps taps,
+                         int H, int W, __nv_bfloat16* __restrict__ dx) {
+  __shared__ float4 s_w[kWideT][2][64];                     // [t][half][channel group]
+  for (int i = threadIdx.x; i < kWideT * 128; i += 256) {
+    const int t = i / 128, r = i % 128, cg = r >> 1, half = r & 1;
+    s_w[t][half][cg] = __ldg(reinterpret_cast<const float4*>(wgt + t * kWideC + cg * 8) + half);
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 63, pl = threadIdx.x >> 6;
+  const unsigned total = static_cast<unsigned>(B) * H * W, HW = static_cast<unsigned>(H) * W;
+  constexpr int U = 4;
+  for (unsigned q0 = (blockIdx.x * 4 + pl) * U; q0 < total; q0 += gridDim.x * 4 * U) {
+    float acc[U][8];
+    const float* gp[U];
+    int hh[U], ww[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned q = min(q0 + u, total - 1);
+      const unsigned b = q / HW, rem = q - b * HW;
+      hh[u] = static_cast<int>(rem / W);
+      ww[u] = static_cast<int>(rem - static_cast<unsigned>(hh[u]) * W);
+      gp[u] = g + static_cast<size_t>(b) * Ho * Wo;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[u][e] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < kWideT; ++t) {
+      const float4 wa = s_w[t][0][cg], wb = s_w[t][1][cg];
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int oh = hh[u] - taps.dh[t], ow = ww[u] - taps.dw[t];
+        const float gv = (oh >= 0 && oh < Ho && ow >= 0 && ow < Wo) ? __ldg(gp[u] + oh * Wo + ow) : 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[u][e] = fmaf(gv, wv[e], acc[u][e]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (q0 + u < total) vstore8(dx + static_cast<size_t>(q0 + u) * kWideC + cg * 8, acc[u]);
+  }
+}
+
+// partial[block][t][c] = sum over the block's input pixels q of x[q][c] * g[q - d_t];  partial_b[block] = its share of sum g.
+// Block = 64 channel groups x 2 tap halves x 2 pixel lanes: a thread keeps 8 taps x 8 channels of accumulators (with all
+// 16 taps per thread: 169 registers, one block per SM, 185 us).
+__global__ void __launch_bounds__(256, 2)
+to1_wide_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, const float* __restrict__ g, int Ho, int Wo,
+                      To1Taps taps, float* __restrict__ partial, float* __restrict__ partial_b) {
+  extern __shared__ float s_wide[];                         // dynamic: [kWideT][kWideC] sums of pixel lane 1 + 8 floats
+  float* s_b = s_wide + kWideT * kWideC;
+  const int cg = threadIdx.x & 63, th = (threadIdx.x >> 6) & 1, pl = threadIdx.x >> 7;
+  float acc[8][8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
+  const unsigned total = static_cast<unsigned>(B) * H * W, HW = static_cast<unsigned>(H) * W;
+  const unsigned per = (total + gridDim.x - 1) / gridDim.x;      // contiguous pixel range per block
+  const unsigned q_begin = blockIdx.x * per, q_end = min(total, q_begin + per);
+  for (unsigned q = q_begin + pl; q < q_end; q += 2) {
+    const unsigned b = q / HW, rem = q - b * HW;
+    const int h = static_cast<int>(rem / W), w = static_cast<int>(rem - static_cast<unsigned>(h) * W);
+    const float* gb = g + static_cast<size_t>(b) * Ho * Wo;
+    float xv[8];
+    vload8(x + static_cast<size_t>(q) * kWideC + cg * 8, xv);
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) {
+      // both tap halves are unrolled with compile-time tap indices; `th` selects at run time (uniform per warp)
+      const int dh = th ? taps.dh[8 + tt] : taps.dh[tt], dw = th ? taps.dw[8 + tt] : taps.dw[tt];
+      const int oh = h - dh, ow = w - dw;
+      const float gv = (oh >= 0 && oh < Ho && ow >= 0 && ow < Wo) ? __ldg(gb + oh * Wo + ow) : 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[tt][e] = fmaf(gv, xv[e], acc[tt][e]);
+    }
+  }
+  if (pl == 1) {
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s_wide[(th * 8 + tt) * kWideC + cg * 8 + e] = acc[tt][e];
+  }
+  // bias gradient: this block's contiguous share of sum g
+  const unsigned gtot = static_cast<unsigned>(B) * Ho * Wo, gper = (gtot + gridDim.x - 1) / gridDim.x;
+  float gs = 0.f;
+  for (unsigned i = blockIdx.x * gper + threadIdx.x; i < min(gtot, (blockIdx.x + 1) * gper); i += 256) gs += __ldg(g + i);
+  gs = warp_sum(gs);
+  if ((threadIdx.x & 31) == 0) s_b[threadIdx.x >> 5] = gs;
+  __syncthreads();
+  if (pl == 0) {
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt)
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        partial[(static_cast<size_t>(blockIdx.x) * kWideT + th * 8 + tt) * kWideC + cg * 8 + e] =
+            acc[tt][e] + s_wide[(th * 8 + tt) * kWideC + cg * 8 + e];
+  }
+  if (threadIdx.x == 0 && partial_b != nullptr) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += s_b[q];
+    partial_b[blockIdx.x] = v;
+  }
+}
+
+static bool wide_shape(int C, int ntaps, long pixels) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("TG_NO_WIDE_TO1"); off = (e && e[0] == '1') ? 1 : 0; }
+  return off == 0 && C == kWideC && ntaps == kWideT && pixels < (1L << 31);
 }
 
 static int fill_taps(To1Taps* t, int ncls, const int* count, const int8_t* dh, const int8_t* dw) {
@@ -915,6 +1120,16 @@ extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, 
     if (rc == 0) return 0;
     TG_REQUIRE(rc == -1, "tg_conv_to1_fwd: tensor-core path failed (%d)", rc);     // -1: shape not covered, fall through
   }
+  if (ncls == 1 && !x_split && mode == 0 && wide_shape(C, cls_count[0], static_cast<long>(B) * H * W) && scratch != nullptr &&
+      scratch_floats >= static_cast<size_t>(kWideT) * B * H * W) {
+    const long total = static_cast<long>(B) * H * W;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    to1_wide_tapdot_kernel<<<dc_grid(total * 8, 256, 4), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), total, wgt, scratch);
+    TG_CHECK_CUDA(cudaGetLastError());
+    TG_REQUIRE(to1_tapsum_launch(scratch, total, 0, B, H, W, taps, bias, Ho, Wo, mode, mask, xin, out, sig_out, st) == 0,
+               "tg_conv_to1_fwd: tap sum failed");
+    return 0;
+  }
   Tap3x3 tp;
   if (ncls == 1 && C == 64 && !x_split && Ho == H && Wo == W && make_tap3x3(&tp, cls_count[0], tap_dh, tap_dw)) {
     const long tiles = static_cast<long>(B) * ((H + kT1H - 1) / kT1H) * ((W + kT1W - 1) / kT1W);
@@ -944,6 +1159,7 @@ extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, 
 }
 
 extern "C" size_t tg_conv_to1_fwd_scratch_floats(int B, int H, int W, int C, int ntaps) {
+  if (tg::wide_shape(C, ntaps, static_cast<long>(B) * H * W)) return static_cast<size_t>(ntaps) * B * H * W;
   if (C != 64 || ntaps < 1 || ntaps > 32) return 0;
   return static_cast<size_t>(ntaps) * B * H * W;
 }
@@ -956,6 +1172,13 @@ extern "C" int tg_conv_to1_bwd_data(const float* g, int B, int Ho, int Wo, const
   To1Taps taps;
   TG_REQUIRE(fill_taps(&taps, 1, &ntaps, tap_dh, tap_dw) > 0, "tg_conv_to1_bwd_data: bad tap table");
   const long total = static_cast<long>(B) * H * W * (C / 8);
+  if (wide_shape(C, ntaps, static_cast<long>(B) * H * W)) {
+    const long px = static_cast<long>(B) * H * W;
+    to1_wide_bwd_data_kernel<<<dc_grid(px, 16, 6), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        g, B, Ho, Wo, wgt, taps, H, W, reinterpret_cast<__nv_bfloat16*>(dx));
+    TG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   Tap3x3 tp;
   if (thin_mma_enabled() && C == 64 && Ho == H && Wo == W && make_tap3x3(&tp, ntaps, tap_dh, tap_dw) &&
       static_cast<long>(B) * H * W < (1L << 31)) {
@@ -999,6 +1222,19 @@ extern "C" int tg_conv_to1_wgrad(const void* x, int B, int H, int W, int C, cons
   TG_REQUIRE(gx >= 1, "tg_conv_to1_wgrad: rows_cap must be >= 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+  if (wide_shape(C, ntaps, static_cast<long>(B) * H * W)) {
+    int gw = 4 * num_sms();
+    if (gw > rows_cap) gw = rows_cap;
+    const long px = static_cast<long>(B) * H * W;
+    if (gw > px) gw = static_cast<int>(px);
+    constexpr int kSmem = kWideT * kWideC * 4 + 64;
+    TG_SET_SMEM_ONCE((to1_wide_wgrad_kernel), kSmem);
+    to1_wide_wgrad_kernel<<<gw, 256, kSmem, st>>>(xx, B, H, W, g, Ho, Wo, taps, partial, partial_b);
+    TG_CHECK_CUDA(cudaGetLastError());
+    conv_to1_wgrad_reduce_kernel<<<(ntaps * C + 31) / 32, 256, 0, st>>>(partial, partial_b, gw, ntaps, C, dw, db, accumulate);
+    TG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   Tap3x3 tp;
   if (thin_mma_enabled() && C == 64 && Ho == H && Wo == W && make_tap3x3(&tp, ntaps, tap_dh, tap_dw) &&
       static_cast<long>(B) * H * W < (1L << 31) && rows_cap * 9 / 19 >= 1) {
@@ -1022,7 +1258,7 @@ extern "C" int tg_conv_to1_wgrad(const void* x, int B, int H, int W, int C, cons
     if (g3 > rows_cap) g3 = rows_cap;
     conv3x3_c64_to1_wgrad_kernel<<<g3, 256, 0, st>>>(xx, B, H, W, g, tp, partial, partial_b);
     TG_CHECK_CUDA(cudaGetLastError());
-    conv_to1_wgrad_reduce_kernel<<<(ntaps * C + 127) / 128, 128, 0, st>>>(partial, partial_b, g3, ntaps, C, dw, db,
+    conv_to1_wgrad_reduce_kernel<<<(ntaps * C + 31) / 32, 256, 0, st>>>(partial, partial_b, g3, ntaps, C, dw, db,
                                                                          accumulate);
     TG_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -1032,7 +1268,7 @@ extern "C" int tg_conv_to1_wgrad(const void* x, int B, int H, int W, int C, cons
   else if (ntaps == 16) conv_to1_wgrad_kernel<16><<<grid, 128, 0, st>>>(xx, B, H, W, C, g, Ho, Wo, taps, partial, partial_b);
   else TG_REQUIRE(false, "tg_conv_to1_wgrad: unsupported tap count %d (supported: 9, 16)", ntaps);
   TG_CHECK_CUDA(cudaGetLastError());
-  conv_to1_wgrad_reduce_kernel<<<(ntaps * C + 127) / 128, 128, 0, st>>>(partial, partial_b, gx, ntaps, C, dw, db,
+  conv_to1_wgrad_reduce_kernel<<<(ntaps * C + 31) / 32, 256, 0, st>>>(partial, partial_b, gx, ntaps, C, dw, db,
                                                                        accumulate);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1149,7 +1385,7 @@ extern "C" int tg_conv_to1_wgrad_f32(const void* x, int B, int H, int W, int C, 
   else if (ntaps == 16) conv_to1_wgrad_kernel<16, float><<<grid, 128, 0, st>>>(xx, B, H, W, C, g, Ho, Wo, taps, partial, partial_b);
   else TG_REQUIRE(false, "tg_conv_to1_wgrad_f32: unsupported tap count %d (supported: 9, 16)", ntaps);
   TG_CHECK_CUDA(cudaGetLastError());
-  conv_to1_wgrad_reduce_kernel<<<(ntaps * C + 127) / 128, 128, 0, st>>>(partial, partial_b, gx, ntaps, C, dw, db,
+  conv_to1_wgrad_reduce_kernel<<<(ntaps * C + 31) / 32, 256, 0, st>>>(partial, partial_b, gx, ntaps, C, dw, db,
                                                                        accumulate);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -838,6 +838,20 @@ int to1_fwd_mma(const void* x, int x_split, int B, int H, int W, const float* wg
   return 0;
 }
 
+// step 2 alone, for callers that produced T themselves (direct_conv.cu: the 512 -> 1 convolution of D model[11])
+int to1_tapsum_launch(const float* T, long total_in, int x_split, int B, int H, int W, const To1Taps& taps,
+                      const float* bias, int Ho, int Wo, int mode, const uint8_t* mask, const float* xin, float* out,
+                      float* sig_out, cudaStream_t st) {
+  const long M = static_cast<long>(B) * Ho * Wo;
+  if (total_in >= (1L << 31) || M >= (1L << 31)) return -1;
+  long g2 = (M + 255) / 256;
+  if (g2 > 16L * num_sms()) g2 = 16L * num_sms();
+  tapsum_kernel<<<static_cast<int>(g2), 256, 0, st>>>(T, static_cast<unsigned>(total_in), x_split, B, H, W, taps, bias, Ho, Wo,
+                                                     mode, mask, xin, out, sig_out);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 bool thin_mma_enabled() {
   static int on = -1;
   if (on < 0) {

@@ -65,4 +65,8 @@ int to1_fwd_mma(const void* x, int x_split, int B, int H, int W, const float* wg
 int rowgemm_dispatch(int k, const RowGemmParams& p, int grid_cap, int* grid_used, cudaStream_t st);
 bool thin_mma_enabled();   // env TG_NO_THIN_MMA=1 selects the CUDA-core kernels (A/B timing only)
 
+int to1_tapsum_launch(const float* T, long total_in, int x_split, int B, int H, int W, const To1Taps& taps,
+                      const float* bias, int Ho, int Wo, int mode, const uint8_t* mask, const float* xin, float* out,
+                      float* sig_out, cudaStream_t st);
+
 }  // namespace tg

@@ -207,9 +207,11 @@ def test_final_conv_sigmoid_composite_and_backward():
     assert rel_err(dw, dw_ref) < 2e-3 and rel_err(db, db_ref) < 2e-3
 
 
-def test_d11_conv_and_backward():
+@pytest.mark.parametrize("B,H", [(2, 8), (3, 32), (1, 5), (7, 9)])
+def test_d11_conv_and_backward(B, H):
+    """Discriminator model[11] (512 -> 1, 4x4): the wide kernels of direct_conv.cu incl. ragged pixel counts."""
     torch.manual_seed(8)
-    B, H, C = 2, 8, 512
+    C = 512
     x = torch.randn(B, C, H, H, device=DEV).bfloat16().float().requires_grad_(True)
     w = (torch.randn(1, C, 4, 4, device=DEV) / 90).requires_grad_(True)
     b = torch.randn(1, device=DEV).requires_grad_(True)
