@@ -15,6 +15,8 @@
 //           over (g, z); tg_bn_bwd_finalize produces dgamma, dbeta, the conv-bias gradient and the
 //           per-channel coefficients; tg_bn_bwd_apply writes gz = dL/d(conv+bias) (bf16), which
 //           the dgrad / wgrad tensor-core kernels consume.
+#include <stdlib.h>
+
 #include "tg_common.cuh"
 #include "../../include/terragan_b200.h"
 
@@ -187,7 +189,11 @@ using GradSrc = GradSrcT<__nv_bfloat16>;
 // registers, the loads in flight are bounded by the register file (measured: 2.1 TB/s for the reduce). Here each
 // thread keeps kRing pixels in flight through cp.async into its own shared-memory slots (no cross-thread
 // sharing, so cp.async.wait_group is the only synchronisation) and the registers only hold the pixel in use.
-constexpr int kRing = 4;
+
+// ring depth per kernel and storage type. Measured on dec1 (1.07 G elements, B = 64): 4 slots 1124 / 1137 us (reduce /
+// apply), 8 / 6 slots 1183 / 1291 us — the larger ring costs more in occupancy than it gains in bytes in flight.
+template <typename T> constexpr int ring_reduce() { return 4; }
+template <typename T> constexpr int ring_apply() { return 4; }
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
@@ -206,7 +212,7 @@ __device__ __forceinline__ void unpack8(const __nv_bfloat16* slot, float (&f)[8]
 __device__ __forceinline__ void unpack8(const float* slot, float (&f)[8]) { vload8(slot, f); }
 // Streams (g0 [+ g1], z, ratio) of pixels p = first, first + stride, ... < M to `body(p, g[8], z[8], r)`.
 // ring: kRing * 3 * blockDim.x uint4 of shared memory.
-template <typename T, typename Body>
+template <typename T, int kRing, typename Body>
 __device__ __forceinline__ void stream_grad_z(const GradSrcT<T>& s0, const GradSrcT<T>& s1, const T* __restrict__ z,
                                               unsigned M, int C, int H, int W, int c, unsigned first, unsigned stride,
                                               const uint8_t* __restrict__ code, const float* __restrict__ lut,
@@ -262,7 +268,7 @@ __device__ __forceinline__ void stream_grad_z(const GradSrcT<T>& s0, const GradS
 
 // sums per channel over all pixels: [0] g', [1] g'*z, [2] r*g', [3] r*z, [4] r   (g' = g * act'(z*scale+shift))
 // block = 256 threads = (C/8 channel vectors) x (256/(C/8) pixel lanes); partial[block][5][C]
-template <typename T>
+template <typename T, int kR>
 __global__ void bn_bwd_reduce_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, long M,
                                      int C, int H, int W, const float* __restrict__ scale,
                                      const float* __restrict__ shift, int act, float slope,
@@ -282,7 +288,7 @@ __global__ void bn_bwd_reduce_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __
   float sc[8], sh[8];
   ldg8f(scale + c, sc);
   ldg8f(shift + c, sh);
-  stream_grad_z(s0, s1, z, static_cast<unsigned>(M), C, H, W, c, blockIdx.x * lanes + my_lane, gridDim.x * lanes, code, lut,
+  stream_grad_z<T, kR>(s0, s1, z, static_cast<unsigned>(M), C, H, W, c, blockIdx.x * lanes + my_lane, gridDim.x * lanes, code, lut,
                 reinterpret_cast<uint4*>(red), [&](unsigned, const float (&g)[8], const float (&zz)[8], float r) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
@@ -359,7 +365,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, doubl
 
 // gz[p][c] = r[p] * scale[c] * (g' - c1[c] - zhat * c2[c]) = r[p] * (A[c]*g' + Bz[c]*z + Cc[c])
 // Channel-stationary like bn_apply_kernel: the five per-channel coefficients live in registers.
-template <typename T>
+template <typename T, int kR>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, unsigned M, int C, int H, int W,
                     const float* __restrict__ shift, const float* __restrict__ coeff, int act, float slope,
@@ -385,7 +391,7 @@ bn_bwd_apply_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, uns
     }
   }
   extern __shared__ uint4 apply_ring[];
-  stream_grad_z(s0, s1, z, M, C, H, W, static_cast<int>(c), blockIdx.x * lanes + lane, gridDim.x * lanes, code, lut, apply_ring,
+  stream_grad_z<T, kR>(s0, s1, z, M, C, H, W, static_cast<int>(c), blockIdx.x * lanes + lane, gridDim.x * lanes, code, lut, apply_ring,
                 [&](unsigned p, const float (&g)[8], const float (&zz)[8], float r) {
                   float o[8];
 #pragma unroll
@@ -406,6 +412,13 @@ static int ew_grid(long n, int block) {
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return static_cast<int>(g);
+}
+
+// experiment switch: TG_BN_RING_REDUCE / TG_BN_RING_APPLY = 2 select a shallower ring (A/B timing)
+static int ring_override(const char* name, int dflt) {
+  const char* e = getenv(name);
+  if (e == nullptr) return dflt;
+  return atoi(e) == 2 ? 2 : dflt;
 }
 
 template <typename T>
@@ -459,14 +472,20 @@ static int bn_bwd_reduce_impl(const tg_grad_src* g0, const tg_grad_src* g1, cons
   TG_REQUIRE(grid >= 1, "tg_bn_bwd_reduce: rows_cap must be >= 1");
   *rows_used = static_cast<int>(grid);
   size_t smem = static_cast<size_t>(lanes) * cv * 40 * sizeof(float);
-  const size_t ring_bytes = static_cast<size_t>(kRing) * 3 * 256 * 8 * sizeof(T);
+  constexpr int kR = ring_reduce<T>();
+  const int ring = ring_override("TG_BN_RING_REDUCE", kR);
+  const size_t ring_bytes = static_cast<size_t>(ring) * 3 * 256 * 8 * sizeof(T);
   if (smem < ring_bytes) smem = ring_bytes;
-  {
-    TG_SET_SMEM_ONCE((bn_bwd_reduce_kernel<T>), 100 * 1024);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define TG_LAUNCH_REDUCE(R)                                                                                          \
+  {                                                                                                                  \
+    TG_SET_SMEM_ONCE((bn_bwd_reduce_kernel<T, R>), 100 * 1024);                                                      \
+    bn_bwd_reduce_kernel<T, R><<<static_cast<int>(grid), 256, smem, st>>>(to_src<T>(g0), to_src<T>(g1),              \
+        reinterpret_cast<const T*>(z), M, C, H, W, scale, shift, act, slope, code, lut_dev, partial);                \
   }
-  bn_bwd_reduce_kernel<T><<<static_cast<int>(grid), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      to_src<T>(g0), to_src<T>(g1), reinterpret_cast<const T*>(z), M, C, H, W, scale, shift, act, slope, code, lut_dev,
-      partial);
+  if (ring == kR) TG_LAUNCH_REDUCE(kR)
+  else TG_LAUNCH_REDUCE(2)
+#undef TG_LAUNCH_REDUCE
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -479,12 +498,19 @@ static int bn_bwd_apply_impl(const tg_grad_src* g0, const tg_grad_src* g1, const
   TG_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "tg_bn_bwd_apply: unsupported C=%d", C);
   TG_REQUIRE(!code || lut_dev, "tg_bn_bwd_apply: code needs a device LUT");
   const long M = static_cast<long>(B) * H * W;
-  {
-    TG_SET_SMEM_ONCE((bn_bwd_apply_kernel<T>), 100 * 1024);
+  constexpr int kR = ring_apply<T>();
+  const int ring = ring_override("TG_BN_RING_APPLY", kR);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define TG_LAUNCH_APPLY(R)                                                                                           \
+  {                                                                                                                  \
+    TG_SET_SMEM_ONCE((bn_bwd_apply_kernel<T, R>), 100 * 1024);                                                       \
+    bn_bwd_apply_kernel<T, R><<<ew_grid(M * (C / 8), 256), 256, R * 3 * 256 * 8 * sizeof(T), st>>>(                  \
+        to_src<T>(g0), to_src<T>(g1), reinterpret_cast<const T*>(z), static_cast<unsigned>(M), C, H, W, shift, coeff, act,  \
+        slope, code, lut_dev, reinterpret_cast<T*>(gz));                                                             \
   }
-  bn_bwd_apply_kernel<T><<<ew_grid(M * (C / 8), 256), 256, kRing * 3 * 256 * 8 * sizeof(T), reinterpret_cast<cudaStream_t>(stream)>>>(
-      to_src<T>(g0), to_src<T>(g1), reinterpret_cast<const T*>(z), static_cast<unsigned>(M), C, H, W, shift, coeff, act, slope,
-      code, lut_dev, reinterpret_cast<T*>(gz));
+  if (ring == kR) TG_LAUNCH_APPLY(kR)
+  else TG_LAUNCH_APPLY(2)
+#undef TG_LAUNCH_APPLY
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

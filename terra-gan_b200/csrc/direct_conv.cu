@@ -252,11 +252,17 @@ conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ xm
       }
     }
   }
-  __syncthreads();
+  // the eight warps add their sums one after the other: a fixed order, so the result is run-to-run reproducible
+  // (shared-memory float atomics made it order-dependent)
+  for (int wq = 0; wq < 8; ++wq) {
+    __syncthreads();
+    if (warp == wq) {
 #pragma unroll
-  for (int t = 0; t <= T; ++t) {
-    atomicAdd(&s_red[2 * lane][t], acc[t][0]);
-    atomicAdd(&s_red[2 * lane + 1][t], acc[t][1]);
+      for (int t = 0; t <= T; ++t) {
+        s_red[2 * lane][t] += acc[t][0];
+        s_red[2 * lane + 1][t] += acc[t][1];
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * (T + 1); i += 256)
@@ -505,12 +511,17 @@ conv3x3_c64_to1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, 
       }
     }
   }
-  __syncthreads();
+  // the 32 pixel groups add their sums in a fixed order (deterministic; no float atomics)
+  for (int gq = 0; gq < 32; ++gq) {
+    __syncthreads();
+    if (grp == gq) {
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+      for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&s_red[t][sub * 8 + j], acc[t][j]);
-  if (sub == 0) atomicAdd(&s_b, gsum);
+        for (int j = 0; j < 8; ++j) s_red[t][sub * 8 + j] += acc[t][j];
+      if (sub == 0) s_b += gsum;
+    }
+  }
   __syncthreads();
   // s_red is indexed by spatial offset (dh+1)*3+(dw+1); emit in the caller's tap order
   for (int i = threadIdx.x; i < 9 * 64; i += 256) {
@@ -746,11 +757,17 @@ conv_to1_wgrad_kernel(const TX* __restrict__ x, int B, int H, int W, int C, cons
       for (int q = 0; q < 8; ++q) acc[t][q] += gv * f[q];
     }
   }
+  // the 16 pixel groups add their sums in a fixed order (deterministic; no float atomics)
+  for (int gq = 0; gq < 16; ++gq) {
+    __syncthreads();
+    if (grp == gq) {
 #pragma unroll
-  for (int t = 0; t < T; ++t)
+      for (int t = 0; t < T; ++t)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&s_red[t][sub * 8 + j], acc[t][j]);
-  if (sub == 0) atomicAdd(&s_b, gsum);
+        for (int j = 0; j < 8; ++j) s_red[t][sub * 8 + j] += acc[t][j];
+      if (sub == 0) s_b += gsum;
+    }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < T * 64; i += 128) {
     const int t = i / 64, c = i % 64;

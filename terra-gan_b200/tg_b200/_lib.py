@@ -197,6 +197,9 @@ KERNELS_PER_CALL = {
     "tg_maxpool2_bwd": 1, "tg_conv_c1_fwd": 1, "tg_conv_c1_wgrad": 2, "tg_conv_to1_fwd": 1, "tg_conv_to1_fwd+tapsum": 1, "tg_conv_to1_fwd_scratch_floats": 0,
     "tg_conv_to1_bwd_data": 1, "tg_conv_to1_wgrad": 2, "tg_final_bwd_pre": 1, "tg_inpaint_loss_fwd": 2,
     "tg_inpaint_loss_bwd": 1, "tg_l1_bf16_fwd": 2, "tg_l1_bf16_bwd": 1, "tg_bce_logits_fwd": 1, "tg_bce_logits_bwd": 1,
+    "tg_quality_metrics": 2, "tg_resize_bilinear_u8": 2, "tg_dsm_normalize": 2, "tg_resize_ksize": 0, "tg_resize_coeffs": 0,
+    "tg_l1_f32_fwd": 2, "tg_conv_c1_wgrad_f32": 2, "tg_conv_to1_wgrad_f32": 2, "tg_wgrad_partial_floats": 0,
+    "tg_wgrad_partial_floats_f32": 0,
 }
 
 

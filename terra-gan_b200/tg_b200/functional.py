@@ -40,6 +40,17 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
                            "kernels only and has no CPU fallback (move the module and its inputs to a CUDA device)")
 
 
+def _check_versions(ctx, what: str) -> None:
+    """The weights are read again in backward (packed dgrad operands): autograd's own saved-tensor version check does
+    not see them, so an optimizer step between forward and backward is caught here instead of silently using the
+    new weights."""
+    for name, p, v in zip(ctx.names, ctx.params.values(), ctx.versions):
+        if p._version != v:
+            raise RuntimeError(f"{what}: parameter {name} was modified in place between forward and backward "
+                               f"(version {v} -> {p._version}); one of the variables needed for gradient computation "
+                               "has been modified by an inplace operation")
+
+
 class GeneratorFn(torch.autograd.Function):
     """PConvUNet.forward — generator.py:31-62."""
 
@@ -54,12 +65,14 @@ class GeneratorFn(torch.autograd.Function):
                                          getattr(module, "_trace", None))
         ctx.module, ctx.names, ctx.save = module, names, save
         ctx.params = params
+        ctx.versions = [p._version for p in plist]
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         if ctx.save is None:
             raise RuntimeError("PConvUNet: backward called but no state was saved")
+        _check_versions(ctx, "PConvUNet")
         if ctx.needs_input_grad[0]:
             raise NotImplementedError("PConvUNet (B200 path): gradient w.r.t. the input image is not implemented "
                                       "(no caller on the reference path needs it: train.py:181-185)")
@@ -81,10 +94,12 @@ class DiscriminatorFn(torch.autograd.Function):
         with torch.no_grad():
             out = module._engine.forward(img, params, module._bn_params(), module.training, save)
         ctx.module, ctx.names, ctx.save, ctx.params = module, names, save, params
+        ctx.versions = [p._version for p in plist]
         return out
 
     @staticmethod
     def backward(ctx, g):
+        _check_versions(ctx, "Discriminator")
         need_p = any(ctx.needs_input_grad[3:])
         with torch.no_grad():
             g_img, grads = ctx.module._engine.backward(g.contiguous(), ctx.params, ctx.save, ctx.needs_input_grad[0],

@@ -91,6 +91,11 @@ def _prof_end(kind: str, flops: float, ev0, shape: str = "") -> None:
 def _req(t: torch.Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor — the TERRA-GAN hot path has no CPU fallback")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device's stream and the library caches per-device state by cudaGetDevice()
+        raise RuntimeError(f"{name}: tensor lives on cuda:{t.device.index} but the current device is "
+                           f"cuda:{torch.cuda.current_device()} — call torch.cuda.set_device() (or use "
+                           "`with torch.cuda.device(...)`) before running the TERRA-GAN modules on another GPU")
     if t.dtype != dtype:
         raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():

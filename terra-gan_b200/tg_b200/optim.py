@@ -43,7 +43,8 @@ class Adam(torch.optim.Optimizer):
         self._packs: Dict[int, object] = {}
         for m in (modules or []):
             self._packs.update(_conv_packs(m))
-        self._index: Dict[int, tuple] = {}      # id(param) -> (dst_fprop, dst_dgrad) int32 scatter indices
+        self._index: Dict[tuple, tuple] = {}    # (id(param), device) -> (dst_fprop, dst_dgrad) int32 scatter indices
+        self.kernel_launches = 0                # kernels launched by step() so far (bench.py reads and resets it)
 
     def attach(self, module) -> None:
         """Also refresh the packed weights of this drop-in module's tensor-core convolutions."""
@@ -57,7 +58,8 @@ class Adam(torch.optim.Optimizer):
                 loss = closure()
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
-            entries, touched, step_no = [], [], None
+            by_step, touched = {}, []      # one launch per distinct step count (a parameter whose grad was None on some
+            #                                steps, or a loaded state_dict with differing steps, lags behind the others)
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -71,32 +73,27 @@ class Adam(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
                 s = int(st["step"].item())          # host tensor: no device synchronisation
-                if step_no is None:
-                    step_no = s
-                elif s != step_no:
-                    raise RuntimeError("tg_b200.optim.Adam: parameters of one group must share the step count")
                 e = AdamTensor()
                 e.param, e.grad, e.exp_avg, e.exp_avg_sq = ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"])
                 e.n = p.numel()
                 pk = self._packs.get(id(p))
                 if pk is not None:
                     wf, wd = pk.w_fprop(p), pk.w_dgrad(p)       # builds the packed copies on first use
-                    idx = self._index.get(id(p))
+                    ikey = (id(p), str(p.device))              # the module may have been moved since the last step
+                    idx = self._index.get(ikey)
                     if idx is None:
                         idx = (P.pack_scatter_index(p.shape, None, p.device), P.pack_scatter_index(p.shape, pk.dplan, p.device))
-                        self._index[id(p)] = idx
+                        self._index[ikey] = idx
                     e.packed_fprop, e.dst_fprop, e.packed_dgrad, e.dst_dgrad = ptr(wf), ptr(idx[0]), ptr(wd), ptr(idx[1])
                     touched.append((pk, p))
-                entries.append((e, g))
-            if not entries:
+                by_step.setdefault(s, []).append((e, g))
+            if not by_step:
                 continue
-            arr = (AdamTensor * len(entries))(*[e for e, _ in entries])
-            check(lib().tg_adam_repack(arr, len(entries), float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
-                                       step_no, stream_ptr()), "tg_adam_repack")
-            extra = (len(entries) + 23) // 24 - 1          # one kernel per 24 tensors: keep bench.py's launch count exact
-            if extra > 0:
-                from . import _lib
-                _lib.CALLS["tg_adam_repack+groups"] = _lib.CALLS.get("tg_adam_repack+groups", 0) + extra
+            for step_no, entries in sorted(by_step.items()):
+                arr = (AdamTensor * len(entries))(*[e for e, _ in entries])
+                check(lib().tg_adam_repack(arr, len(entries), float(group["lr"]), float(beta1), float(beta2),
+                                           float(group["eps"]), step_no, stream_ptr()), "tg_adam_repack")
+                self.kernel_launches += (len(entries) + 23) // 24       # one kernel per 24 tensors (bench.py counts launches)
             for pk, p in touched:
                 torch.autograd.graph.increment_version(p)       # the master changed behind autograd's back
                 pk.mark_fresh(p)                                # ... and its packed copies are already current
