@@ -263,7 +263,8 @@ class PConv2dFn(torch.autograd.Function):
                 ops.conv_c1_wgrad(xin, m8, k, s, p, gz, False, dw, None)
                 if ctx.needs_input_grad[0]:
                     dpl = pk.dplan
-                    wt = weight.reshape(cout, k * k)[:, dpl.kpos].t().contiguous()
+                    from .layers import index_dev
+                    wt = weight.reshape(cout, k * k).index_select(1, index_dev(dpl.kpos, weight.device)).t().contiguous()
                     taps = [(dh, dw_) for (_, dh, dw_) in dpl.taps]
                     counts = [c for (_, c, _, _) in dpl.subs]
                     ho, wo = ssum.shape[1], ssum.shape[2]

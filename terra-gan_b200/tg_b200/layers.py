@@ -120,6 +120,17 @@ class ConvPack:
 
 _MASK01 = [0.0, 1.0]
 _mask01_dev: Dict[str, torch.Tensor] = {}
+_index_dev: Dict[tuple, torch.Tensor] = {}
+
+
+def index_dev(idx, device) -> torch.Tensor:
+    """Cached device LongTensor of a constant Python index list. Indexing a CUDA tensor with a Python list uploads
+    the list from pageable memory on EVERY call and synchronises the stream — two such lookups in the backward pass
+    kept the host from running ahead of the GPU (a ~2 ms bubble per train step)."""
+    key = (tuple(idx), str(device))
+    if key not in _index_dev:
+        _index_dev[key] = torch.tensor(list(idx), dtype=torch.long, device=device)
+    return _index_dev[key]
 
 
 def mask01_dev(device) -> torch.Tensor:
@@ -507,7 +518,7 @@ class DiscriminatorEngine:
         g_img = None
         if need_input_grad:
             w0 = params["model.0.weight"].reshape(64, 16)
-            wt0 = w0[:, self.d0_plan.kpos].t().contiguous()
+            wt0 = w0.index_select(1, index_dev(self.d0_plan.kpos, w0.device)).t().contiguous()
             g_img, _ = ops.conv_to1_fwd(gz0, True, (H // 2, W // 2), wt0, self.d0_counts, self.d0_taps, None, (H, W))
             g_img = g_img.reshape(B, 1, H, W)
         return g_img, grads
@@ -587,6 +598,6 @@ class VggEngine:
             else:
                 gz, _ = ops.conv_igemm(gz, wd, pk.dplan, (h, w), gate=ys[pi], gate_slope=0.0)
         w0 = self._w0_folded(vgg["0.weight"])
-        wt0 = w0[:, self.d_kpos].t().contiguous()
+        wt0 = w0.index_select(1, index_dev(self.d_kpos, w0.device)).t().contiguous()
         g_img, _ = ops.conv_to1_fwd(gz[:, 0], False, (H, W), wt0, [9], self.d_taps, None, (H, W))
         return g_img.reshape(-1, 1, H, W)
