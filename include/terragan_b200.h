@@ -115,8 +115,14 @@ typedef struct tg_conv_args {
   const float* addend;      /* F32 only, or NULL: fp32 tensor of out's shape added to the accumulator before bias / ratio /
                                statistics (tf32x3: the lo*hi + hi*lo cross terms computed by a first launch, so that the
                                long hi*hi accumulation chain is not lengthened by them) */
+  void* pool_out;           /* bf16 [B][Ho/2][Wo/2][N] or NULL: also write the 2x2 max-pool of the (activated) output —
+                               nn.MaxPool2d(2,2) of VGG16 features[4], [9] (losses.py:31-32) fused into the conv epilogue.
+                               Only where tg_conv_pool_fusable() says so (the halo-reuse kernels) */
+  int32_t skip_out;         /* with pool_out: do not store the full-resolution output (`out` may then be NULL) */
 } tg_conv_args;
 int tg_conv_igemm(tg_conv_args* args, void* stream);
+/* 1 if tg_conv_igemm would accept `pool_out` for these arguments (shape / dtype / kernel family), else 0. */
+int tg_conv_pool_fusable(const tg_conv_args* args);
 
 /* Weight gradient of the same convolutions (autograd of pconv.py:30 / discriminator.py:11):
  *   partial[s][(tap, c)][n] = sum over the s-th share of output pixels of x[pix (+) tap][c] * g[pix][n]

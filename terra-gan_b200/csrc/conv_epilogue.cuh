@@ -260,7 +260,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
           // (no shuffles, no validity mask on the store path)
           const int rr = q * 32 + row;
           const long pix2 = box_pix + static_cast<long>(rr >> 3) * p.Wo + (rr & 7);
-          if (!TG_DBG(p, 1)) *reinterpret_cast<uint4*>(p.out + pix2 * p.Cout + col0 + chunk * 8) = val;
+          if (!TG_DBG(p, 1) && !p.skip_out) *reinterpret_cast<uint4*>(p.out + pix2 * p.Cout + col0 + chunk * 8) = val;
         } else {
           // pixel index of the row this lane stores: held by lane `row` of the warp
           const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(pix & 0xffffffffu), row);
@@ -269,6 +269,41 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, int q, 
             const long pix2 = static_cast<long>((static_cast<unsigned long long>(hi) << 32) | lo);
             *reinterpret_cast<uint4*>(p.out + pix2 * p.Cout + col0 + chunk * 8) = val;
           }
+        }
+      }
+      if (kBox8 && p.pool_out != nullptr) {
+        // fused nn.MaxPool2d(2, 2) (VGG16 features[4] / [9], losses.py:31-32): this warp's staging tile holds 4 tile rows x 8
+        // columns of pixels (row = 8 * tile_row + col), i.e. 2 x 4 pooled pixels; every lane takes one (pooled pixel,
+        // 16-byte channel chunk) and reduces its four source rows straight out of shared memory
+        constexpr int kItems = 8 * kLPR;                     // pooled pixels x chunks held by the tile
+#pragma unroll
+        for (int it = 0; it < kItems / 32; ++it) {
+          const int item = it * 32 + lane;
+          const int pp = item / kLPR, chunk = item % kLPR;
+          const int r00 = (pp >> 2) * 16 + (pp & 3) * 2;
+          uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int srow = r00 + (s4 & 1) + (s4 >> 1) * 8;
+            const int key = (kSC == 64) ? (srow & 7) : ((srow >> 1) & 3);
+            const uint4 v4 = *reinterpret_cast<const uint4*>(stage + srow * kRowBytes + ((chunk ^ key) << 4));
+            if (s4 == 0) {
+              m4 = v4;
+            } else {
+              const uint32_t a[4] = {m4.x, m4.y, m4.z, m4.w}, b[4] = {v4.x, v4.y, v4.z, v4.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a[e]),
+                                                  *reinterpret_cast<const __nv_bfloat162*>(&b[e]));
+                o[e] = *reinterpret_cast<const uint32_t*>(&r2);
+              }
+              m4 = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          const int ph = (th * p.Ht >> 1) + 2 * q + (pp >> 2), pw = (tw * p.Wt >> 1) + (pp & 3);
+          const long ppix = (static_cast<long>(tb) * (p.Ho >> 1) + ph) * (p.Wo >> 1) + pw;
+          *reinterpret_cast<uint4*>(p.pool_out + ppix * p.Cout + col0 + chunk * 8) = m4;
         }
       }
       __syncwarp();

@@ -321,6 +321,12 @@ static int launch_conv(const tg_conv_args* a, const CUtensorMap& tmA, const CUte
 
 }  // namespace tg
 
+extern "C" int tg_conv_pool_fusable(const tg_conv_args* a) {
+  using namespace tg;
+  if (a == nullptr || a->dtype != TG_DTYPE_BF16 || a->gate != nullptr || !halo_enabled()) return 0;
+  return (conv_halo_eligible(a) || (halo_stream_enabled() && conv_halo_stream_eligible(a))) ? 1 : 0;
+}
+
 extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   using namespace tg;
   TG_REQUIRE(a != nullptr, "tg_conv_igemm: null args");
@@ -390,6 +396,16 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   kp.gate_slope = a->gate_slope;
   kp.addend = a->addend;
   TG_REQUIRE(a->addend == nullptr || f32, "tg_conv_igemm: addend is an fp32-path feature");
+  kp.pool_out = reinterpret_cast<__nv_bfloat16*>(a->pool_out);
+  kp.skip_out = a->skip_out;
+  TG_REQUIRE(a->pool_out != nullptr || !a->skip_out, "tg_conv_igemm: skip_out needs pool_out");
+  if (a->pool_out != nullptr) {
+    // the fused 2x2 max-pool lives in the epilogue of the halo-reuse kernels (bf16, 3x3 / stride 1, N = 64 or 128, H % 16 == 0,
+    // W % 8 == 0, no dgrad gate); tg_conv_pool_fusable() tells the caller in advance
+    TG_REQUIRE(!f32 && a->gate == nullptr && halo_enabled() &&
+                   (conv_halo_eligible(a) || (halo_stream_enabled() && conv_halo_stream_eligible(a))),
+               "tg_conv_igemm: pool_out is not supported for this shape (see tg_conv_pool_fusable)");
+  }
 #ifdef TG_PERF_DEBUG
   {
     static const int dbg = [] { const char* e = getenv("TG_CONV_DEBUG"); return e ? atoi(e) : 0; }();

@@ -43,6 +43,8 @@ struct ConvKParams {
   float gate_slope;
   int debug;                      // perf experiments only: 1 no stores, 2 no epilogue work, 4 no MMA
   const float* addend;            // fp32 path only: [out shape] added to the accumulator before the epilogue, or null
+  __nv_bfloat16* pool_out;        // halo kernels only: [B][Ho/2][Wo/2][Cout] = 2x2 max-pool of the (activated) output, or null
+  int skip_out;                   // with pool_out: do not store the full-resolution output at all
 };
 
 #ifdef __CUDACC__

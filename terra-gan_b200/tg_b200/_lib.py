@@ -42,6 +42,7 @@ class ConvArgs(C.Structure):
         ("stats", c_void_p), ("stats_rows_cap", C.c_int32), ("stats_rows_used", C.c_int32),
         ("gate", c_void_p), ("gate_slope", C.c_float),
         ("dtype", C.c_int32), ("addend", c_void_p),
+        ("pool_out", c_void_p), ("skip_out", C.c_int32),
     ]
 
 
@@ -83,6 +84,7 @@ PROTOTYPES = {
     "tg_mask_from_f32": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
     "tg_mask_to_f32": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
     "tg_conv_igemm": (c_int, [C.POINTER(ConvArgs), c_void_p]),
+    "tg_conv_pool_fusable": (c_int, [C.POINTER(ConvArgs)]),
     "tg_wgrad_igemm": (c_int, [C.POINTER(WgradArgs), c_void_p]),
     "tg_wgrad_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                 c_void_p]),

@@ -565,15 +565,24 @@ class VggEngine:
         h, w = H, W
         for idx, cin, cout in VGG_CONVS[1:]:
             pk = self.pack[idx]
+            if idx in VGG_POOL_AFTER:
+                # conv -> ReLU -> MaxPool2d(2,2) (features[2..4], [7..9]): the pool rides in the conv epilogue; the branch
+                # that needs no gradient (the target image) never writes the full-resolution activation at all
+                keep = save is not None or tr is not None
+                y_full, _, y = ops.conv_igemm(y, pk.w_fprop(vgg[f"{idx}.weight"], mode), pk.fplan, (h, w),
+                                              bias=vgg[f"{idx}.bias"], act=ACT_RELU, pool="also" if keep else "only")
+                if save is not None:
+                    save.append(y_full)
+                if tr is not None:
+                    tr[idx] = y_full
+                h, w = h // 2, w // 2
+                continue
             y, _ = ops.conv_igemm(y, pk.w_fprop(vgg[f"{idx}.weight"], mode), pk.fplan, (h, w), bias=vgg[f"{idx}.bias"],
                                   act=ACT_RELU)
             if save is not None:
                 save.append(y)
             if tr is not None:
                 tr[idx] = y
-            if idx in VGG_POOL_AFTER:
-                y = ops.maxpool2(y[:, 0]).unsqueeze(1)
-                h, w = h // 2, w // 2
         if tr is not None:
             self.trace.append(tr)
         return y

@@ -6,6 +6,7 @@ current CUDA stream. Allocation is always done here with torch (the library neve
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -16,6 +17,7 @@ from .plan import TapPlan
 
 BF16 = torch.bfloat16
 F32 = torch.float32
+_NO_POOL_FUSE = os.environ.get("TG_NO_POOL_FUSE", "") == "1"      # A/B switch: stand-alone max-pool kernels
 
 
 def _act_dtype(t: torch.Tensor, name: str):
@@ -117,11 +119,14 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
                bias: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
                shift: Optional[torch.Tensor] = None, act: int = 0, slope: float = 0.0,
                want_stats: bool = False, out: Optional[torch.Tensor] = None,
-               gate: Optional[torch.Tensor] = None, gate_slope: float = 0.0):
+               gate: Optional[torch.Tensor] = None, gate_slope: float = 0.0, pool: str = ""):
     """out[B][Po][Ho][Wo][N] = epilogue(sum_taps x (+) tap . w)  — see tg_conv_igemm.
 
     x: bf16 [B, P, H, W, C];  w_packed: bf16 [N, Ktot];  plan: fprop_plan / dgrad_plan.
-    Returns (out, stats) where stats is None or fp32 [rows, 2, N] per-CTA partial sums."""
+    Returns (out, stats) where stats is None or fp32 [rows, 2, N] per-CTA partial sums.
+    pool = "also": additionally returns the 2x2 max-pool of the output, fused into the epilogue (VGG features[4] / [9]) —
+    (out, stats, pooled [B,1,Ho/2,Wo/2,N]); pool = "only": the full-resolution output is never written (out is None).
+    Where the shape is not fusable (tg_conv_pool_fusable) the pool runs as its own kernel (tg_maxpool2)."""
     dt = _act_dtype(x, "x")
     addend = None
     if isinstance(w_packed, tuple):
@@ -140,10 +145,8 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
     Po = plan.out_planes
     if P != plan.in_planes:
         raise RuntimeError(f"conv_igemm: input has {P} planes, plan expects {plan.in_planes}")
-    if out is None:
-        out = torch.empty((B, Po, Ho, Wo, N), dtype=dt, device=x.device)
-    else:
-        _req(out, dt, "out")
+    if pool not in ("", "also", "only"):
+        raise ValueError("conv_igemm: pool must be '', 'also' or 'only'")
     a = ConvArgs()
     a.x, a.B, a.P, a.H, a.W, a.C = ptr(x), B, P, H, W, Cc
     a.w, a.N, a.Ktot = ptr(w_packed), N, Ktot
@@ -153,7 +156,23 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
     a.num_taps = len(plan.taps)
     for i, (pl, dh, dw) in enumerate(plan.taps):
         a.tap_plane[i], a.tap_dh[i], a.tap_dw[i] = pl, dh, dw
-    a.out, a.Po, a.Ho, a.Wo = ptr(out), Po, Ho, Wo
+    a.Po, a.Ho, a.Wo = Po, Ho, Wo
+    a.dtype = _lib.DTYPE_BF16 if dt == BF16 else _lib.DTYPE_F32
+    fuse_pool = False
+    if pool:
+        if gate is not None:
+            raise RuntimeError("conv_igemm: pool cannot be combined with a dgrad gate")
+        fuse_pool = (dt == BF16 and Po == 1 and not _NO_POOL_FUSE and bool(lib().tg_conv_pool_fusable(C.byref(a))))
+    pooled = None
+    if fuse_pool:
+        pooled = torch.empty((B, 1, Ho // 2, Wo // 2, N), dtype=dt, device=x.device)
+        a.pool_out, a.skip_out = ptr(pooled), 1 if pool == "only" else 0
+    if out is None:
+        if not (fuse_pool and pool == "only"):
+            out = torch.empty((B, Po, Ho, Wo, N), dtype=dt, device=x.device)
+    else:
+        _req(out, dt, "out")
+    a.out = ptr(out)
     lut_arr = None
     if code is not None:
         _req(code, torch.uint8, "code")
@@ -168,7 +187,6 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
                 raise RuntimeError(f"conv_igemm: {name} must have N={N} entries")
         setattr(a, name, ptr(t))
     a.act, a.slope = act, slope
-    a.dtype = _lib.DTYPE_BF16 if dt == BF16 else _lib.DTYPE_F32
     a.addend = ptr(addend)
     if gate is not None:
         _req(gate, dt, "gate")
@@ -186,6 +204,12 @@ def conv_igemm(x: torch.Tensor, w_packed: torch.Tensor, plan: TapPlan, out_hw: T
               f"B{B} {H}x{W}x{Cc}(P{P}) -> {Ho}x{Wo}x{N}(P{Po}) taps{len(plan.taps)}")
     if stats is not None:
         stats = stats[: a.stats_rows_used]
+    if pool:
+        if pooled is None:                      # not fusable here: the stand-alone pooling kernel
+            pooled = maxpool2(out[:, 0]).unsqueeze(1)
+            if pool == "only":
+                out = None
+        return out, stats, pooled
     return out, stats
 
 

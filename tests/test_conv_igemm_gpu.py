@@ -210,3 +210,26 @@ def test_fprop_stream_halo_lut_stats(Cin, Cout, H, W, B):
     s = stats.double().sum(0)
     assert rel_err(s[0], z.double().sum((0, 1, 2))) < 1e-3
     assert rel_err(s[1], (z.double() ** 2).sum((0, 1, 2))) < 1e-3
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W,B", [(64, 64, 32, 16, 2), (128, 128, 32, 24, 3), (64, 128, 16, 8, 1), (64, 64, 24, 16, 2)])
+def test_fused_maxpool_epilogue(Cin, Cout, H, W, B):
+    """conv -> ReLU -> MaxPool2d(2,2) with the pool in the conv epilogue (VGG features[2..4], [7..9]): the pooled tensor is
+    bit-identical to pooling the stored output, with and without writing the full-resolution tensor; a shape the halo
+    kernels do not take (H % 16 != 0) goes through the stand-alone pooling kernel with the same result."""
+    torch.manual_seed(5)
+    dev = "cuda"
+    x = torch.randn(B, Cin, H, W, device=dev).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device=dev) / (Cin * 9) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device=dev)
+    pl = P.fprop_plan(3, 1, 1)
+    xin = nhwc(x).unsqueeze(1).contiguous()
+    wp = P.pack_w_fprop(w.float())
+    ref, _ = ops.conv_igemm(xin, wp, pl, (H, W), bias=bias, act=1)
+    want = ops.maxpool2(ref[:, 0])
+    full, _, pooled = ops.conv_igemm(xin, wp, pl, (H, W), bias=bias, act=1, pool="also")
+    assert torch.equal(full, ref) and torch.equal(pooled[:, 0], want)
+    none, _, pooled2 = ops.conv_igemm(xin, wp, pl, (H, W), bias=bias, act=1, pool="only")
+    assert none is None and torch.equal(pooled2[:, 0], want)
+    tref = F.max_pool2d(F.relu(F.conv2d(x.float(), w.float(), bias, 1, 1)), 2)
+    assert rel_err(pooled[:, 0], nhwc(tref)) < 1e-2
