@@ -67,7 +67,10 @@ class BucketedGradReducer:
         cuda = tensors[0].is_cuda
         if cuda:
             if self._comm_stream is None:
-                self._comm_stream = torch.cuda.Stream()
+                # high priority: the compute kernels are persistent (one CTA per SM), so a collective can only start at
+                # a kernel boundary; with priority it is scheduled first when SMs free up instead of queueing behind
+                # the next convolution
+                self._comm_stream = torch.cuda.Stream(priority=-1)
             ready = torch.cuda.Event()
             ready.record()                                  # gradients of this bucket are complete here
             self._comm_stream.wait_event(ready)
