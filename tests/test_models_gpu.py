@@ -563,3 +563,79 @@ def test_graphed_generator_matches_eager_inference():
         assert torch.equal(out, eager)
     with pytest.raises(RuntimeError, match="captured for"):
         gg(torch.zeros(1, 1, H, H, device=DEV), torch.ones(1, 1, H, H, device=DEV))
+
+
+# ---------------------------------------------------------------------------------------------
+# loss edge cases the reference guards with host-side branches (losses.py:171, :411, :419)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["ones", "zeros", "rect"])
+def test_boundary_loss_edge_cases(kind):
+    """BoundaryAwareLoss.forward (losses.py:386-428): an empty boundary band (all-valid or all-hole mask) returns 0
+    (the reference's `if torch.sum(boundary) < 1.0` branch, :411) — decided on the device here."""
+    from mvp_gan.src.utils.losses import BoundaryAwareLoss
+    B, H = 2, 64
+    pred, target = O.make_tiles(1, B, H), O.make_tiles(2, B, H)
+    mask = O.make_mask(3, B, H, kind)
+    ref = O.boundary_loss(pred, target, mask)
+    bl = BoundaryAwareLoss(device=torch.device(DEV))
+    pc = pred.to(DEV).requires_grad_(True)
+    got = bl(pc, target.to(DEV), mask.to(DEV))
+    assert abs(got.item() - ref.item()) < 1e-6 + 1e-5 * abs(ref.item())
+    got.backward()
+    if kind != "rect":
+        assert ref.item() == 0.0 and got.item() == 0.0 and float(pc.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("human", ["none", "empty", "full"])
+def test_human_guided_loss_edge_cases(human):
+    """HumanGuidedLoss.forward (losses.py:152-204): no feedback, an all-zero human mask (the reference's `.sum() > 0`
+    host branch, :171, skips the human term) and an all-ones human mask."""
+    H, B = 128, 2
+    images, masks = O.make_tiles(40, B, H), O.make_mask(41, B, H, "rect")
+    pred = (images * masks + 0.5 * (1 - masks)).clone()
+    vgg = O.make_vgg_state(3)
+    hm = None if human == "none" else (torch.zeros if human == "empty" else torch.ones)(B, 1, H, H)
+    ref = O.human_guided_loss(pred, images, masks, hm, vgg)
+    config = {"training": {"loss_weights": {"perceptual": 0.1, "tv": 0.1, "boundary": 0.5},
+                           "modes": {"human_guided": {"human_feedback_weight": 0.3, "base_loss_weight": 0.7,
+                                                      "learning_rate": 1e-4}}}}
+    crit = HumanGuidedLoss(config, device=torch.device(DEV), vgg_state_dict=vgg)
+    fb = None if hm is None else {"mask": hm.to(DEV)}
+    got = crit(pred.to(DEV), images.to(DEV), masks.to(DEV), fb)
+    assert abs(got.item() - ref.item()) < TOL * abs(ref.item()), (got.item(), ref.item())
+    if human == "empty":        # identical to no feedback at all
+        base = crit(pred.to(DEV), images.to(DEV), masks.to(DEV), None)
+        assert abs(got.item() - base.item()) < 1e-7
+
+
+def test_inpainting_loss_weight_switches():
+    """InpaintingLoss with terms switched off (perceptual / tv / boundary weight 0 — losses.py:77, :96, :106 `if` guards)."""
+    H, B = 128, 2
+    vgg = O.make_vgg_state(3)
+    pred, target, mask = O.make_tiles(60, B, H), O.make_tiles(61, B, H), O.make_mask(62, B, H, "large")
+    for pw, tw, bw in ((0.0, 0.1, 0.5), (0.1, 0.0, 0.5), (0.1, 0.1, 0.0), (0.0, 0.0, 0.0)):
+        ref = O.inpainting_loss(pred, target, mask, vgg, pw, tw, bw)
+        crit = InpaintingLoss(perceptual_weight=pw, tv_weight=tw, boundary_weight=bw, device=torch.device(DEV), vgg_state_dict=vgg)
+        got = crit(pred.to(DEV), target.to(DEV), mask.to(DEV))
+        assert abs(got.item() - ref.item()) < TOL * abs(ref.item()), (pw, tw, bw, got.item(), ref.item())
+    tv_ref = O.total_variation(pred)
+    assert abs(crit.total_variation_loss(pred.to(DEV)).item() - tv_ref.item()) < 1e-5 * abs(tv_ref.item())
+
+
+def test_validation_pass_keeps_discriminator_in_train_mode():
+    """train.py:278-304: `generator.eval()` under no_grad while the discriminator stays in train mode (its BatchNorm keeps
+    using batch statistics and updating its running averages during validation)."""
+    H, B = 128, 2
+    real, masks = O.make_tiles(30, B, H), O.make_mask(31, B, H, "rect")
+    G, D, vgg = _make_modules()
+    G.eval()
+    d_sd = O.make_discriminator_state(2)
+    with torch.no_grad():
+        ref_gen = O.pconv_unet(real * masks, masks, O.make_generator_state(1), False)
+        ref_val = O.discriminator(ref_gen, d_sd, True)
+        gen = G((real * masks).to(DEV), masks.to(DEV))
+        val = D(gen)
+    assert rel_err(gen, ref_gen) < TOL and rel_err(val, ref_val) < TOL
+    for bi in (3, 6, 9):
+        assert int(D.model[bi].num_batches_tracked) == 1
+        assert rel_err(D.model[bi].running_var, d_sd[f"model.{bi}.running_var"]) < TOL
