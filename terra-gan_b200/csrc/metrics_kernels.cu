@@ -63,62 +63,83 @@ quality_metrics_kernel(const float* __restrict__ pred, const float* __restrict__
       }
     }
     __syncthreads();
-    // horizontal pass: for every halo row, the 11-wide sums at the kMT output columns
-    for (int i = tid; i < kMH * kMT; i += 256) {
-      const int r = i / kMT, c = i % kMT;
+    // horizontal pass: for every halo row, the 11-wide sums at the kMT output columns. One thread = 4 adjacent outputs
+    // of one row: 14 loads and products feed 4 windows (the first summed in full, the next three by sliding:
+    // + entering - leaving), instead of 11 loads per output
+    for (int i = tid; i < kMH * (kMT / 4); i += 256) {
+      const int r = i / (kMT / 4), c0 = (i % (kMT / 4)) * 4;
+      float pv[14], tv[14];
+#pragma unroll
+      for (int k = 0; k < 14; ++k) { pv[k] = s_p[r][c0 + k]; tv[k] = s_t[r][c0 + k]; }
       float sp = 0.f, st = 0.f, spp = 0.f, stt = 0.f, spt = 0.f;
 #pragma unroll
-      for (int k = 0; k < 2 * kMR + 1; ++k) {
-        const float p = s_p[r][c + k], t = s_t[r][c + k];
-        sp += p; st += t; spp += p * p; stt += t * t; spt += p * t;
+      for (int k = 0; k < 11; ++k) { sp += pv[k]; st += tv[k]; spp += pv[k] * pv[k]; stt += tv[k] * tv[k]; spt += pv[k] * tv[k]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j > 0) {
+          const float pa = pv[j + 10], ta = tv[j + 10], pb = pv[j - 1], tb = tv[j - 1];
+          sp += pa - pb; st += ta - tb; spp += pa * pa - pb * pb; stt += ta * ta - tb * tb; spt += pa * ta - pb * tb;
+        }
+        s_h[0][r][c0 + j] = sp; s_h[1][r][c0 + j] = st; s_h[2][r][c0 + j] = spp; s_h[3][r][c0 + j] = stt; s_h[4][r][c0 + j] = spt;
       }
-      s_h[0][r][c] = sp; s_h[1][r][c] = st; s_h[2][r][c] = spp; s_h[3][r][c] = stt; s_h[4][r][c] = spt;
     }
     __syncthreads();
-    // vertical pass + every per-pixel term: 4 pixels per thread
-    for (int i = tid; i < kMT * kMT; i += 256) {
-      const int r = i / kMT, c = i % kMT;
-      const int h = h0 + r, w = w0 + c;
-      if (h >= H || w >= W) continue;
-      float sums[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    // vertical pass + every per-pixel term. One thread = 4 vertically adjacent pixels of one column (256 threads cover
+    // the 32 x 32 tile): the column sums slide like the row sums above
+    {
+      const int c = tid & (kMT - 1), r0 = (tid / kMT) * 4;
+      const int w = w0 + c;
+      float sums[5];
 #pragma unroll
-      for (int k = 0; k < 2 * kMR + 1; ++k) {
+      for (int q = 0; q < 5; ++q) {
+        float a = 0.f;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) sums[q] += s_h[q][r + k][c];
+        for (int k = 0; k < 2 * kMR + 1; ++k) a += s_h[q][r0 + k][c];
+        sums[q] = a;
       }
-      const float inv = 1.f / 121.f;
-      const float mu1 = sums[0] * inv, mu2 = sums[1] * inv;
-      const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-      const float s1 = sums[2] * inv - mu1_sq, s2 = sums[3] * inv - mu2_sq, s12 = sums[4] * inv - mu12;
-      const float C1 = 0.0001f, C2 = 0.0009f;
-      const float ssim = ((2.f * mu12 + C1) * (2.f * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2));
-      const float p = s_p[r + kMR][c + kMR], t = s_t[r + kMR][c + kMR];
-      const float d = p - t;
-      acc[0] += fabsf(d);
-      acc[1] += static_cast<double>(d) * d;
-      acc[2] += ssim;
-      if (mb != nullptr) {
-        float mx = -1e30f, mn = 1e30f;       // dilate = max over the 3x3 window, erode = min (= 1 - max(1 - m))
 #pragma unroll
-        for (int dr = 0; dr < 3; ++dr)
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + j;
+        if (j > 0) {
 #pragma unroll
-          for (int dc = 0; dc < 3; ++dc) {
-            const float v = s_m[r + dr][c + dc];
-            if (v == v) { mx = fmaxf(mx, v); mn = fminf(mn, v); }
-          }
-        float bd = mx - mn;                   // dilated - eroded
-        bd = fminf(fmaxf(bd, 0.f), 1.f);
-        const float e = d * bd;
-        acc[3] += static_cast<double>(e) * e;
-        acc[4] += bd;
-      }
-      if (h + 1 < H) {
-        acc[5] += fabsf(s_p[r + kMR + 1][c + kMR] - p);
-        acc[7] += fabsf(s_t[r + kMR + 1][c + kMR] - t);
-      }
-      if (w + 1 < W) {
-        acc[6] += fabsf(s_p[r + kMR][c + kMR + 1] - p);
-        acc[8] += fabsf(s_t[r + kMR][c + kMR + 1] - t);
+          for (int q = 0; q < 5; ++q) sums[q] += s_h[q][r + 2 * kMR][c] - s_h[q][r - 1][c];
+        }
+        const int h = h0 + r;
+        if (h >= H || w >= W) continue;
+        const float inv = 1.f / 121.f;
+        const float mu1 = sums[0] * inv, mu2 = sums[1] * inv;
+        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+        const float s1 = sums[2] * inv - mu1_sq, s2 = sums[3] * inv - mu2_sq, s12 = sums[4] * inv - mu12;
+        const float C1 = 0.0001f, C2 = 0.0009f;
+        const float ssim = ((2.f * mu12 + C1) * (2.f * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2));
+        const float p = s_p[r + kMR][c + kMR], t = s_t[r + kMR][c + kMR];
+        const float d = p - t;
+        acc[0] += fabsf(d);
+        acc[1] += static_cast<double>(d) * d;
+        acc[2] += ssim;
+        if (mb != nullptr) {
+          float mx = -1e30f, mn = 1e30f;       // dilate = max over the 3x3 window, erode = min (= 1 - max(1 - m))
+#pragma unroll
+          for (int dr = 0; dr < 3; ++dr)
+#pragma unroll
+            for (int dc = 0; dc < 3; ++dc) {
+              const float v = s_m[r + dr][c + dc];
+              if (v == v) { mx = fmaxf(mx, v); mn = fminf(mn, v); }
+            }
+          float bd = mx - mn;                   // dilated - eroded
+          bd = fminf(fmaxf(bd, 0.f), 1.f);
+          const float e = d * bd;
+          acc[3] += static_cast<double>(e) * e;
+          acc[4] += bd;
+        }
+        if (h + 1 < H) {
+          acc[5] += fabsf(s_p[r + kMR + 1][c + kMR] - p);
+          acc[7] += fabsf(s_t[r + kMR + 1][c + kMR] - t);
+        }
+        if (w + 1 < W) {
+          acc[6] += fabsf(s_p[r + kMR][c + kMR + 1] - p);
+          acc[8] += fabsf(s_t[r + kMR][c + kMR + 1] - t);
+        }
       }
     }
   }
