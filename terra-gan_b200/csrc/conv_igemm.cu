@@ -30,11 +30,14 @@ namespace tg {
 
 constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
 
-template <int BN>
+// kMT: M-tiles (128 pixels each) that share every weight tile. The operand traffic per MMA — 16 KB of pixels + BN x 128 B
+// of weights for four MMAs — is what bounds the N = 128 layers (128 B/clk/SM from L2, 50 % tensor pipe in ncu);
+// two M-tiles per unit, each with its own accumulator pair, cut it to 96 B/clk.
+template <int BN, int kMT = 1>
 struct ConvSmem {
-  static constexpr int kStages = (BN >= 256) ? 3 : 4;
+  static constexpr int kStages = (BN >= 256 || kMT > 1) ? 3 : 4;
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = kMT * kABytes + kBBytes;
   static constexpr int kTiles = kStages * kStageBytes;
   static constexpr int kStatsFloats = 4 * 2 * 512;  // per epilogue warp (sum, sumsq) x channel
   static constexpr int kVecFloats = 3 * 512;        // bias / scale / shift
@@ -45,7 +48,7 @@ struct ConvSmem {
 
 // kF32: fp32 activations / weights in shared memory (TMA boxes of 32 channels = the same 128-byte rows),
 // kind::tf32 MMAs, fp32 output -- the verification path.
-template <int BN, bool kF32 = false>
+template <int BN, bool kF32 = false, int kMT = 1>
 __global__ void __launch_bounds__(384, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvKParams p) {
@@ -53,23 +56,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  using S = ConvSmem<BN>;
+  using S = ConvSmem<BN, kMT>;
   constexpr int kStages = S::kStages;
+  constexpr int kAcc = 2 * kMT;                 // accumulators: two sets of kMT
+  static_assert(kAcc * BN <= 512, "accumulators must fit the 512 TMEM columns");
   float* s_stats = reinterpret_cast<float*>(smem + S::kTiles);
   float* s_vec = s_stats + S::kStatsFloats;
   uint8_t* s_out = reinterpret_cast<uint8_t*>(s_vec + S::kVecFloats);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + S::kStageOutBytes);
   uint64_t* full_bar = bars;                    // [kStages]
   uint64_t* empty_bar = bars + kStages;         // [kStages]
-  uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
-  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* tfull_bar = bars + 2 * kStages;     // [kAcc]
+  uint64_t* tempty_bar = bars + 2 * kStages + kAcc;  // [kAcc]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAcc);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int kKB = kF32 ? 32 : 64;      // channels per K block (128 bytes)
-  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t kTmemCols = (kAcc * BN <= 32) ? 32 : (kAcc * BN <= 64) ? 64 : (kAcc * BN <= 128) ? 128
+                                 : (kAcc * BN <= 256) ? 256 : 512;
 
   // ---- one-time setup ----
   for (int i = threadIdx.x; i < S::kStatsFloats; i += blockDim.x) s_stats[i] = 0.f;
@@ -91,7 +96,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
     }
@@ -103,8 +108,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // a unit = kMT consecutive M-tiles (the host guarantees m_tiles % kMT == 0) x one N-tile of one sub-convolution
   const int m_tiles = p.tiles_b * p.tiles_h * p.tiles_w;
-  const int total_tiles = p.num_sub * m_tiles * p.n_tiles;
+  const int m_units = m_tiles / kMT;
+  const int total_tiles = p.num_sub * m_units * p.n_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -114,12 +121,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         const int rest = tile / p.n_tiles;
-        const int mt = rest % m_tiles;
-        const int sb = rest / m_tiles;
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tb = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
+        const int mu = rest % m_units;
+        const int sb = rest / m_units;
+        int w0[kMT], h0[kMT], b0[kMT];
+#pragma unroll
+        for (int j = 0; j < kMT; ++j) {
+          const int mt = mu * kMT + j;
+          w0[j] = (mt % p.tiles_w) * p.Wt;
+          h0[j] = ((mt / p.tiles_w) % p.tiles_h) * p.Ht;
+          b0[j] = (mt / (p.tiles_w * p.tiles_h)) * p.Bt;
+        }
         const ConvSubK sub = p.sub[sb];
         for (int t = 0; t < sub.tap_count; ++t) {
           const int tt = sub.tap_begin + t;
@@ -127,9 +138,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * S::kStageBytes;
-            uint8_t* sbm = sa + kABytes;
+            uint8_t* sbm = sa + kMT * kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-            tma_load_5d(sa, &tmA, &full_bar[stage], cb * kKB, w0 + dw, h0 + dh, pl, b0);
+#pragma unroll
+            for (int j = 0; j < kMT; ++j)
+              tma_load_5d(sa + j * kABytes, &tmA, &full_bar[stage], cb * kKB, w0[j] + dw, h0[j] + dh, pl, b0[j]);
             tma_load_2d(sbm, &tmB, &full_bar[stage], sub.k_off + (t * p.cin_blocks + cb) * kKB,
                         nt * BN);
             if (++stage == kStages) {
@@ -149,12 +162,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t d_lo0 = static_cast<uint32_t>(d0), d_hi = static_cast<uint32_t>(d0 >> 32);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
+      int acc = 0;               // first accumulator of the current set (0 or kMT)
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int sb = (tile / p.n_tiles) / m_tiles;
+        const int sb = (tile / p.n_tiles) / m_units;
         const int kblocks = p.sub[sb].tap_count * p.cin_blocks;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+#pragma unroll
+        for (int j = 0; j < kMT; ++j) mbar_wait(&tempty_bar[acc + j], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -162,12 +176,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           // descriptor lo word = base + stage offset (>> 4); +2 per 16 bf16 (32 B) along K inside the swizzle row
           const uint32_t a_lo = d_lo0 + static_cast<uint32_t>(stage) * (S::kStageBytes >> 4);
-          const uint32_t b_lo = a_lo + (kABytes >> 4);
+          const uint32_t b_lo = a_lo + (kMT * kABytes >> 4);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (kF32) umma_tf32_lh(d_tmem, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
-              else umma_bf16_lh(d_tmem, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
+            for (int j = 0; j < kMT; ++j) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (kF32) umma_tf32_lh(d_tmem + j * BN, a_lo + j * (kABytes >> 4) + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
+                else umma_bf16_lh(d_tmem + j * BN, a_lo + j * (kABytes >> 4) + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
+              }
             }
             umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           }
@@ -176,8 +193,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             phase ^= 1;
           }
         }
-        if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < kMT; ++j) umma_commit(&tfull_bar[acc + j]);  // accumulators complete -> epilogue
+        }
+        acc += kMT;
+        if (acc == kAcc) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -196,22 +217,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         const int rest = tile / p.n_tiles;
-        const int mt = rest % m_tiles;
-        const int sb = rest / m_tiles;
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tb = mt / (p.tiles_w * p.tiles_h);
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-        conv_epilogue_tile_f32<BN, 512>(p, q, lane, nt, sb, tw, th, tb, t_addr, s_vec, my_stats, has_vec, hsel, e_wt,
-                                        e_ht, e_bt);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        const int sb = rest / m_units;
+#pragma unroll 1
+        for (int j = 0; j < kMT; ++j) {
+          const int mt = (rest % m_units) * kMT + j;
+          const int tw = mt % p.tiles_w;
+          const int th = (mt / p.tiles_w) % p.tiles_h;
+          const int tb = mt / (p.tiles_w * p.tiles_h);
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+          conv_epilogue_tile_f32<BN, 512>(p, q, lane, nt, sb, tw, th, tb, t_addr, s_vec, my_stats, has_vec, hsel, e_wt,
+                                          e_ht, e_bt);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (++acc == kAcc) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
         }
       }
     } else {
@@ -223,25 +247,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         const int rest = tile / p.n_tiles;
-        const int mt = rest % m_tiles;
-        const int sb = rest / m_tiles;
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tb = mt / (p.tiles_w * p.tiles_h);
-        EpiPrefetch pre;
-        conv_epilogue_prefetch<BN, kMode>(p, q, lane, nt, sb, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-        conv_epilogue_tile<BN, 512, S::kStoreCols, kMode>(p, q, lane, nt, sb, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
-                                                          s_out + (warp - 4) * (32 * S::kStoreCols * 2), hsel, e_wt, e_ht,
-                                                          e_bt, nullptr, &pre);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        const int sb = rest / m_units;
+#pragma unroll 1
+        for (int j = 0; j < kMT; ++j) {
+          const int mt = (rest % m_units) * kMT + j;
+          const int tw = mt % p.tiles_w;
+          const int th = (mt / p.tiles_w) % p.tiles_h;
+          const int tb = mt / (p.tiles_w * p.tiles_h);
+          EpiPrefetch pre;
+          conv_epilogue_prefetch<BN, kMode>(p, q, lane, nt, sb, tw, th, tb, hsel, e_wt, e_ht, e_bt, pre);
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+          conv_epilogue_tile<BN, 512, S::kStoreCols, kMode>(p, q, lane, nt, sb, tw, th, tb, t_addr, s_vec, my_stats, has_vec,
+                                                            s_out + (warp - 4) * (32 * S::kStoreCols * 2), hsel, e_wt, e_ht,
+                                                            e_bt, nullptr, &pre);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (++acc == kAcc) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
         }
       }
     });
@@ -309,12 +336,21 @@ static void choose_box(int Ho, int Wo, int pixels, int* Bt, int* Ht, int* Wt) {
   *Bt = pixels / (wt * ht);
 }
 
-template <int BN, bool kF32 = false>
+static bool conv_wide_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TG_NO_CONV_WIDE");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int BN, bool kF32 = false, int kMT = 1>
 static int launch_conv(const tg_conv_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        const ConvKParams& kp, int grid, cudaStream_t st) {
-  using S = ConvSmem<BN>;
-  TG_SET_SMEM_ONCE((conv_igemm_kernel<BN, kF32>), S::kTotal);
-  conv_igemm_kernel<BN, kF32><<<grid, 384, S::kTotal, st>>>(tmA, tmB, kp);
+  using S = ConvSmem<BN, kMT>;
+  TG_SET_SMEM_ONCE((conv_igemm_kernel<BN, kF32, kMT>), S::kTotal);
+  conv_igemm_kernel<BN, kF32, kMT><<<grid, 384, S::kTotal, st>>>(tmA, tmB, kp);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -437,9 +473,13 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
     uint32_t box[2] = {(uint32_t)kb_elems, (uint32_t)BN};
     if ((f32 ? make_tmap_f32 : make_tmap_bf16)(&tmB, a->w, 2, dims, str, box) != 0) return -3;
   }
-  const long total_tiles = (long)kp.num_sub * kp.tiles_b * kp.tiles_h * kp.tiles_w * kp.n_tiles;
+  const long m_tiles_all = (long)kp.tiles_b * kp.tiles_h * kp.tiles_w;
   const int sms = num_sms();
   TG_REQUIRE(sms > 0, "tg_conv_igemm: no CUDA device");
+  // two M-tiles per unit sharing the weight tile (N = 128 or 64): only when that still fills the machine
+  const bool wide = !f32 && (BN == 128 || BN == 64) && conv_wide_enabled() && m_tiles_all % 2 == 0 &&
+                    (long)kp.num_sub * (m_tiles_all / 2) * kp.n_tiles >= 2L * sms;
+  const long total_tiles = (long)kp.num_sub * (wide ? m_tiles_all / 2 : m_tiles_all) * kp.n_tiles;
   int grid = (int)(total_tiles < sms ? total_tiles : sms);
   if (a->stats != nullptr) {
     TG_REQUIRE(a->stats_rows_cap >= grid, "tg_conv_igemm: stats_rows_cap %d < grid %d", a->stats_rows_cap, grid);
@@ -452,6 +492,8 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
     if (BN == 128) return launch_conv<128, true>(a, tmA, tmB, kp, grid, st);
     return launch_conv<64, true>(a, tmA, tmB, kp, grid, st);
   }
+  if (wide) return BN == 128 ? launch_conv<128, false, 2>(a, tmA, tmB, kp, grid, st)
+                             : launch_conv<64, false, 2>(a, tmA, tmB, kp, grid, st);
   if (BN == 256) return launch_conv<256>(a, tmA, tmB, kp, grid, st);
   if (BN == 192) return launch_conv<192>(a, tmA, tmB, kp, grid, st);
   if (BN == 128) return launch_conv<128>(a, tmA, tmB, kp, grid, st);
