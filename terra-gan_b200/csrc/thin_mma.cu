@@ -23,7 +23,8 @@ namespace tg {
 template <int K>
 struct RowGemmCfg {
   static constexpr int T = K * K;
-  static constexpr int KE = 3 * T + 2;                   // src_hi*w_hi, src_lo*w_hi, src_hi*w_lo, 1*bias_hi, 1*bias_lo
+  static constexpr int TP = (T + 1) / 2 * 2;             // taps padded to an even count: each section starts on a bf16x2 word
+  static constexpr int KE = 3 * TP + 2;                  // src_hi*w_hi, src_lo*w_hi, src_hi*w_lo, 1*bias_hi, 1*bias_lo
   static constexpr int KP = (KE + 15) / 16 * 16;         // reduction length issued to the tensor core
   static constexpr int NKB = (KP + 63) / 64;             // 64-element (128-byte) swizzle blocks
   static constexpr int NBUF = NKB == 1 ? 2 : 1;          // A tile + accumulator double-buffered when A is small
@@ -44,11 +45,14 @@ __device__ __forceinline__ uint32_t split_hi_lo(float v) {
 //   build A(i) from the prefetched source values -> MMA(i) issued -> prefetch source of tile i+1 ->
 //   epilogue of tile i-1 (NBUF = 2) or i (NBUF = 1) while the loads / the MMA are in flight.
 // The bias rides in the GEMM (two extra reduction elements 1 x bias_hi, 1 x bias_lo).
+// The kernel is bound by instruction issue (ncu: 740-2500 instructions per warp and tile), so the per-tile integer work
+// is kept small: pixel coordinates advance incrementally (no divisions in the loop), taps outside the image are read
+// at clamped coordinates and zeroed with AND masks, the hi / lo split is done on bf16x2 pairs, ReLU on packed bf16x2.
 template <int K, bool MASKED>
 __global__ void __launch_bounds__(128)
 rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant__ CUtensorMap tm_out) {
   using Cfg = RowGemmCfg<K>;
-  constexpr int T = Cfg::T, KP = Cfg::KP, NBUF = Cfg::NBUF;
+  constexpr int T = Cfg::T, TP = Cfg::TP, KP = Cfg::KP, NBUF = Cfg::NBUF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* s_a = smem;
@@ -63,13 +67,15 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
   for (int i = tid; i < 64 * KP; i += 128) {
     const int n = i / KP, e = i % KP;
     unsigned short bits = 0;
-    if (e < 3 * T) {
-      const int part = e / T, t = e % T;
-      const uint32_t hl = split_hi_lo(__ldg(p.wgt + n * p.w_sn + p.perm[t] * p.w_st));
-      bits = static_cast<unsigned short>(part == 2 ? (hl >> 16) : (hl & 0xffffu));
-    } else if (e < 3 * T + 2 && p.bias != nullptr) {
+    if (e < 3 * TP) {
+      const int part = e / TP, t = e % TP;
+      if (t < T) {
+        const uint32_t hl = split_hi_lo(__ldg(p.wgt + n * p.w_sn + p.perm[t] * p.w_st));
+        bits = static_cast<unsigned short>(part == 2 ? (hl >> 16) : (hl & 0xffffu));
+      }
+    } else if (e < 3 * TP + 2 && p.bias != nullptr) {
       const uint32_t hl = split_hi_lo(__ldg(p.bias + n));
-      bits = static_cast<unsigned short>(e == 3 * T ? (hl & 0xffffu) : (hl >> 16));
+      bits = static_cast<unsigned short>(e == 3 * TP ? (hl & 0xffffu) : (hl >> 16));
     }
     const int kb = e >> 6, ec = e & 63;
     uint8_t* dst = s_b + kb * 8192 + (n >> 3) * 1024 + (n & 7) * 128 + (((ec >> 3) ^ (n & 7)) << 4) + (ec & 7) * 2;
@@ -94,101 +100,125 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
   const unsigned HoWo = static_cast<unsigned>(p.Ho) * p.Wo;
   const unsigned tiles = (p.total + 127u) / 128u;
 
-  // raw source values of this thread's pixel of a tile
-  // (nothing may consume the loaded registers here: the loads stay in flight across the epilogue)
-  auto load_src = [&](unsigned tile, float (&v)[T], uint8_t (&mk)[MASKED ? T : 1]) {
-    const unsigned P = tile * 128u + tid;
-    const bool valid = P < p.total;
-    const unsigned Pc = valid ? P : p.total - 1;
-    const unsigned b = Pc / HoWo, rem = Pc - b * HoWo;
-    const int ho = static_cast<int>(rem / p.Wo), wo = static_cast<int>(rem - static_cast<unsigned>(ho) * p.Wo);
-    const int hb = p.flip ? ho * p.S + p.pad : ho * p.S - p.pad;
-    const int wb = p.flip ? wo * p.S + p.pad : wo * p.S - p.pad;
+  // this thread's pixel of a tile; consecutive tiles of a CTA are `step` pixels apart, decomposed once into (db, dh, dw)
+  struct Geo { unsigned P; int b, ho, wo; };
+  const unsigned stepP = 128u * gridDim.x;
+  const int step_b = static_cast<int>(stepP / HoWo);
+  const int step_h = static_cast<int>((stepP % HoWo) / p.Wo), step_w = static_cast<int>((stepP % HoWo) % p.Wo);
+  auto geo_init = [&](unsigned tile) -> Geo {
+    Geo g;
+    g.P = tile * 128u + tid;
+    g.b = static_cast<int>(g.P / HoWo);
+    const unsigned rem = g.P - static_cast<unsigned>(g.b) * HoWo;
+    g.ho = static_cast<int>(rem / p.Wo);
+    g.wo = static_cast<int>(rem - static_cast<unsigned>(g.ho) * p.Wo);
+    return g;
+  };
+  auto geo_step = [&](Geo& g) {
+    g.P += stepP;
+    g.wo += step_w;
+    if (g.wo >= p.Wo) { g.wo -= p.Wo; ++g.ho; }
+    g.ho += step_h;
+    if (g.ho >= p.Ho) { g.ho -= p.Ho; ++g.b; }
+    g.b += step_b;
+  };
+  const int dstep = p.flip ? -1 : 1;
+  const int base_off = p.flip ? p.pad : -p.pad;
+
+  // per-tile state that travels with the prefetched source values
+  struct TileInfo { unsigned P, hbits, wbits, oidx; };
+
+  // raw source values of this thread's pixel of a tile, read at clamped coordinates; `hbits` / `wbits` say which tap rows /
+  // columns are inside the image (nothing may consume the loaded registers here: the loads stay in flight across the epilogue)
+  auto load_src = [&](const Geo& g, float (&v)[T], uint8_t (&mk)[MASKED ? T : 1], TileInfo& ti) {
+    const bool valid = g.P < p.total;
+    const int b = valid ? g.b : 0, ho = valid ? g.ho : 0, wo = valid ? g.wo : 0;
+    const int hb = ho * p.S + base_off, wb = wo * p.S + base_off;
+    int hc[K], wc[K];
+    unsigned hbits = 0, wbits = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int h = hb + dstep * k, w = wb + dstep * k;
+      hbits |= (static_cast<unsigned>(h) < static_cast<unsigned>(p.H)) ? (1u << k) : 0u;
+      wbits |= (static_cast<unsigned>(w) < static_cast<unsigned>(p.W)) ? (1u << k) : 0u;
+      hc[k] = min(max(h, 0), p.H - 1) * p.W;
+      wc[k] = min(max(w, 0), p.W - 1);
+    }
+    ti.P = g.P;
+    ti.hbits = valid ? hbits : 0u;
+    ti.wbits = wbits;
+    ti.oidx = 0;
+    if (p.out_split)
+      ti.oidx = ((static_cast<unsigned>(b) * 4u + 2u * (ho & 1) + (wo & 1)) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1);
     const float* sb = p.src + static_cast<size_t>(b) * p.H * p.W;
     const uint8_t* mb = MASKED ? p.src_mask + static_cast<size_t>(b) * p.H * p.W : nullptr;
 #pragma unroll
     for (int kh = 0; kh < K; ++kh) {
-      const int h = p.flip ? hb - kh : hb + kh;
 #pragma unroll
       for (int kw = 0; kw < K; ++kw) {
-        const int w = p.flip ? wb - kw : wb + kw;
-        const bool in = valid && h >= 0 && h < p.H && w >= 0 && w < p.W && !TG_DBG(p, 2);
-        const int off = in ? h * p.W + w : 0;
-        // out-of-image taps read element 0 of the image and are zeroed through the mask byte / `inb` bit below
+        const int off = hc[kh] + wc[kw];
         v[kh * K + kw] = __ldg(sb + off);
-        if (MASKED) mk[kh * K + kw] = in ? __ldg(mb + off) : static_cast<uint8_t>(0);
+        if (MASKED) mk[kh * K + kw] = __ldg(mb + off);
       }
     }
-  };
-  // which taps of this thread's pixel fall inside the image (bit t), recomputed at build time: pure ALU
-  auto inside_bits = [&](unsigned tile) -> unsigned long long {
-    const unsigned P = tile * 128u + tid;
-    if (P >= p.total || TG_DBG(p, 2)) return 0ull;
-    const unsigned b = P / HoWo, rem = P - b * HoWo;
-    const int ho = static_cast<int>(rem / p.Wo), wo = static_cast<int>(rem - static_cast<unsigned>(ho) * p.Wo);
-    const int hb = p.flip ? ho * p.S + p.pad : ho * p.S - p.pad;
-    const int wb = p.flip ? wo * p.S + p.pad : wo * p.S - p.pad;
-    unsigned hbits = 0, wbits = 0;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int h = p.flip ? hb - k : hb + k, w = p.flip ? wb - k : wb + k;
-      hbits |= (h >= 0 && h < p.H) ? (1u << k) : 0u;
-      wbits |= (w >= 0 && w < p.W) ? (1u << k) : 0u;
-    }
-    unsigned long long bits = 0;
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-      if ((hbits >> k) & 1u) bits |= static_cast<unsigned long long>(wbits) << (k * K);
-    return bits;
   };
 
   // L2 prefetch of the source rows of a tile a few iterations ahead: its first touch is a DRAM read that queues
   // behind this kernel's own write stream (measured: 2x the kernel time when left on the critical path)
-  auto prefetch_src = [&](unsigned tile) {
-    const unsigned P = tile * 128u + tid;
-    if (P >= p.total) return;
-    const unsigned b = P / HoWo, rem = P - b * HoWo;
-    const int ho = static_cast<int>(rem / p.Wo), wo = static_cast<int>(rem - static_cast<unsigned>(ho) * p.Wo);
-    const int hb = p.flip ? ho * p.S + p.pad : ho * p.S - p.pad;
-    const int w = min(max(wo * p.S, 0), p.W - 1);
-    const size_t img = static_cast<size_t>(b) * p.H * p.W;
+  auto prefetch_src = [&](const Geo& g) {
+    if (g.P >= p.total) return;
+    const int hb = g.ho * p.S + base_off;
+    const int w = min(g.wo * p.S, p.W - 1);
+    const size_t img = static_cast<size_t>(g.b) * p.H * p.W;
 #pragma unroll
     for (int kh = 0; kh < K; ++kh) {
-      const int h = p.flip ? hb - kh : hb + kh;
-      if (h >= 0 && h < p.H) {
+      const int h = hb + dstep * kh;
+      if (static_cast<unsigned>(h) < static_cast<unsigned>(p.H)) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src + img + h * p.W + w));
-        if (p.src_mask != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src_mask + img + h * p.W + w));
+        if (MASKED) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src_mask + img + h * p.W + w));
       }
     }
   };
 
-  auto build_a = [&](uint8_t* a_tile, const float (&v)[T], const uint8_t (&mk)[MASKED ? T : 1], unsigned long long inb,
-                     bool valid) {
-    uint32_t hl[T];
+  auto build_a = [&](uint8_t* a_tile, const float (&v)[T], const uint8_t (&mk)[MASKED ? T : 1], const TileInfo& ti) {
+    uint32_t mh[K], mw[K];
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const bool keep = MASKED ? (mk[t] != 0) : (((inb >> t) & 1ull) != 0);
-      hl[t] = split_hi_lo(keep ? v[t] : 0.f);
+    for (int k = 0; k < K; ++k) {
+      mh[k] = 0u - ((ti.hbits >> k) & 1u);
+      mw[k] = 0u - ((ti.wbits >> k) & 1u);
     }
-    const uint32_t one = valid ? 0x3f80u : 0u;             // bf16 1.0: switches the bias on for real pixels
+    uint32_t hiw[TP / 2], low[TP / 2];
+#pragma unroll
+    for (int q = 0; q < TP / 2; ++q) {
+      float x[2];
+#pragma unroll
+      for (int z = 0; z < 2; ++z) {
+        const int t = 2 * q + z;           // compile-time
+        uint32_t bits = 0;
+        if (t < T) {
+          bits = __float_as_uint(v[t]) & mh[t / K] & mw[t % K];
+          if (MASKED) bits = mk[t] != 0 ? bits : 0u;
+        }
+        x[z] = __uint_as_float(bits);
+      }
+      const uint32_t h = pack_bf16x2(x[0], x[1]);
+      hiw[q] = h;
+      low[q] = pack_bf16x2(x[0] - __uint_as_float(h << 16), x[1] - __uint_as_float(h & 0xffff0000u));
+    }
+    const uint32_t one2 = ti.P < p.total ? 0x3f803f80u : 0u;   // bf16 (1, 1): switches the bias (hi, lo) on for real pixels
     uint8_t* rowp = a_tile + (tid >> 3) * 1024 + (tid & 7) * 128;
 #pragma unroll
     for (int j = 0; j < KP / 8; ++j) {
       uint32_t wd[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint32_t two[2];
-#pragma unroll
-        for (int z = 0; z < 2; ++z) {
-          const int e = j * 8 + q * 2 + z;       // compile-time
-          uint32_t x16 = 0;
-          if (e < T) x16 = hl[e] & 0xffffu;
-          else if (e < 2 * T) x16 = hl[e - T] >> 16;
-          else if (e < 3 * T) x16 = hl[e - 2 * T] & 0xffffu;
-          else if (e < 3 * T + 2) x16 = one;
-          two[z] = x16;
-        }
-        wd[q] = two[0] | (two[1] << 16);
+        const int w = j * 4 + q;           // compile-time word index: elements 2w, 2w + 1
+        uint32_t x32 = 0;
+        if (w < TP / 2) x32 = hiw[w];
+        else if (w < TP) x32 = low[w - TP / 2];
+        else if (w < 3 * TP / 2) x32 = hiw[w - TP];
+        else if (w == 3 * TP / 2) x32 = one2;
+        wd[q] = x32;
       }
       *reinterpret_cast<uint4*>(rowp + (j >> 3) * 16384 + ((((j & 7) ^ (tid & 7))) << 4)) =
           make_uint4(wd[0], wd[1], wd[2], wd[3]);
@@ -197,8 +227,7 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
 
   // thread = pixel row = TMEM lane: ratio, stats, activation, bf16; the warp's 32 x 128 B sub-tile is staged in
   // SWIZZLE_128B order and leaves through one TMA tensor store (plain layout) or 4-rows-per-instruction stores
-  auto epilogue = [&](unsigned tile, uint32_t t_acc, uint8_t* stage_tile) {
-    const unsigned P = tile * 128u + tid;
+  auto epilogue = [&](unsigned tile, unsigned P, unsigned oidx, uint32_t t_acc, uint8_t* stage_tile) {
     const bool valid = P < p.total;
     uint4* st = reinterpret_cast<uint4*>(stage_tile) + warp * 256;
     float rs = 1.f;
@@ -227,18 +256,24 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
         my_stats[ch * 32 + lane] += csum;
         my_stats[64 + ch * 32 + lane] += csq;
       }
-      if (p.act == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      } else if (p.act == 2) {
+      if (p.act == 2) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);   // slope in [0, 1)
       }
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      if (p.act == 1) {          // ReLU commutes with the rounding: max on the packed pairs
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[j]), zero2);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&m);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        st[lane * 8 + ((ch * 4 + j) ^ (lane & 7))] =
-            make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        st[lane * 8 + ((ch * 4 + j) ^ (lane & 7))] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     }
     if (!p.out_split) {
       fence_proxy_async();
@@ -248,10 +283,6 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
         bulk_commit_group();
       }
     } else {
-      const unsigned Pc = valid ? P : p.total - 1;
-      const unsigned b = Pc / HoWo, rem = Pc - b * HoWo;
-      const unsigned ho = rem / p.Wo, wo = rem - ho * p.Wo;
-      const unsigned oidx = ((b * 4u + 2u * (ho & 1) + (wo & 1)) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1);
       const unsigned vmask = __ballot_sync(0xffffffffu, valid);
       __syncwarp();
 #pragma unroll
@@ -267,10 +298,16 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
 
   float v[T];
   uint8_t mk[MASKED ? T : 1];
-  for (int d = 1; d < 4; ++d)
-    if (blockIdx.x + d * gridDim.x < tiles) prefetch_src(blockIdx.x + d * gridDim.x);
-  if (blockIdx.x < tiles) load_src(blockIdx.x, v, mk);
-  unsigned prev_tile = 0;
+  TileInfo cur{0u, 0u, 0u, 0u};
+  Geo gl = geo_init(blockIdx.x);              // geometry of the tile whose source is loaded next
+  Geo gp = geo_init(blockIdx.x + gridDim.x);  // geometry of the tile whose source rows are pulled into L2 next
+  for (int d = 1; d < 4; ++d) {
+    prefetch_src(gp);
+    geo_step(gp);
+  }
+  if (blockIdx.x < tiles) load_src(gl, v, mk, cur);
+  geo_step(gl);
+  unsigned prev_tile = 0, prev_P = 0, prev_oidx = 0;
   int it = 0;
   for (unsigned tile = blockIdx.x;; tile += gridDim.x, ++it) {
     const bool have = tile < tiles;          // CTA-uniform
@@ -280,7 +317,8 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
       if (lane == 0) bulk_wait_read_all();
       __syncwarp();
     }
-    if (have) build_a(s_a + buf * Cfg::kABytes, v, mk, MASKED ? 0ull : inside_bits(tile), tile * 128u + tid < p.total);
+    if (have) build_a(s_a + buf * Cfg::kABytes, v, mk, cur);
+    const unsigned this_P = cur.P, this_oidx = cur.oidx;
     fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
     tc_fence_before();            // earlier tcgen05.ld of this accumulator are complete before it is overwritten
     __syncthreads();
@@ -295,24 +333,28 @@ rowgemm64_kernel(const __grid_constant__ RowGemmParams p, const __grid_constant_
       }
       umma_commit(&mbar[buf]);
     }
-    if (have && tile + gridDim.x < tiles) load_src(tile + gridDim.x, v, mk);
-    if (tile + 4 * gridDim.x < tiles && !TG_DBG(p, 4)) prefetch_src(tile + 4 * gridDim.x);
+    if (have && tile + gridDim.x < tiles) load_src(gl, v, mk, cur);
+    geo_step(gl);
+    if (!TG_DBG(p, 4)) prefetch_src(gp);
+    geo_step(gp);
     if (NBUF == 1) {
       if (have) {
         mbar_wait(&mbar[0], it & 1);
         tc_fence_after();
         if (lane == 0) bulk_wait_read_all();     // previous tile's store has left the staging area
         __syncwarp();
-        epilogue(tile, tmem, s_stage);
+        epilogue(tile, this_P, this_oidx, tmem, s_stage);
       }
     } else {
       if (it > 0) {
         const int pb = (it - 1) % NBUF;
         mbar_wait(&mbar[pb], ((it - 1) / NBUF) & 1);
         tc_fence_after();
-        epilogue(prev_tile, tmem + pb * 64, s_a + pb * Cfg::kABytes);
+        epilogue(prev_tile, prev_P, prev_oidx, tmem + pb * 64, s_a + pb * Cfg::kABytes);
       }
       prev_tile = tile;
+      prev_P = this_P;
+      prev_oidx = this_oidx;
     }
     if (!have) break;
   }
@@ -343,6 +385,7 @@ static int rowgemm_launch(const RowGemmParams& p, int grid_cap, int* grid_used, 
     if (make_tmap_bf16(&tm_out, p.out, 2, dims, str, box) != 0) return -3;
   }
   int per_sm = (220 * 1024) / Cfg::kSmem;
+  if (per_sm > 512 / (64 * Cfg::NBUF)) per_sm = 512 / (64 * Cfg::NBUF);     // TMEM columns: a CTA beyond this waits in tmem_alloc
   if (per_sm > 5) per_sm = 5;
   const long tiles = (static_cast<long>(p.total) + 127) / 128;
   long grid = static_cast<long>(num_sms()) * per_sm;
