@@ -1094,7 +1094,8 @@ extern "C" int tg_conv_c1_wgrad(const float* x, const uint8_t* xmask, int B, int
     tp.S = s; tp.pad = pad; tp.flip = 0; tp.y_split = g_split;
     tp.total = static_cast<unsigned>(static_cast<long>(B) * Ho * Wo);
     tp.partial = partial; tp.partial_c = nullptr; tp.center = -1;
-    const int cap = static_cast<int>(static_cast<long>(rows_cap) * (T + 1) / (2 * T + 1));   // same buffer, 2T+1 rows per CTA
+    const int TP = (T + 1) / 2 * 2;
+    const int cap = static_cast<int>(static_cast<long>(rows_cap) * (T + 1) / (2 * TP + 1));   // same buffer, 2TP+1 rows per CTA
     TG_REQUIRE(cap >= 1, "tg_conv_c1_wgrad: rows_cap too small");
     int used = 0;
     TG_REQUIRE(tapwgrad_dispatch(k, tp, g, cap, &used, st) == 0, "tg_conv_c1_wgrad: launch failed");
@@ -1116,7 +1117,7 @@ extern "C" int tg_conv_c1_wgrad(const float* x, const uint8_t* xmask, int B, int
   return 0;
 }
 
-extern "C" int tg_conv_c1_wgrad_rows(void) { return tg::num_sms() * 2; }
+extern "C" int tg_conv_c1_wgrad_rows(void) { return tg::num_sms() * 2 + 8; }
 
 extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, int C, const float* wgt, int ncls,
                                const int* cls_count, const int8_t* tap_dh, const int8_t* tap_dw, const float* bias, int Ho,
@@ -1254,7 +1255,7 @@ extern "C" int tg_conv_to1_wgrad(const void* x, int B, int H, int W, int C, cons
   }
   Tap3x3 tp;
   if (thin_mma_enabled() && C == 64 && Ho == H && Wo == W && make_tap3x3(&tp, ntaps, tap_dh, tap_dw) &&
-      static_cast<long>(B) * H * W < (1L << 31) && rows_cap * 9 / 19 >= 1) {
+      static_cast<long>(B) * H * W < (1L << 31) && rows_cap * 9 / 21 >= 1) {
     // dw[pos][c] = sum_n g[n - d_pos] * x[n][c]: the "flipped" 3x3 taps of g against the activation tile
     TapWgradParams wp{};
     wp.src = g; wp.B = B; wp.H = H; wp.W = W; wp.Ho = H; wp.Wo = W;
@@ -1262,7 +1263,7 @@ extern "C" int tg_conv_to1_wgrad(const void* x, int B, int H, int W, int C, cons
     wp.total = static_cast<unsigned>(static_cast<long>(B) * H * W);
     wp.partial = partial; wp.partial_c = partial_b; wp.center = 4;
     int used = 0;
-    TG_REQUIRE(tapwgrad_dispatch(3, wp, x, rows_cap * 9 / 19, &used, st) == 0, "tg_conv_to1_wgrad: launch failed");
+    TG_REQUIRE(tapwgrad_dispatch(3, wp, x, rows_cap * 9 / 21, &used, st) == 0, "tg_conv_to1_wgrad: launch failed");
     int8_t perm[9];
     for (int t = 0; t < 9; ++t) perm[t] = static_cast<int8_t>(tp.idx[t]);
     TG_REQUIRE(tapwgrad_reduce(3, partial, partial_b, used, dw, 9, 1, perm, db, partial_b ? 2 : 0, accumulate, st) == 0,

@@ -407,36 +407,49 @@ static int rowgemm_launch(const RowGemmParams& p, int grid_cap, int* grid_used, 
 
 // ------------------------------------------------------------------------------------------------
 // Weight gradient:  D[row][c] += sum over the 128 pixels of a tile of A[row][pixel] * Y[pixel][c]
-//   A (thread-built, K-major over pixels): rows t / T+t = bf16 hi / lo part of the tap-t source value of each
-//   pixel, row 2T = 1 (bias gradient); Y tile [128 pixels][64] arrives by TMA and is the MN-major B operand.
+//   A (thread-built): rows t / TP+t = bf16 hi / lo part of the tap-t source value of each pixel (TP = taps padded to an
+//   even count), row 2TP = 1 (bias gradient). A is stored MN-major — [pixel][64 rows] 128-byte lines, SWIZZLE_128B, two
+//   64-row blocks — so a thread writes the column of its pixel as a few 16-byte chunks instead of one 2-byte store per row.
+//   The Y tile [128 pixels][64] arrives by TMA and is the MN-major B operand.
 // One accumulator (128 lanes x 64 columns) lives in TMEM for the whole kernel and is read once at the end.
-// warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator, warps 4-7 and 8-11: two groups of A builders
-// taking alternate tiles (one tile's source-load latency per iteration is otherwise exposed); warps 4-7 read out.
+// warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator, then kGroups groups of 128 A builders taking tiles
+// round-robin (a tile's source-load latency is otherwise exposed: ncu long-scoreboard stalls); group 0 reads out.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTwStages = 3;
-constexpr int kTwSmem = kTwStages * (32768 + 16384) + 256 + 1024;
+template <int K>
+struct TapWgradCfg {
+  static constexpr int T = K * K;
+  static constexpr int TP = (T + 1) / 2 * 2;
+  static constexpr int NR = 2 * TP + 1;                     // accumulator rows in use
+  static constexpr int kChunks = (NR + 7) / 8;              // 16-byte chunks (8 rows) a builder thread writes per pixel
+  static constexpr int kGroups = K <= 4 ? 4 : 2;            // register budget: the 7x7 builder holds 49 values + 49 mask bytes
+  static constexpr int kStages = K <= 4 ? 4 : 3;
+  static constexpr int kThreads = 128 + kGroups * 128;
+  static constexpr int kSmem = kStages * (32768 + 16384) + 256 + 1024;
+  static_assert(NR <= 128, "tap rows must fit the 128 accumulator lanes");
+};
 
 template <int K, bool MASKED>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(TapWgradCfg<K>::kThreads, 1)
 tapwgrad_kernel(const __grid_constant__ TapWgradParams p, const __grid_constant__ CUtensorMap tm_y) {
-  constexpr int T = K * K, NR = 2 * T + 1;
-  static_assert(NR <= 128, "tap rows must fit the 128 accumulator lanes");
+  using Cfg = TapWgradCfg<K>;
+  constexpr int T = Cfg::T, TP = Cfg::TP, NR = Cfg::NR, kStages = Cfg::kStages, kGroups = Cfg::kGroups;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* s_a = smem;                                   // [stage][2 k-blocks][128 rows][128 B]
-  uint8_t* s_y = s_a + kTwStages * 32768;                // [stage][128 pixels][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_y + kTwStages * 16384);
+  uint8_t* s_a = smem;                                   // [stage][2 row blocks][128 pixels][128 B]
+  uint8_t* s_y = s_a + kStages * 32768;                  // [stage][128 pixels][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_y + kStages * 16384);
   uint64_t* full_y = bars;
-  uint64_t* full_a = bars + kTwStages;
-  uint64_t* empty = bars + 2 * kTwStages;
-  uint64_t* done = bars + 3 * kTwStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kTwStages + 1);
-  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);
+  uint64_t* full_a = bars + kStages;
+  uint64_t* empty = bars + 2 * kStages;
+  uint64_t* done = bars + 3 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);      // [4 * kGroups]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < kTwStages * 32768 / 16; i += 384) reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // rows >= NR of the A tiles are never written by the builders: zero once
+  for (int i = tid; i < kStages * 32768 / 16; i += Cfg::kThreads) reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
-    for (int i = 0; i < kTwStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_y[i], 1);
       mbar_init(&full_a[i], 128);
       mbar_init(&empty[i], 1);
@@ -461,7 +474,7 @@ tapwgrad_kernel(const __grid_constant__ TapWgradParams p, const __grid_constant_
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_y[stage], 16384);
         tma_load_2d(s_y + stage * 16384, &tm_y, &full_y[stage], 0, static_cast<int>(tile * 128u));   // tail rows: zero fill
-        if (++stage == kTwStages) {
+        if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
@@ -469,8 +482,8 @@ tapwgrad_kernel(const __grid_constant__ TapWgradParams p, const __grid_constant_
     }
   } else if (warp == 1) {
     {   // whole warp (warp-uniform addressing); one elected lane issues
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);     // A K-major, B (= Y) MN-major
-      const uint64_t da0 = make_smem_desc(smem_u32(s_a), 16, 1024), dy0 = make_smem_desc(smem_u32(s_y), 16384, 1024);
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, true);     // A and B (= Y) MN-major
+      const uint64_t da0 = make_smem_desc(smem_u32(s_a), 16384, 1024), dy0 = make_smem_desc(smem_u32(s_y), 16384, 1024);
       const uint32_t a_lo0 = static_cast<uint32_t>(da0), a_hi = static_cast<uint32_t>(da0 >> 32);
       const uint32_t y_lo0 = static_cast<uint32_t>(dy0), y_hi = static_cast<uint32_t>(dy0 >> 32);
       int stage = 0;
@@ -484,13 +497,12 @@ tapwgrad_kernel(const __grid_constant__ TapWgradParams p, const __grid_constant_
         const uint32_t y_lo = y_lo0 + static_cast<uint32_t>(stage) * (16384 >> 4);
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_bf16_lh(tmem, a_lo + (ks >> 2) * (16384 >> 4) + (ks & 3) * 2, a_hi, y_lo + ks * 128, y_hi, idesc,
-                         ks ? 1u : (first ? 0u : 1u));
+          for (int ks = 0; ks < 8; ++ks)       // 16 pixels (two 8-line swizzle atoms, 2048 B) per MMA
+            umma_bf16_lh(tmem, a_lo + ks * 128, a_hi, y_lo + ks * 128, y_hi, idesc, ks ? 1u : (first ? 0u : 1u));
           umma_commit(&empty[stage]);
         }
         first = false;
-        if (++stage == kTwStages) {
+        if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
@@ -499,99 +511,134 @@ tapwgrad_kernel(const __grid_constant__ TapWgradParams p, const __grid_constant_
     }
   } else if (warp >= 4) {
     const int j = (tid - 128) & 127;             // pixel of the tile (= TMEM lane at read-out for group 0)
-    const int grp = (tid - 128) >> 7;            // builder group: tiles i = grp, grp + 2, ...
-    const unsigned HoWo = static_cast<unsigned>(p.Ho) * p.Wo;
-    struct Geo { int hb, wb; size_t img; bool valid; };
-    auto geo = [&](unsigned tile) -> Geo {
-      const unsigned P = tile * 128u + j;
+    const int grp = (tid - 128) >> 7;            // builder group: tiles i = grp, grp + kGroups, ...
+    // pixel index -> (image, plane, row, column) of the Y grid as mixed-radix digits; consecutive tiles of a group are
+    // `stepP` pixels apart, decomposed once, so the loop carries digits instead of dividing
+    const int NP = p.y_split ? 4 : 1;
+    const int Hd = p.y_split ? p.Ho >> 1 : p.Ho, Wd = p.y_split ? p.Wo >> 1 : p.Wo;
+    struct Geo { unsigned P; int b, pl, h, w; };
+    auto decompose = [&](unsigned P) -> Geo {
       Geo g;
-      g.valid = P < p.total;
-      const unsigned Pc = g.valid ? P : p.total - 1;
-      const unsigned b = Pc / HoWo, rem = Pc - b * HoWo;
-      int ho, wo;
-      if (p.y_split) {
-        const unsigned plane_sz = HoWo >> 2, w2n = static_cast<unsigned>(p.Wo) >> 1;
-        const unsigned plane = rem / plane_sz, r2 = rem - plane * plane_sz;
-        const unsigned h2 = r2 / w2n, w2 = r2 - h2 * w2n;
-        ho = static_cast<int>(2 * h2 + (plane >> 1));
-        wo = static_cast<int>(2 * w2 + (plane & 1));
-      } else {
-        ho = static_cast<int>(rem / p.Wo);
-        wo = static_cast<int>(rem - static_cast<unsigned>(ho) * p.Wo);
-      }
-      g.hb = p.flip ? ho * p.S + p.pad : ho * p.S - p.pad;
-      g.wb = p.flip ? wo * p.S + p.pad : wo * p.S - p.pad;
-      g.img = static_cast<size_t>(b) * p.H * p.W;
+      g.P = P;
+      g.w = static_cast<int>(P % static_cast<unsigned>(Wd));
+      P /= static_cast<unsigned>(Wd);
+      g.h = static_cast<int>(P % static_cast<unsigned>(Hd));
+      P /= static_cast<unsigned>(Hd);
+      g.pl = static_cast<int>(P % static_cast<unsigned>(NP));
+      g.b = static_cast<int>(P / static_cast<unsigned>(NP));
       return g;
     };
-    // loads only; nothing consumes the registers before the next build (they stay in flight)
-    auto load_src = [&](const Geo& g, float (&v)[T], uint8_t (&mk)[MASKED ? T : 1]) {
-#pragma unroll
-      for (int kh = 0; kh < K; ++kh) {
-        const int h = p.flip ? g.hb - kh : g.hb + kh;
-#pragma unroll
-        for (int kw = 0; kw < K; ++kw) {
-          const int w = p.flip ? g.wb - kw : g.wb + kw;
-          const bool in = g.valid && h >= 0 && h < p.H && w >= 0 && w < p.W;
-          const int off = in ? h * p.W + w : 0;
-          v[kh * K + kw] = __ldg(p.src + g.img + off);
-          if (MASKED) mk[kh * K + kw] = in ? __ldg(p.src_mask + g.img + off) : static_cast<uint8_t>(0);
-        }
-      }
+    const unsigned stepP = 128u * gridDim.x * kGroups;
+    const Geo st = decompose(stepP);
+    auto geo_step = [&](Geo& g) {
+      g.P += stepP;
+      g.w += st.w;
+      if (g.w >= Wd) { g.w -= Wd; ++g.h; }
+      g.h += st.h;
+      if (g.h >= Hd) { g.h -= Hd; ++g.pl; }
+      g.pl += st.pl;
+      if (g.pl >= NP) { g.pl -= NP; ++g.b; }
+      g.b += st.b;
     };
-    auto inside_bits = [&](const Geo& g) -> unsigned long long {
-      if (!g.valid) return 0ull;
-      unsigned hbits = 0, wbits = 0;
+    const int dstep = p.flip ? -1 : 1;
+    const int base_off = p.flip ? p.pad : -p.pad;
+    // loads only, at clamped coordinates; nothing consumes the registers before the next build (they stay in flight)
+    auto load_src = [&](const Geo& g, float (&v)[T], uint8_t (&mk)[MASKED ? T : 1], unsigned& hbits, unsigned& wbits) {
+      const bool valid = g.P < p.total;
+      const int b = valid ? g.b : 0;
+      int ho = valid ? g.h : 0, wo = valid ? g.w : 0;
+      if (p.y_split) {
+        const int pl = valid ? g.pl : 0;
+        ho = 2 * ho + (pl >> 1);
+        wo = 2 * wo + (pl & 1);
+      }
+      const int hb = ho * p.S + base_off, wb = wo * p.S + base_off;
+      int hc[K], wc[K];
+      unsigned hb_ = 0, wb_ = 0;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const int h = p.flip ? g.hb - k : g.hb + k, w = p.flip ? g.wb - k : g.wb + k;
-        hbits |= (h >= 0 && h < p.H) ? (1u << k) : 0u;
-        wbits |= (w >= 0 && w < p.W) ? (1u << k) : 0u;
+        const int h = hb + dstep * k, w = wb + dstep * k;
+        hb_ |= (static_cast<unsigned>(h) < static_cast<unsigned>(p.H)) ? (1u << k) : 0u;
+        wb_ |= (static_cast<unsigned>(w) < static_cast<unsigned>(p.W)) ? (1u << k) : 0u;
+        hc[k] = min(max(h, 0), p.H - 1) * p.W;
+        wc[k] = min(max(w, 0), p.W - 1);
       }
-      unsigned long long bits = 0;
+      hbits = valid ? hb_ : 0u;
+      wbits = wb_;
+      const float* sb = p.src + static_cast<size_t>(b) * p.H * p.W;
+      const uint8_t* mb = MASKED ? p.src_mask + static_cast<size_t>(b) * p.H * p.W : nullptr;
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-        if ((hbits >> k) & 1u) bits |= static_cast<unsigned long long>(wbits) << (k * K);
-      return bits;
+      for (int kh = 0; kh < K; ++kh) {
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          const int off = hc[kh] + wc[kw];
+          v[kh * K + kw] = __ldg(sb + off);
+          if (MASKED) mk[kh * K + kw] = __ldg(mb + off);
+        }
+      }
     };
 
     float v[T];
     uint8_t mk[MASKED ? T : 1];
+    unsigned hbits = 0, wbits = 0;
     float csum = 0.f;
     const unsigned my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
-    Geo g = geo(blockIdx.x + grp * gridDim.x);
-    if (static_cast<unsigned>(grp) < my_tiles) load_src(g, v, mk);
-    // element (row m, pixel j): k-block j>>6, 16-byte chunk (j&63)>>3 swizzled by the row, 2-byte slot j&7
-    const uint32_t col_off = (j >> 6) * 16384 + (j & 7) * 2;
-    const uint32_t chunk = (j & 63) >> 3;
-    for (unsigned i = grp; i < my_tiles; i += 2) {
-      const int stage = static_cast<int>(i % kTwStages);
-      const uint32_t phase = (i / kTwStages) & 1u;
-      const unsigned long long inb = MASKED ? 0ull : inside_bits(g);
-      mbar_wait(&empty[stage], phase ^ 1);
-      uint8_t* a_st = s_a + stage * 32768 + col_off;
+    Geo g = decompose((blockIdx.x + static_cast<unsigned>(grp) * gridDim.x) * 128u + j);
+    bool valid = g.P < p.total;
+    if (static_cast<unsigned>(grp) < my_tiles) load_src(g, v, mk, hbits, wbits);
+    // pixel j of the tile = line j of each 64-row block; its 16-byte chunk c (rows 8c .. 8c+7) sits at (c ^ (j & 7)) << 4
+    uint8_t* const line = s_a + j * 128;
+    for (unsigned i = grp; i < my_tiles; i += kGroups) {
+      const int stage = static_cast<int>(i % kStages);
+      const uint32_t phase = (i / kStages) & 1u;
+      uint32_t mh[K], mw[K];
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const bool keep = MASKED ? (mk[t] != 0) : (((inb >> t) & 1ull) != 0);
-        const float x = keep ? v[t] : 0.f;
-        if (t == p.center) csum += x;
-        const uint32_t hl = split_hi_lo(x);
-        const int m0 = t, m1 = T + t;
-        *reinterpret_cast<unsigned short*>(a_st + (m0 >> 3) * 1024 + (m0 & 7) * 128 + ((chunk ^ (m0 & 7)) << 4)) =
-            static_cast<unsigned short>(hl & 0xffffu);
-        *reinterpret_cast<unsigned short*>(a_st + (m1 >> 3) * 1024 + (m1 & 7) * 128 + ((chunk ^ (m1 & 7)) << 4)) =
-            static_cast<unsigned short>(hl >> 16);
+      for (int k = 0; k < K; ++k) {
+        mh[k] = 0u - ((hbits >> k) & 1u);
+        mw[k] = 0u - ((wbits >> k) & 1u);
       }
-      {
-        constexpr int m2 = 2 * T;
-        *reinterpret_cast<unsigned short*>(a_st + (m2 >> 3) * 1024 + (m2 & 7) * 128 + ((chunk ^ (m2 & 7)) << 4)) =
-            g.valid ? static_cast<unsigned short>(0x3f80) : static_cast<unsigned short>(0);
+      uint32_t hiw[TP / 2], low[TP / 2];
+#pragma unroll
+      for (int q = 0; q < TP / 2; ++q) {
+        float x[2];
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+          const int t = 2 * q + z;           // compile-time
+          uint32_t bits = 0;
+          if (t < T) {
+            bits = __float_as_uint(v[t]) & mh[t / K] & mw[t % K];
+            if (MASKED) bits = mk[t] != 0 ? bits : 0u;
+          }
+          x[z] = __uint_as_float(bits);
+          if (t < T && t == p.center) csum += x[z];
+        }
+        const uint32_t h = pack_bf16x2(x[0], x[1]);
+        hiw[q] = h;
+        low[q] = pack_bf16x2(x[0] - __uint_as_float(h << 16), x[1] - __uint_as_float(h & 0xffff0000u));
+      }
+      const uint32_t one = valid ? 0x3f80u : 0u;        // row 2TP = 1 for real pixels (bias gradient = sum of Y)
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* a_st = line + stage * 32768;
+#pragma unroll
+      for (int c = 0; c < Cfg::kChunks; ++c) {
+        uint32_t wd[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = c * 4 + q;           // compile-time word index: rows 2w, 2w + 1
+          uint32_t x32 = 0;
+          if (w < TP / 2) x32 = hiw[w];
+          else if (w < TP) x32 = low[w - TP / 2];
+          else if (w == TP) x32 = one;
+          wd[q] = x32;
+        }
+        *reinterpret_cast<uint4*>(a_st + (c >> 3) * 16384 + (((c & 7) ^ (j & 7)) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
       }
       fence_proxy_async();
       mbar_arrive(&full_a[stage]);
-      if (i + 2 < my_tiles) {
-        g = geo(blockIdx.x + (i + 2) * gridDim.x);
-        load_src(g, v, mk);
+      if (i + kGroups < my_tiles) {
+        geo_step(g);
+        valid = g.P < p.total;
+        load_src(g, v, mk, hbits, wbits);
       }
     }
     if (p.partial_c != nullptr) {
@@ -619,7 +666,11 @@ tapwgrad_kernel(const __grid_constant__ TapWgradParams p, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (tid == 0 && p.partial_c != nullptr) p.partial_c[blockIdx.x] = s_red[0] + s_red[1] + s_red[2] + s_red[3] + s_red[4] + s_red[5] + s_red[6] + s_red[7];
+  if (tid == 0 && p.partial_c != nullptr) {
+    float s = 0.f;
+    for (int i = 0; i < 4 * kGroups; ++i) s += s_red[i];
+    p.partial_c[blockIdx.x] = s;
+  }
   if (warp == 2) tmem_dealloc<64>(tmem);
 }
 
@@ -627,20 +678,20 @@ __global__ void tapwgrad_reduce_kernel(const float* __restrict__ partial, const 
                                        float* __restrict__ out_w, int w_sn, int w_st, RowGemmParams perm_holder,
                                        float* __restrict__ out_b, int bias_mode, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int NR = 2 * T + 1;
+  const int TP = (T + 1) / 2 * 2, NR = 2 * TP + 1;
   if (i < 64 * T) {
     const int t = i / 64, c = i % 64;
     double s = 0.0;
     for (int r = 0; r < rows; ++r) {
       const float* pr = partial + static_cast<size_t>(r) * NR * 64;
-      s += static_cast<double>(pr[t * 64 + c]) + static_cast<double>(pr[(T + t) * 64 + c]);
+      s += static_cast<double>(pr[t * 64 + c]) + static_cast<double>(pr[(TP + t) * 64 + c]);
     }
     float* d = out_w + c * w_sn + perm_holder.perm[t] * w_st;
     *d = (accumulate ? *d : 0.f) + static_cast<float>(s);
   } else if (i < 64 * T + 64 && bias_mode == 1 && out_b != nullptr) {
     const int c = i - 64 * T;
     double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += partial[(static_cast<size_t>(r) * NR + 2 * T) * 64 + c];
+    for (int r = 0; r < rows; ++r) s += partial[(static_cast<size_t>(r) * NR + 2 * TP) * 64 + c];
     out_b[c] = (accumulate ? out_b[c] : 0.f) + static_cast<float>(s);
   } else if (i == 64 * T + 64 && bias_mode == 2 && out_b != nullptr && partial_c != nullptr) {
     double s = 0.0;
@@ -651,7 +702,8 @@ __global__ void tapwgrad_reduce_kernel(const float* __restrict__ partial, const 
 
 template <int K, bool MASKED>
 static int tapwgrad_launch(const TapWgradParams& p, const void* y, int grid_cap, int* grid_used, cudaStream_t st) {
-  TG_SET_SMEM_ONCE((tapwgrad_kernel<K, MASKED>), kTwSmem);
+  using Cfg = TapWgradCfg<K>;
+  TG_SET_SMEM_ONCE((tapwgrad_kernel<K, MASKED>), Cfg::kSmem);
   CUtensorMap tm_y;
   const uint64_t dims[2] = {64, p.total};
   const uint64_t str[1] = {128};
@@ -663,7 +715,7 @@ static int tapwgrad_launch(const TapWgradParams& p, const void* y, int grid_cap,
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
   if (grid < 1) grid = 1;
   if (grid_used) *grid_used = static_cast<int>(grid);
-  tapwgrad_kernel<K, MASKED><<<static_cast<int>(grid), 384, kTwSmem, st>>>(p, tm_y);
+  tapwgrad_kernel<K, MASKED><<<static_cast<int>(grid), Cfg::kThreads, Cfg::kSmem, st>>>(p, tm_y);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
