@@ -245,6 +245,10 @@ int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, int C, cons
 /* Floats of device scratch with which tg_conv_to1_fwd runs its C = 64 cases on the tensor cores (per-pixel tap
  * dot products, then the shifted sum); with scratch == NULL or too small it runs the CUDA-core kernels. */
 size_t tg_conv_to1_fwd_scratch_floats(int B, int H, int W, int C, int ntaps);
+/* Kernels tg_conv_to1_fwd launches for this shape when scratch is supplied: 1 = the one-kernel path (C = 64, taps inside a
+ * 3x3 window, plain layout, Ho x Wo == H x W, H and W >= 16), which needs no scratch at all; 2 otherwise; 0 = bad tap table. */
+int tg_conv_to1_fwd_kernels(int x_split, int H, int W, int C, int ncls, const int* cls_count, const int8_t* tap_dh,
+                            const int8_t* tap_dw, int Ho, int Wo);
 /* dx[B][H][W][C] (bf16) = sum_t g[b][h - dh_t][w - dw_t] * wgt[t][c];  g fp32 [B][Ho][Wo]. */
 int tg_conv_to1_bwd_data(const float* g, int B, int Ho, int Wo, const float* wgt, int ntaps,
                          const int8_t* tap_dh, const int8_t* tap_dw, int H, int W, int C, void* dx,

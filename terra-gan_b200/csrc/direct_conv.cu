@@ -1130,9 +1130,10 @@ extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, 
   TG_REQUIRE(mode == 0 || (mask && xin), "tg_conv_to1_fwd: composite mode needs mask and xin");
   To1Taps taps;
   TG_REQUIRE(fill_taps(&taps, ncls, cls_count, tap_dh, tap_dw) > 0, "tg_conv_to1_fwd: bad tap table");
-  if (thin_mma_enabled() && C == 64 && scratch != nullptr) {
-    int ntaps = 0;
-    for (int i = 0; i < ncls; ++i) ntaps += cls_count[i];
+  int ntaps_all = 0;
+  for (int i = 0; i < ncls; ++i) ntaps_all += cls_count[i];
+  if (thin_mma_enabled() && C == 64 && (scratch != nullptr || to1_fused_covers(x_split, H, W, taps, ntaps_all, Ho, Wo))) {
+    const int ntaps = ntaps_all;
     const int rc = to1_fwd_mma(x, x_split, B, H, W, wgt, taps, ntaps, bias, Ho, Wo, mode, mask, xin, out, sig_out, scratch,
                                scratch_floats, reinterpret_cast<cudaStream_t>(stream));
     if (rc == 0) return 0;
@@ -1174,6 +1175,17 @@ extern "C" int tg_conv_to1_fwd(const void* x, int x_split, int B, int H, int W, 
       sig_out);
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int tg_conv_to1_fwd_kernels(int x_split, int H, int W, int C, int ncls, const int* cls_count, const int8_t* tap_dh,
+                                       const int8_t* tap_dw, int Ho, int Wo) {
+  using namespace tg;
+  if (cls_count == nullptr || tap_dh == nullptr || tap_dw == nullptr || (ncls != 1 && ncls != 4)) return 0;
+  To1Taps taps;
+  if (fill_taps(&taps, ncls, cls_count, tap_dh, tap_dw) <= 0) return 0;
+  int ntaps = 0;
+  for (int i = 0; i < ncls; ++i) ntaps += cls_count[i];
+  return (C == 64 && to1_fused_covers(x_split, H, W, taps, ntaps, Ho, Wo)) ? 1 : 2;
 }
 
 extern "C" size_t tg_conv_to1_fwd_scratch_floats(int B, int H, int W, int C, int ntaps) {

@@ -906,11 +906,251 @@ tapsum_kernel(const float* __restrict__ T, unsigned total_in, int x_split, int B
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 64 -> 1 convolution with taps inside a 3x3 window, one kernel: a 16 x 16 pixel patch (interior 14 x 14 + halo) arrives as
+// ONE TMA box (zero-filled outside the image = the zero padding), two MMAs (M = 128 patch pixels each, N = 32: the tap
+// weight vectors as bf16 hi parts in columns 0..15 and lo parts in columns 16..31, K = 64 channels) leave
+// T[pixel][tap] with pixel = TMEM lane; each epilogue thread owns one patch pixel: it adds hi + lo, parks its <= 16 tap
+// products in shared memory, and after a barrier the interior pixels gather theirs at the tap offsets, add the bias and
+// apply the sigmoid / composite epilogue (generator.py:56-62). Compared with tapdot + tapsum this drops the [taps][pixels]
+// fp32 scratch round trip (72 B per pixel next to the 128 B read of x) and 3/4 of the MMA work (N = 32 instead of
+// 128 mostly idle accumulator rows x 256 pixels).
+// warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator, warps 4-7 / 8-11: two epilogue groups on alternate tiles.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTfStages = 4;
+constexpr int kTfPatch = 16, kTfIn = 14;                    // patch edge, interior edge
+constexpr int kTfSmem = kTfStages * 32768 + 4096 + 4 * 16 * 256 * 4 + 256 + 1024;
+
+struct To1FusedParams {
+  int B, H, W, tiles_h, tiles_w, ntaps;
+  int8_t dh[16], dw[16];
+  const float* wgt;        // [ntaps][64]
+  const float* bias;       // optional [1]
+  int mode;                // 0: out = conv + bias; 1: out = sigmoid(conv + bias) * (1 - mask) + xin * mask
+  const uint8_t* mask;
+  const float* xin;
+  float* out;
+  float* sig_out;
+};
+
+__global__ void __launch_bounds__(384, 1)
+to1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ To1FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_x = smem;                                     // [stage][256 patch pixels][128 B]
+  uint8_t* s_w = s_x + kTfStages * 32768;                  // [32 rows: hi taps | lo taps][128 B]
+  float* s_t = reinterpret_cast<float*>(s_w + 4096);       // [2 groups][2][16 taps][256 pixels]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_t + 4 * 16 * 256);
+  uint64_t* full = bars;                                   // [kTfStages]
+  uint64_t* empty = bars + kTfStages;                      // [kTfStages]
+  uint64_t* tfull = bars + 2 * kTfStages;                  // [2]
+  uint64_t* tempty = bars + 2 * kTfStages + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTfStages + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < 4096 / 16; i += 384) reinterpret_cast<uint4*>(s_w)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  for (int i = tid; i < p.ntaps * 64; i += 384) {
+    const int t = i >> 6, c = i & 63;
+    const uint32_t hl = split_hi_lo(__ldg(p.wgt + i));
+    const int n0 = t, n1 = 16 + t;
+    *reinterpret_cast<unsigned short*>(s_w + (n0 >> 3) * 1024 + (n0 & 7) * 128 + (((c >> 3) ^ (n0 & 7)) << 4) + (c & 7) * 2) =
+        static_cast<unsigned short>(hl & 0xffffu);
+    *reinterpret_cast<unsigned short*>(s_w + (n1 >> 3) * 1024 + (n1 & 7) * 128 + (((c >> 3) ^ (n1 & 7)) << 4) + (c & 7) * 2) =
+        static_cast<unsigned short>(hl >> 16);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kTfStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 2) tmem_alloc<128>(tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const unsigned per_img = static_cast<unsigned>(p.tiles_h) * p.tiles_w;
+  const unsigned tiles = static_cast<unsigned>(p.B) * per_img;
+  const unsigned my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (unsigned i = 0; i < my_tiles; ++i) {
+        const unsigned tile = blockIdx.x + i * gridDim.x;
+        const int b = static_cast<int>(tile / per_img), r = static_cast<int>(tile % per_img);
+        const int ty = r / p.tiles_w, tx = r % p.tiles_w;
+        const int stage = static_cast<int>(i % kTfStages);
+        mbar_wait(&empty[stage], ((i / kTfStages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&full[stage], 32768);
+        tma_load_4d(s_x + stage * 32768, &tm_x, &full[stage], 0, tx * kTfIn - 1, ty * kTfIn - 1, b);
+      }
+    }
+  } else if (warp == 1) {
+    {   // whole warp (warp-uniform addressing); one elected lane issues
+      constexpr uint32_t idesc = make_idesc_bf16(128, 32, false, false);
+      const uint64_t dx0 = make_smem_desc(smem_u32(s_x), 16, 1024), dw0 = make_smem_desc(smem_u32(s_w), 16, 1024);
+      const uint32_t x_lo0 = static_cast<uint32_t>(dx0), w_lo0 = static_cast<uint32_t>(dw0), d_hi = static_cast<uint32_t>(dx0 >> 32);
+      for (unsigned i = 0; i < my_tiles; ++i) {
+        const int stage = static_cast<int>(i % kTfStages);
+        const int acc = static_cast<int>(i & 1u);
+        mbar_wait(&tempty[acc], ((i >> 1) & 1u) ^ 1u);
+        mbar_wait(&full[stage], (i / kTfStages) & 1u);
+        tc_fence_after();
+        const uint32_t x_lo = x_lo0 + static_cast<uint32_t>(stage) * (32768 >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16_lh(tmem + acc * 64 + half * 32, x_lo + half * (16384 >> 4) + ks * 2, d_hi, w_lo0 + ks * 2, d_hi, idesc,
+                           ks ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          umma_commit(&tfull[acc]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // two groups of four warps take alternate tiles (group g owns accumulator g), so that one tile's TMEM read, shared-memory
+    // exchange and global epilogue traffic overlap the other's; thread = patch pixels e0 (rows 0-7) and e0 + 128 (rows 8-15)
+    const int g = (warp - 4) >> 2, q = warp & 3;   // TMEM lane quarter = warp % 4
+    const int e0 = q * 32 + lane;
+    const float bv = p.bias ? __ldg(p.bias) : 0.f;
+    int off[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) off[t] = t < p.ntaps ? t * 256 + p.dh[t] * kTfPatch + p.dw[t] : 0;
+    float* const st_base = s_t + g * (2 * 16 * 256);
+    unsigned n = 0;
+    for (unsigned i = g; i < my_tiles; i += 2, ++n) {
+      const unsigned tile = blockIdx.x + i * gridDim.x;
+      const int b = static_cast<int>(tile / per_img), r = static_cast<int>(tile % per_img);
+      const int ty = r / p.tiles_w, tx = r % p.tiles_w;
+      float* st = st_base + (n & 1u) * (16 * 256);
+      // output pixels of this thread and their composite operands, requested before the accumulator is waited for
+      bool live[2];
+      size_t o[2];
+      uint32_t mk[2] = {0u, 0u};       // raw loads only: nothing may consume them before the gather (they stay in flight)
+      float xi[2] = {0.f, 0.f};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int e = e0 + h * 128, ph = e >> 4, pw = e & 15;
+        const int oh = ty * kTfIn + ph - 1, ow = tx * kTfIn + pw - 1;
+        live[h] = ph >= 1 && ph <= kTfIn && pw >= 1 && pw <= kTfIn && oh < p.H && ow < p.W;
+        o[h] = (static_cast<size_t>(b) * p.H + (live[h] ? oh : 0)) * p.W + (live[h] ? ow : 0);
+        if (p.mode != 0 && live[h]) {
+          mk[h] = __ldg(p.mask + o[h]);
+          xi[h] = __ldg(p.xin + o[h]);
+        }
+      }
+      mbar_wait(&tfull[g], n & 1u);
+      tc_fence_after();
+      uint32_t raw0[32], raw1[32];
+      tmem_ld_32x32(tmem + (static_cast<uint32_t>(q * 32) << 16) + g * 64, raw0);
+      tmem_ld_32x32(tmem + (static_cast<uint32_t>(q * 32) << 16) + g * 64 + 32, raw1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[g]);
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        if (t < p.ntaps) {
+          st[t * 256 + e0] = __uint_as_float(raw0[t]) + __uint_as_float(raw0[16 + t]);
+          st[t * 256 + e0 + 128] = __uint_as_float(raw1[t]) + __uint_as_float(raw1[16 + t]);
+        }
+      }
+      if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");      // the tile's tap products are all in shared memory
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      // pin the first use of the prefetched composite operands below the barrier (the compiler otherwise hoists the mask
+      // test above the accumulator wait and stalls there on the load: ncu, 18 % of the samples)
+      asm volatile("" : "+r"(mk[0]), "+r"(mk[1]), "+f"(xi[0]), "+f"(xi[1]));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (!live[h]) continue;
+        const int e = e0 + h * 128;
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (t < p.ntaps) a += st[off[t] + e];
+        const float v = a + bv;
+        if (p.mode == 0) {
+          p.out[o[h]] = v;
+        } else {
+          const float sg = 1.f / (1.f + __expf(-v));
+          if (p.sig_out) p.sig_out[o[h]] = sg;
+          const float m = mk[h] ? 1.f : 0.f;
+          p.out[o[h]] = sg * (1.f - m) + xi[h] * m;
+        }
+      }
+      // no second barrier: the group's other buffer is used next, and nobody reaches this one again before the next bar.sync
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<128>(tmem);
+}
+
+static bool to1_fused_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TG_NO_TO1_FUSED");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+bool to1_fused_covers(int x_split, int H, int W, const To1Taps& taps, int ntaps, int Ho, int Wo) {
+  if (!thin_mma_enabled() || !to1_fused_enabled() || x_split || Ho != H || Wo != W) return false;
+  if (taps.ncls != 1 || ntaps < 1 || ntaps > 16 || H < kTfPatch || W < kTfPatch) return false;
+  for (int t = 0; t < ntaps; ++t) {
+    const int dh = taps.dh[taps.begin[0] + t], dw = taps.dw[taps.begin[0] + t];
+    if (dh < -1 || dh > 1 || dw < -1 || dw > 1) return false;
+  }
+  return true;
+}
+
+// returns 0 when launched, -1 when the shape is not covered
+static int to1_fused_launch(const void* x, int B, int H, int W, const float* wgt, const To1Taps& taps, int ntaps, const float* bias,
+                            int mode, const uint8_t* mask, const float* xin, float* out, float* sig_out, cudaStream_t st) {
+  if (!to1_fused_covers(0, H, W, taps, ntaps, H, W)) return -1;
+  To1FusedParams p{};
+  for (int t = 0; t < ntaps; ++t) {
+    p.dh[t] = taps.dh[taps.begin[0] + t];
+    p.dw[t] = taps.dw[taps.begin[0] + t];
+  }
+  p.B = B; p.H = H; p.W = W; p.ntaps = ntaps;
+  p.tiles_h = (H + kTfIn - 1) / kTfIn;
+  p.tiles_w = (W + kTfIn - 1) / kTfIn;
+  p.wgt = wgt; p.bias = bias; p.mode = mode; p.mask = mask; p.xin = xin; p.out = out; p.sig_out = sig_out;
+  CUtensorMap tm_x;
+  const uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+  const uint64_t str[3] = {128, static_cast<uint64_t>(W) * 128, static_cast<uint64_t>(W) * H * 128};
+  const uint32_t box[4] = {64, kTfPatch, kTfPatch, 1};
+  if (make_tmap_bf16(&tm_x, x, 4, dims, str, box) != 0) return -3;
+  TG_SET_SMEM_ONCE((to1_fused_kernel), kTfSmem);
+  const long tiles = static_cast<long>(B) * p.tiles_h * p.tiles_w;
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  to1_fused_kernel<<<grid, 384, kTfSmem, st>>>(tm_x, p);
+  TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int to1_fwd_mma(const void* x, int x_split, int B, int H, int W, const float* wgt, const To1Taps& taps, int ntaps,
                 const float* bias, int Ho, int Wo, int mode, const uint8_t* mask, const float* xin, float* out,
                 float* sig_out, float* scratch, size_t scratch_floats, cudaStream_t st) {
   const long total = static_cast<long>(B) * H * W;
   if (ntaps < 1 || ntaps > 32 || total >= (1L << 31) || static_cast<long>(B) * Ho * Wo >= (1L << 31)) return -1;
+  if (to1_fused_covers(x_split, H, W, taps, ntaps, Ho, Wo)) {
+    const int rc = to1_fused_launch(x, B, H, W, wgt, taps, ntaps, bias, mode, mask, xin, out, sig_out, st);
+    if (rc != -1) return rc;
+  }
   if (scratch == nullptr || scratch_floats < static_cast<size_t>(ntaps) * total) return -1;
   if (x_split && (H % 2 || W % 2)) return -1;
   if (total % 4 != 0) return -1;                       // 16-byte stores into the rows of T

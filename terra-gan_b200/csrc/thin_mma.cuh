@@ -61,6 +61,9 @@ int to1_fwd_mma(const void* x, int x_split, int B, int H, int W, const float* wg
                 const float* bias, int Ho, int Wo, int mode, const uint8_t* mask, const float* xin, float* out,
                 float* sig_out, float* scratch, size_t scratch_floats, cudaStream_t st);
 
+// true when to1_fwd_mma runs this shape as ONE kernel without scratch (taps inside a 3x3 window, plain layout, same-size output)
+bool to1_fused_covers(int x_split, int H, int W, const To1Taps& taps, int ntaps, int Ho, int Wo);
+
 // k in {3, 4, 7}. grid_cap > 0 bounds the grid (= number of per-CTA stats rows); returns 0, or -1 if k is unsupported.
 int rowgemm_dispatch(int k, const RowGemmParams& p, int grid_cap, int* grid_used, cudaStream_t st);
 bool thin_mma_enabled();   // env TG_NO_THIN_MMA=1 selects the CUDA-core kernels (A/B timing only)

@@ -117,6 +117,8 @@ PROTOTYPES = {
                                 C.POINTER(C.c_int8), C.POINTER(C.c_int8), c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_size_t, c_void_p]),
     "tg_conv_to1_fwd_scratch_floats": (C.c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "tg_conv_to1_fwd_kernels": (c_int, [c_int, c_int, c_int, c_int, c_int, C.POINTER(c_int), C.POINTER(C.c_int8),
+                                        C.POINTER(C.c_int8), c_int, c_int]),
     "tg_adam_repack": (c_int, [C.POINTER(AdamTensor), c_int, C.c_float, C.c_float, C.c_float, C.c_float, c_int, c_void_p]),
     "tg_conv_to1_bwd_data": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, C.POINTER(C.c_int8),
                                      C.POINTER(C.c_int8), c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -196,7 +198,7 @@ KERNELS_PER_CALL = {
     "tg_conv_igemm": 1, "tg_wgrad_igemm": 1, "tg_wgrad_reduce": 1,
     "tg_bn_finalize": 1, "tg_bn_eval_coeff": 1, "tg_bn_apply": 1, "tg_bn_bwd_reduce": 1, "tg_bn_bwd_finalize": 1,
     "tg_bn_bwd_apply": 1, "tg_upsample_concat": 1, "tg_upsample_concat_bwd": 1, "tg_maxpool2": 1,
-    "tg_maxpool2_bwd": 1, "tg_conv_c1_fwd": 1, "tg_conv_c1_wgrad": 2, "tg_conv_to1_fwd": 1, "tg_conv_to1_fwd+tapsum": 1, "tg_conv_to1_fwd_scratch_floats": 0,
+    "tg_maxpool2_bwd": 1, "tg_conv_c1_fwd": 1, "tg_conv_c1_wgrad": 2, "tg_conv_to1_fwd": 1, "tg_conv_to1_fwd+tapsum": 1, "tg_conv_to1_fwd_scratch_floats": 0, "tg_conv_to1_fwd_kernels": 0,
     "tg_conv_to1_bwd_data": 1, "tg_conv_to1_wgrad": 2, "tg_final_bwd_pre": 1, "tg_inpaint_loss_fwd": 2,
     "tg_inpaint_loss_bwd": 1, "tg_l1_bf16_fwd": 2, "tg_l1_bf16_bwd": 1, "tg_bce_logits_fwd": 1, "tg_bce_logits_bwd": 1,
     "tg_quality_metrics": 2, "tg_resize_bilinear_u8": 2, "tg_dsm_normalize": 2, "tg_resize_ksize": 0, "tg_resize_coeffs": 0,

@@ -513,7 +513,8 @@ def conv_to1_fwd(x, x_split, hw, wgt, cls_counts, taps, bias, out_hw, mode=0, ma
                                         ptr(bias), Ho, Wo, mode, ptr(mask), ptr(xin), ptr(out), ptr(sig), stream_ptr()),
               "tg_conv_to1_fwd_f32")
         return out, sig
-    nscr = lib().tg_conv_to1_fwd_scratch_floats(B, H, W, Cc, len(taps))
+    one_kernel = lib().tg_conv_to1_fwd_kernels(1 if x_split else 0, H, W, Cc, len(cls_counts), cc, dh, dw, Ho, Wo) == 1
+    nscr = 0 if one_kernel else lib().tg_conv_to1_fwd_scratch_floats(B, H, W, Cc, len(taps))
     scratch = torch.empty((nscr,), dtype=torch.float32, device=x.device) if nscr else None
     ev0 = _prof_begin()
     check(lib().tg_conv_to1_fwd(ptr(x), 1 if x_split else 0, B, H, W, Cc, ptr(wgt), len(cls_counts), cc, dh, dw,

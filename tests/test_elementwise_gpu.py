@@ -180,6 +180,31 @@ def test_conv_c1_fwd_wgrad(k, s, p, act, split):
     assert rel_err(dw, dw_ref) < 1e-3 and rel_err(db, db_ref) < 1e-3
 
 
+@pytest.mark.parametrize("B,H,W,mode", [(1, 16, 16, 0), (3, 48, 80, 1), (2, 30, 100, 0), (2, 128, 64, 1), (1, 8, 24, 0)])
+def test_to1_3x3_fused_ragged_patches(B, H, W, mode):
+    """64 -> 1, 3x3: the one-kernel path (14 x 14 interior patches) on sizes that are not multiples of the patch, non-square
+    grids, both epilogues; H or W < 16 takes the two-kernel path (generator.py:56-62, losses.py:79-89 data gradient)."""
+    torch.manual_seed(21)
+    C = 64
+    x = torch.randn(B, C, H, W, device=DEV).bfloat16().float()
+    w = torch.randn(1, C, 3, 3, device=DEV) / 24
+    b = torch.randn(1, device=DEV)
+    mask = (torch.rand(B, 1, H, W, device=DEV) < 0.5).float()
+    xin = torch.rand(B, 1, H, W, device=DEV) * mask
+    conv = F.conv2d(x, w, b, 1, 1)
+    ref = conv if mode == 0 else torch.sigmoid(conv) * (1 - mask) + xin * mask
+    pl = P.fprop_plan(3, 1, 1)
+    taps = [(dh, dw) for (_, dh, dw) in pl.taps]
+    wt = w[0].permute(1, 2, 0).reshape(9, C).contiguous()
+    m8 = ops.mask_from_f32(mask[:, 0].contiguous())
+    out, sig = ops.conv_to1_fwd(nhwc(x).bfloat16(), False, (H, W), wt, [9], taps, b, (H, W), mode=mode,
+                                mask=m8 if mode else None, xin=xin[:, 0].contiguous() if mode else None, want_sig=bool(mode))
+    assert out.shape == (B, H, W)
+    assert rel_err(out, ref[:, 0]) < 2e-3
+    if mode:
+        assert rel_err(sig, torch.sigmoid(conv)[:, 0]) < 2e-3
+
+
 def test_final_conv_sigmoid_composite_and_backward():
     torch.manual_seed(7)
     B, H, C = 2, 32, 64
