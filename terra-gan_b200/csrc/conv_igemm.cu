@@ -33,10 +33,14 @@ constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
 // kMT: M-tiles (128 pixels each) that share every weight tile. The operand traffic per MMA — 16 KB of pixels + BN x 128 B
 // of weights for four MMAs — is what bounds the N = 128 layers (128 B/clk/SM from L2, 50 % tensor pipe in ncu);
 // two M-tiles per unit, each with its own accumulator pair, cut it to 96 B/clk.
-template <int BN, int kMT = 1>
+// k2: CTA pair (cluster of 2, tcgen05.mma.cta_group::2): the pair computes a 256-pixel x BN tile; each CTA stages its own
+// 128 pixels and HALF of the weight tile (BN/2 rows), the tensor cores of both SMs read the two halves across the pair.
+// Per SM and K block that is 16 KB + 16 KB instead of 16 KB + 32 KB for four N = 256 MMAs (512 clocks): 64 instead of
+// 96 B/clk of shared-memory operand reads and of L2 -> SM fill, and room for 5 stages instead of 3.
+template <int BN, int kMT = 1, bool k2 = false>
 struct ConvSmem {
-  static constexpr int kStages = (BN >= 256 || kMT > 1) ? 3 : 4;
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStages = k2 ? 5 : (BN >= 256 || kMT > 1) ? 3 : 4;
+  static constexpr int kBBytes = k2 ? BN * 64 : BN * 128;
   static constexpr int kStageBytes = kMT * kABytes + kBBytes;
   static constexpr int kTiles = kStages * kStageBytes;
   static constexpr int kStatsFloats = 4 * 2 * 512;  // per epilogue warp (sum, sumsq) x channel
@@ -48,7 +52,7 @@ struct ConvSmem {
 
 // kF32: fp32 activations / weights in shared memory (TMA boxes of 32 channels = the same 128-byte rows),
 // kind::tf32 MMAs, fp32 output -- the verification path.
-template <int BN, bool kF32 = false, int kMT = 1>
+template <int BN, bool kF32 = false, int kMT = 1, bool k2 = false>
 __global__ void __launch_bounds__(384, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvKParams p) {
@@ -56,10 +60,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  using S = ConvSmem<BN, kMT>;
+  using S = ConvSmem<BN, kMT, k2>;
   constexpr int kStages = S::kStages;
   constexpr int kAcc = 2 * kMT;                 // accumulators: two sets of kMT
   static_assert(kAcc * BN <= 512, "accumulators must fit the 512 TMEM columns");
+  static_assert(!k2 || (kMT == 1 && !kF32), "the CTA-pair variant is bf16, one M-tile per CTA");
+  // CTA pair: rank 0 (the leader) issues the MMAs for both SMs; its full / tempty barriers collect the arrivals of both CTAs
+  const uint32_t cta_rank = k2 ? cluster_ctarank() : 0u;
   float* s_stats = reinterpret_cast<float*>(smem + S::kTiles);
   float* s_vec = s_stats + S::kStatsFloats;
   uint8_t* s_out = reinterpret_cast<uint8_t*>(s_vec + S::kVecFloats);
@@ -98,27 +105,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], k2 ? 16 : 8);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (k2) tmem_alloc_2cta<kTmemCols>(tmem_slot);
+    else tmem_alloc<kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (k2) cluster_sync_all();      // the peer's barriers and TMEM exist before anything remote touches them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   // a unit = kMT consecutive M-tiles (the host guarantees m_tiles % kMT == 0) x one N-tile of one sub-convolution
   const int m_tiles = p.tiles_b * p.tiles_h * p.tiles_w;
-  const int m_units = m_tiles / kMT;
+  constexpr int kUnitM = k2 ? 2 : kMT;        // M-tiles per unit (CTA pair: one per CTA)
+  const int m_units = m_tiles / kUnitM;
   const int total_tiles = p.num_sub * m_units * p.n_tiles;
+  const int first_tile = k2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = k2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int nt = tile % p.n_tiles;
         const int rest = tile / p.n_tiles;
         const int mu = rest % m_units;
@@ -126,7 +140,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int w0[kMT], h0[kMT], b0[kMT];
 #pragma unroll
         for (int j = 0; j < kMT; ++j) {
-          const int mt = mu * kMT + j;
+          const int mt = k2 ? mu * 2 + static_cast<int>(cta_rank) : mu * kMT + j;
           w0[j] = (mt % p.tiles_w) * p.Wt;
           h0[j] = ((mt / p.tiles_w) % p.tiles_h) * p.Ht;
           b0[j] = (mt / (p.tiles_w * p.tiles_h)) * p.Bt;
@@ -139,12 +153,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * S::kStageBytes;
             uint8_t* sbm = sa + kMT * kABytes;
+            if constexpr (k2) {
+              // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+              const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              tma_load_5d_2cta(sa, &tmA, lead_bar, cb * kKB, w0[0] + dw, h0[0] + dh, pl, b0[0]);
+              tma_load_2d_2cta(sbm, &tmB, lead_bar, sub.k_off + (t * p.cin_blocks + cb) * kKB,
+                               nt * BN + static_cast<int>(cta_rank) * (BN / 2));
+            } else {
             mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
 #pragma unroll
             for (int j = 0; j < kMT; ++j)
               tma_load_5d(sa + j * kABytes, &tmA, &full_bar[stage], cb * kKB, w0[j] + dw, h0[j] + dh, pl, b0[j]);
             tma_load_2d(sbm, &tmB, &full_bar[stage], sub.k_off + (t * p.cin_blocks + cb) * kKB,
                         nt * BN);
+            }
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -152,19 +175,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       }
+      if constexpr (k2) {
+        // the leader's multicast commits arrive on THIS CTA's empty barriers: drain them before the CTA may exit
+        for (int i = 0; i < kStages; ++i) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && cta_rank == 0) {
     // ===================== MMA issuer =====================
     // whole warp runs the loop (warp-uniform descriptors in uniform registers); one elected lane issues
     {
-      constexpr uint32_t idesc = kF32 ? make_idesc_tf32(128, BN, false, false) : make_idesc_bf16(128, BN, false, false);
+      constexpr uint32_t idesc = kF32 ? make_idesc_tf32(128, BN, false, false)
+                                      : make_idesc_bf16(k2 ? 256 : 128, BN, false, false);
       const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);     // A and B: K-major, 8-row atoms 1024 B apart
       const uint32_t d_lo0 = static_cast<uint32_t>(d0), d_hi = static_cast<uint32_t>(d0 >> 32);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;               // first accumulator of the current set (0 or kMT)
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int sb = (tile / p.n_tiles) / m_units;
         const int kblocks = p.sub[sb].tap_count * p.cin_blocks;
 #pragma unroll
@@ -183,10 +217,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (kF32) umma_tf32_lh(d_tmem + j * BN, a_lo + j * (kABytes >> 4) + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
+                else if (k2) umma_bf16_lh_2cta(d_tmem, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
                 else umma_bf16_lh(d_tmem + j * BN, a_lo + j * (kABytes >> 4) + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, k ? 1u : static_cast<uint32_t>(kb != 0));
               }
             }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if constexpr (k2) umma_commit_2cta(&empty_bar[stage]);   // both CTAs' slots
+            else umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           }
           if (++stage == kStages) {
             stage = 0;
@@ -195,7 +231,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < kMT; ++j) umma_commit(&tfull_bar[acc + j]);  // accumulators complete -> epilogue
+          for (int j = 0; j < kMT; ++j) {  // accumulators complete -> epilogue (of both CTAs of a pair)
+            if constexpr (k2) umma_commit_2cta(&tfull_bar[acc + j]);
+            else umma_commit(&tfull_bar[acc + j]);
+          }
         }
         acc += kMT;
         if (acc == kAcc) {
@@ -214,7 +253,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if constexpr (kF32) {
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int nt = tile % p.n_tiles;
         const int rest = tile / p.n_tiles;
         const int sb = rest / m_units;
@@ -244,13 +283,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       constexpr int kMode = decltype(mode_tag)::value;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int nt = tile % p.n_tiles;
         const int rest = tile / p.n_tiles;
         const int sb = rest / m_units;
 #pragma unroll 1
         for (int j = 0; j < kMT; ++j) {
-          const int mt = (rest % m_units) * kMT + j;
+          const int mt = k2 ? (rest % m_units) * 2 + static_cast<int>(cta_rank) : (rest % m_units) * kMT + j;
           const int tw = mt % p.tiles_w;
           const int th = (mt / p.tiles_w) % p.tiles_h;
           const int tb = mt / (p.tiles_w * p.tiles_h);
@@ -264,7 +303,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                                             e_bt, nullptr, &pre);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+            if constexpr (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // the leader's barrier
+            else mbar_arrive(&tempty_bar[acc]);
+          }
           if (++acc == kAcc) {
             acc = 0;
             acc_phase ^= 1;
@@ -293,9 +335,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
+  if constexpr (k2) cluster_sync_all();      // neither CTA frees TMEM / exits while the pair's MMAs or arrivals may still touch it
+  else __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == 2) {
+    if constexpr (k2) tmem_dealloc_2cta<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -352,6 +398,46 @@ static int launch_conv(const tg_conv_args* a, const CUtensorMap& tmA, const CUte
   TG_SET_SMEM_ONCE((conv_igemm_kernel<BN, kF32, kMT>), S::kTotal);
   conv_igemm_kernel<BN, kF32, kMT><<<grid, 384, S::kTotal, st>>>(tmA, tmB, kp);
   TG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static bool conv_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TG_NO_CONV_PAIR");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+// smallest number of 256-pixel units for which the CTA-pair kernel is chosen: one per pair of SMs, unless
+// TG_CONV_PAIR_MIN overrides it (the parity tests force the pair kernel onto their small shapes with 1)
+static long conv_pair_min_units(int sms) {
+  static long v = -1;
+  if (v < 0) {
+    const char* e = getenv("TG_CONV_PAIR_MIN");
+    v = (e != nullptr && atol(e) > 0) ? atol(e) : 0;
+  }
+  return v > 0 ? v : sms / 2;
+}
+
+// CTA-pair variant (cluster of 2, cta_group::2 MMAs); `grid` = 2 x the number of pairs
+template <int BN>
+static int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKParams& kp, int grid, cudaStream_t st) {
+  using S = ConvSmem<BN, 1, true>;
+  TG_SET_SMEM_ONCE((conv_igemm_kernel<BN, false, 1, true>), S::kTotal);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, false, 1, true>, tmA, tmB, kp));
   return 0;
 }
 
@@ -467,15 +553,26 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
     uint32_t box[5] = {(uint32_t)kb_elems, (uint32_t)kp.Wt, (uint32_t)kp.Ht, 1, (uint32_t)kp.Bt};
     if ((f32 ? make_tmap_f32 : make_tmap_bf16)(&tmA, a->x, 5, dims, str, box) != 0) return -3;
   }
-  {
-    uint64_t dims[2] = {(uint64_t)a->Ktot, (uint64_t)a->N};
-    uint64_t str[1] = {(uint64_t)a->Ktot * esz};
-    uint32_t box[2] = {(uint32_t)kb_elems, (uint32_t)BN};
-    if ((f32 ? make_tmap_f32 : make_tmap_bf16)(&tmB, a->w, 2, dims, str, box) != 0) return -3;
-  }
   const long m_tiles_all = (long)kp.tiles_b * kp.tiles_h * kp.tiles_w;
   const int sms = num_sms();
   TG_REQUIRE(sms > 0, "tg_conv_igemm: no CUDA device");
+  // N = 256 tiles on CTA pairs (cta_group::2) whenever there is at least one 256-pixel unit per pair of SMs
+  const long pair_units = (long)kp.num_sub * (m_tiles_all / 2) * kp.n_tiles;
+  const bool pair = !f32 && BN == 256 && conv_pair_enabled() && m_tiles_all % 2 == 0 && pair_units >= conv_pair_min_units(sms);
+  {
+    uint64_t dims[2] = {(uint64_t)a->Ktot, (uint64_t)a->N};
+    uint64_t str[1] = {(uint64_t)a->Ktot * esz};
+    uint32_t box[2] = {(uint32_t)kb_elems, (uint32_t)(pair ? BN / 2 : BN)};
+    if ((f32 ? make_tmap_f32 : make_tmap_bf16)(&tmB, a->w, 2, dims, str, box) != 0) return -3;
+  }
+  if (pair) {
+    const int grid2 = 2 * (int)(pair_units < sms / 2 ? pair_units : sms / 2);
+    if (a->stats != nullptr) {
+      TG_REQUIRE(a->stats_rows_cap >= grid2, "tg_conv_igemm: stats_rows_cap %d < grid %d", a->stats_rows_cap, grid2);
+    }
+    a->stats_rows_used = grid2;
+    return launch_conv_pair<256>(tmA, tmB, kp, grid2, reinterpret_cast<cudaStream_t>(stream));
+  }
   // two M-tiles per unit sharing the weight tile (N = 128 or 64): only when that still fills the machine
   const bool wide = !f32 && (BN == 128 || BN == 64) && conv_wide_enabled() && m_tiles_all % 2 == 0 &&
                     (long)kp.num_sub * (m_tiles_all / 2) * kp.n_tiles >= 2L * sms;
