@@ -556,9 +556,11 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
   const long m_tiles_all = (long)kp.tiles_b * kp.tiles_h * kp.tiles_w;
   const int sms = num_sms();
   TG_REQUIRE(sms > 0, "tg_conv_igemm: no CUDA device");
-  // N = 256 tiles on CTA pairs (cta_group::2) whenever there is at least one 256-pixel unit per pair of SMs
+  // N = 256 / 192 tiles on CTA pairs (cta_group::2) whenever there is at least one 256-pixel unit per pair of SMs
   const long pair_units = (long)kp.num_sub * (m_tiles_all / 2) * kp.n_tiles;
-  const bool pair = !f32 && BN == 256 && conv_pair_enabled() && m_tiles_all % 2 == 0 && pair_units >= conv_pair_min_units(sms);
+  static const bool pair192 = [] { const char* e = getenv("TG_CONV_PAIR_192"); return e != nullptr && e[0] == '1'; }();
+  const bool pair = !f32 && (BN == 256 || (BN == 192 && pair192)) && conv_pair_enabled() && m_tiles_all % 2 == 0 &&
+                    pair_units >= conv_pair_min_units(sms);
   {
     uint64_t dims[2] = {(uint64_t)a->Ktot, (uint64_t)a->N};
     uint64_t str[1] = {(uint64_t)a->Ktot * esz};
@@ -571,7 +573,8 @@ extern "C" int tg_conv_igemm(tg_conv_args* a, void* stream) {
       TG_REQUIRE(a->stats_rows_cap >= grid2, "tg_conv_igemm: stats_rows_cap %d < grid %d", a->stats_rows_cap, grid2);
     }
     a->stats_rows_used = grid2;
-    return launch_conv_pair<256>(tmA, tmB, kp, grid2, reinterpret_cast<cudaStream_t>(stream));
+    return BN == 256 ? launch_conv_pair<256>(tmA, tmB, kp, grid2, reinterpret_cast<cudaStream_t>(stream))
+                     : launch_conv_pair<192>(tmA, tmB, kp, grid2, reinterpret_cast<cudaStream_t>(stream));
   }
   // two M-tiles per unit sharing the weight tile (N = 128 or 64): only when that still fills the machine
   const bool wide = !f32 && (BN == 128 || BN == 64) && conv_wide_enabled() && m_tiles_all % 2 == 0 &&

@@ -16,8 +16,16 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
     --clock-control none --profile-from-start off \
     -k 'regex:conv_igemm_kernel|conv_halo|wgrad_igemm|wgrad_wide|wgrad_halo|rowgemm64|tapdot|tapwgrad_kernel' \
     --csv --log-file $O/r02_ncu_tensorcore_step_metrics.csv python tools/profile_step.py 64 3 > $O/r02_ncu_tc.log 2>&1
-for k in 'wgrad_wide_kernel' 'conv_igemm_kernel' 'rowgemm64_kernel' 'tapwgrad_kernel'; do
+# --set full captures: the first three conv_igemm launches of the step are enc2 (<128, kMT = 2>), enc3 and enc4 (the CTA-pair <256> kernel)
+for k in 'conv_igemm_kernel' 'conv_halo_kernel' 'wgrad_wide_kernel' 'bn_bwd_reduce_kernel'; do
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$k" -c 3 \
-      -o $O/r02b_full_$k -f python tools/profile_step.py 64 3 > $O/r02b_ncu_full_$k.log 2>&1 || true
+      -o $O/r02c_full_$k -f python tools/profile_step.py 64 3 > $O/r02c_ncu_full_$k.log 2>&1 || true
 done
+# A/B: CTA-pair kernel also for the N = 192 layer (dec2 data gradient)
+for v in 0 1 0 1; do
+  TG_CONV_PAIR_192=$v python bench.py --no-cpu-baseline --steps 8 --warmup 3 --per-launch pair192_pl_$v.txt 2>> $O/bench.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('pair192=$v', round(d['value'],1), round(d['ms_per_step'],2), d['clocks']['sm_mhz'])" >> $O/pair192_ab.txt
+done
+cat $O/pair192_ab.txt
 ls -la $O/*.ncu-rep
