@@ -26,16 +26,7 @@ struct __align__(16) bf16x8 {
   __nv_bfloat162 v[4];
 };
 
-__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
-  const uint4 raw = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) { vload8(p, f); }
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   uint4 raw;
   raw.x = pack_bf16x2(f[0], f[1]);
@@ -57,6 +48,40 @@ __device__ __forceinline__ void ldg8f(const float* p, float (&f)[8]) {
 __device__ __forceinline__ long split_index(int b, int h, int w, int H, int W) {
   return ((static_cast<long>(b) * 4 + 2 * (h & 1) + (w & 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
 }
+
+// (b, h, w) of the pixels first, first + stride, first + 2 stride, ... without per-pixel integer divisions: the stride is
+// decomposed once into (db, dh, dw) and added with carries. (The two runtime divisions per pixel of the parity-split
+// index, plus 64-bit multiply-adds for three addresses, were ~100 of the ~280 instructions these issue-bound kernels
+// spent per 8-channel vector.)
+struct PixelWalk {
+  int b, h, w, db, dh, dw, H, W;
+  __device__ __forceinline__ PixelWalk(unsigned first, unsigned stride, int H_, int W_) : H(H_), W(W_) {
+    const unsigned HW = static_cast<unsigned>(H_) * W_;
+    b = static_cast<int>(first / HW);
+    unsigned rem = first - static_cast<unsigned>(b) * HW;
+    h = static_cast<int>(rem / W_);
+    w = static_cast<int>(rem - static_cast<unsigned>(h) * W_);
+    db = static_cast<int>(stride / HW);
+    rem = stride - static_cast<unsigned>(db) * HW;
+    dh = static_cast<int>(rem / W_);
+    dw = static_cast<int>(rem - static_cast<unsigned>(dh) * W_);
+  }
+  __device__ __forceinline__ void next() {
+    w += dw;
+    int c = w >= W ? 1 : 0;
+    w -= c ? W : 0;
+    h += dh + c;
+    c = h >= H ? 1 : 0;
+    h -= c ? H : 0;
+    b += db + c;
+  }
+  // parity-split pixel index, 32-bit (the callers guarantee fewer than 2^31 pixels)
+  __device__ __forceinline__ unsigned split() const {
+    const unsigned plane = static_cast<unsigned>(b) * 4u + 2u * (h & 1) + (w & 1);
+    return (plane * static_cast<unsigned>(H >> 1) + static_cast<unsigned>(h >> 1)) * static_cast<unsigned>(W >> 1) +
+           static_cast<unsigned>(w >> 1);
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // forward
@@ -138,8 +163,10 @@ bn_apply_kernel(const T* __restrict__ z, unsigned M, int C, int H, int W,
   ldg8f(scale + c, sc);
   ldg8f(shift + c, sh);
   const unsigned stride = gridDim.x * lanes;
-  const unsigned HW = static_cast<unsigned>(H) * W;
-  for (unsigned p0 = blockIdx.x * lanes + lane; p0 < M; p0 += 2 * stride) {
+  const unsigned first = blockIdx.x * lanes + lane;
+  // the parity-split destination of consecutive pixels of the sequence: walked, not divided out per pixel
+  PixelWalk walk(y_split ? first : 0u, y_split ? stride : 0u, H, W);
+  for (unsigned p0 = first; p0 < M; p0 += 2 * stride) {
     const unsigned p1 = p0 + stride;
     const bool two = p1 < M;
     float v0[8], v1[8];
@@ -159,13 +186,12 @@ bn_apply_kernel(const T* __restrict__ z, unsigned M, int C, int H, int W,
       }
       if (y_nhwc) store8(y_nhwc + static_cast<size_t>(p) * C + c, v);
       if (y_split) {
-        const unsigned b = p / HW, rem = p - b * HW;
-        const unsigned h = rem / W, w = rem - h * W;
         if (mask_split && code[p] == 0) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = 0.f;
         }
-        store8(y_split + static_cast<size_t>(split_index(b, h, w, H, W)) * C + c, v);
+        store8(y_split + static_cast<size_t>(walk.split()) * C + c, v);
+        walk.next();
       }
     }
   }
@@ -220,28 +246,33 @@ __device__ __forceinline__ void stream_grad_z(const GradSrcT<T>& s0, const GradS
   constexpr unsigned kSlot = 8 * sizeof(T);     // bytes per ring slot
   T* ring = reinterpret_cast<T*>(ring_raw);
   const bool need_split = s0.split || (s1.ptr && s1.split);
-  const unsigned HW = static_cast<unsigned>(H) * W;
   const unsigned nthr = blockDim.x, tid = threadIdx.x;
   const uint32_t ring_s = smem_u32(ring);
   uint8_t codes[kRing];
-  auto issue = [&](unsigned p, int d) {
-    if (p < M) {
-      long ps = 0;
-      if (need_split) {
-        const unsigned b = p / HW, rem = p - b * HW;
-        const unsigned h = rem / W, w = rem - h * W;
-        ps = split_index(b, h, w, H, W);
-      }
-      cp_async_vec8(ring_s + ((d * 3 + 0) * nthr + tid) * kSlot, s0.ptr + (s0.split ? ps : static_cast<long>(p)) * s0.pix_stride + s0.chan_off + c);
+  // fills are issued for consecutive pixels of the sequence first, first + stride, ...: the parity-split position is walked
+  // with carries; plain addresses are one 32 x 32 -> 64-bit multiply-add from the pixel index (persistent 64-bit pointers
+  // per stream cost the apply kernel its third CTA per SM in registers)
+  unsigned p_iss = first;
+  const unsigned s0_ps = static_cast<unsigned>(s0.pix_stride), s1_ps = static_cast<unsigned>(s1.pix_stride);   // channel counts
+  const T* const s0b = s0.ptr + s0.chan_off + c;
+  const T* const s1b = s1.ptr ? s1.ptr + s1.chan_off + c : nullptr;
+  const T* const zb = z + c;
+  PixelWalk walk(need_split ? first : 0u, need_split ? stride : 0u, H, W);
+  auto issue = [&](int d) {
+    if (p_iss < M) {
+      const unsigned ps = need_split ? walk.split() : 0u;
+      cp_async_vec8(ring_s + ((d * 3 + 0) * nthr + tid) * kSlot, s0b + static_cast<size_t>(s0.split ? ps : p_iss) * s0_ps);
       if (s1.ptr)
-        cp_async_vec8(ring_s + ((d * 3 + 1) * nthr + tid) * kSlot, s1.ptr + (s1.split ? ps : static_cast<long>(p)) * s1.pix_stride + s1.chan_off + c);
-      cp_async_vec8(ring_s + ((d * 3 + 2) * nthr + tid) * kSlot, z + static_cast<size_t>(p) * C + c);
-      codes[d] = code ? __ldg(code + p) : static_cast<uint8_t>(0);
+        cp_async_vec8(ring_s + ((d * 3 + 1) * nthr + tid) * kSlot, s1b + static_cast<size_t>(s1.split ? ps : p_iss) * s1_ps);
+      cp_async_vec8(ring_s + ((d * 3 + 2) * nthr + tid) * kSlot, zb + static_cast<size_t>(p_iss) * static_cast<unsigned>(C));
+      codes[d] = code ? __ldg(code + p_iss) : static_cast<uint8_t>(0);
     }
     cp_async_commit();
+    p_iss += stride;
+    if (need_split) walk.next();
   };
 #pragma unroll
-  for (int d = 0; d < kRing; ++d) issue(first + d * stride, d);
+  for (int d = 0; d < kRing; ++d) issue(d);
   for (unsigned base = first; base < M; base += kRing * stride) {
 #pragma unroll
     for (int d = 0; d < kRing; ++d) {
@@ -258,7 +289,7 @@ __device__ __forceinline__ void stream_grad_z(const GradSrcT<T>& s0, const GradS
         }
         unpack8(ring + ((d * 3 + 2) * nthr + tid) * 8, zz);
         const float r = code ? __ldg(lut + codes[d]) : 1.f;
-        issue(p + kRing * stride, d);      // the slot has been read into registers: refill it
+        issue(d);      // the slot has been read into registers: refill it with the next pixel of the sequence
         body(p, g, zz, r);
       }
     }
@@ -366,7 +397,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, doubl
 // gz[p][c] = r[p] * scale[c] * (g' - c1[c] - zhat * c2[c]) = r[p] * (A[c]*g' + Bz[c]*z + Cc[c])
 // Channel-stationary like bn_apply_kernel: the five per-channel coefficients live in registers.
 template <typename T, int kR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 1)      // bf16: three CTAs per SM (the bytes in flight are what hides HBM latency)
 bn_bwd_apply_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, unsigned M, int C, int H, int W,
                     const float* __restrict__ shift, const float* __restrict__ coeff, int act, float slope,
                     const uint8_t* __restrict__ code, const float* __restrict__ lut,

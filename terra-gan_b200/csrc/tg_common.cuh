@@ -375,15 +375,19 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t m, uint32_t n, b
 }
 
 // ---- 8-element vectors of the activation storage type (bf16: one 16-byte word; fp32: two) ----
+// bf16 -> fp32 is exact and is just the 16 bits moved up: one shift for the low half, one AND for the high half of a
+// packed pair (__bfloat1622float2 compiles to PRMT + shift for the high half: three instead of two operations per pair in
+// kernels that are bound by instruction issue)
+__device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& lo, float& hi) {
+  lo = __uint_as_float(w << 16);
+  hi = __uint_as_float(w & 0xffff0000u);
+}
 __device__ __forceinline__ void vload8(const __nv_bfloat16* p, float (&f)[8]) {
   const uint4 raw = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+  unpack_bf16x2(raw.x, f[0], f[1]);
+  unpack_bf16x2(raw.y, f[2], f[3]);
+  unpack_bf16x2(raw.z, f[4], f[5]);
+  unpack_bf16x2(raw.w, f[6], f[7]);
 }
 __device__ __forceinline__ void vload8(const float* p, float (&f)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p);

@@ -58,23 +58,25 @@ def test_mask_merge_up_bit_exact():
 
 
 # ---------------- BatchNorm forward / backward ----------------
-@pytest.mark.parametrize("C,act", [(64, 1), (128, 2), (512, 1)])
-def test_bn_forward_backward(C, act):
+# the last two shapes give every thread several pixels of a non-square grid (the kernels walk (b, h, w) incrementally with
+# carries instead of dividing per pixel) and an odd number of pixels per channel-vector lane
+@pytest.mark.parametrize("C,act,B,H,W", [(64, 1, 3, 16, 16), (128, 2, 3, 16, 16), (512, 1, 3, 16, 16), (64, 2, 6, 96, 80),
+                                         (128, 1, 5, 112, 48)])
+def test_bn_forward_backward(C, act, B, H, W):
     torch.manual_seed(2)
-    B, H = 3, 16
-    z = torch.randn(B, C, H, H, device=DEV).bfloat16()
+    z = torch.randn(B, C, H, W, device=DEV).bfloat16()
     gamma = (1 + 0.2 * torch.randn(C, device=DEV))
     beta = 0.2 * torch.randn(C, device=DEV)
     rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
-    code = torch.randint(0, 10, (B, H, H), device=DEV, dtype=torch.uint8)
+    code = torch.randint(0, 10, (B, H, W), device=DEV, dtype=torch.uint8)
     lut = torch.tensor(P.ratio_lut(3), device=DEV)
     # stats partials as the conv epilogue would write them (2 rows)
     zf = nhwc(z.float())
-    half = B * H * H // 2
+    half = B * H * W // 2
     flat = zf.reshape(-1, C)
     partial = torch.stack([torch.stack([flat[:half].sum(0), (flat[:half] ** 2).sum(0)]),
                            torch.stack([flat[half:].sum(0), (flat[half:] ** 2).sum(0)])]).contiguous()
-    scale, shift, mean, invstd = ops.bn_finalize(partial, B * H * H, gamma, beta, 1e-5, 0.1, rm, rv)
+    scale, shift, mean, invstd = ops.bn_finalize(partial, B * H * W, gamma, beta, 1e-5, 0.1, rm, rv)
     y, ys = ops.bn_apply(nhwc(z), scale, shift, act, 0.2, code=code, want_nhwc=True, want_split=True, mask_split=True)
     # reference: the same chain in fp32 with autograd (z = pre-BN value incl. ratio; ratio enters via dz/dconv)
     conv = (z.float() / 1.0).clone().requires_grad_(True)   # treat z as ratio-scaled conv output
@@ -87,8 +89,8 @@ def test_bn_forward_backward(C, act):
     assert rel_err(P.from_parity_split(ys), nhwc(yr) * m) < 1e-2
     assert rel_err(rm, rm2) < 1e-4 and rel_err(rv, rv2) < 1e-4
     # backward: two gradient sources (one plain, one parity-split), ratio folded into gz
-    g0 = torch.randn(B, H, H, C, device=DEV).bfloat16()
-    g1 = torch.randn(B, H, H, C, device=DEV).bfloat16()
+    g0 = torch.randn(B, H, W, C, device=DEV).bfloat16()
+    g1 = torch.randn(B, H, W, C, device=DEV).bfloat16()
     gtot = nchw(g0.float() + g1.float())
     (dz, dg, db) = torch.autograd.grad(yr, [conv, g_ref, b_ref], gtot)
     ratio = lut[code.long()].unsqueeze(-1)
@@ -112,13 +114,14 @@ def test_bn_eval_coeff():
 
 
 # ---------------- decoder assembly / pooling ----------------
-@pytest.mark.parametrize("Cu,Cs", [(512, 512), (128, 64), (64, 0)])
-def test_upsample_concat_fwd_bwd(Cu, Cs):
+# the last case has more 8-channel items than threads in the grid on a non-square image with a channel-vector count that is
+# not a power of two (the kernel walks (b, i, j, channel vector) with carries between a thread's items)
+@pytest.mark.parametrize("Cu,Cs,B,h,w", [(64, 0, 2, 8, 8), (128, 64, 2, 8, 8), (512, 512, 2, 8, 8), (128, 64, 5, 72, 40)])
+def test_upsample_concat_fwd_bwd(Cu, Cs, B, h, w):
     torch.manual_seed(4)
-    B, h = 2, 8
-    up = torch.randn(B, Cu, h, h, device=DEV).bfloat16().float().requires_grad_(True)
-    skip = torch.randn(B, Cs, 2 * h, 2 * h, device=DEV).bfloat16().float() if Cs else None
-    mm = (torch.rand(B, 1, 2 * h, 2 * h, device=DEV) < 0.7).float()
+    up = torch.randn(B, Cu, h, w, device=DEV).bfloat16().float().requires_grad_(True)
+    skip = torch.randn(B, Cs, 2 * h, 2 * w, device=DEV).bfloat16().float() if Cs else None
+    mm = (torch.rand(B, 1, 2 * h, 2 * w, device=DEV) < 0.7).float()
     upf = F.interpolate(up, scale_factor=2, mode="bilinear", align_corners=False)      # generator.py:67
     merged = torch.cat([upf, skip], 1) if Cs else upf
     ref = merged * mm
