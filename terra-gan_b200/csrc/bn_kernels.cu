@@ -238,14 +238,22 @@ __device__ __forceinline__ void unpack8(const __nv_bfloat16* slot, float (&f)[8]
 __device__ __forceinline__ void unpack8(const float* slot, float (&f)[8]) { vload8(slot, f); }
 // Streams (g0 [+ g1], z, ratio) of pixels p = first, first + stride, ... < M to `body(p, g[8], z[8], r)`.
 // ring: kRing * 3 * blockDim.x uint4 of shared memory.
-template <typename T, int kRing, typename Body>
-__device__ __forceinline__ void stream_grad_z(const GradSrcT<T>& s0, const GradSrcT<T>& s1, const T* __restrict__ z,
+// MODE: the launch's feature set as a compile-time constant, so that the per-pixel instruction stream only holds what
+// the layer uses (the kernels are issue-bound; null-pointer tests, the second source and both activation variants were
+// evaluated per pixel). Bits: 1 second gradient source, 2 parity-split source(s), 4 ratio code, 8 LeakyReLU (else ReLU).
+// MODE < 0: everything decided at run time (any other combination, and the fp32 verification path).
+constexpr int kBwdS1 = 1, kBwdSplit = 2, kBwdCode = 4, kBwdLeaky = 8;
+template <typename T, int kRing, int MODE, typename Body>
+__device__ __forceinline__ void stream_grad_z(const GradSrcT<T>& s0, const GradSrcT<T>& s1_in, const T* __restrict__ z,
                                               unsigned M, int C, int H, int W, int c, unsigned first, unsigned stride,
-                                              const uint8_t* __restrict__ code, const float* __restrict__ lut,
+                                              const uint8_t* __restrict__ code_in, const float* __restrict__ lut,
                                               uint4* ring_raw, Body body) {
   constexpr unsigned kSlot = 8 * sizeof(T);     // bytes per ring slot
   T* ring = reinterpret_cast<T*>(ring_raw);
-  const bool need_split = s0.split || (s1.ptr && s1.split);
+  GradSrcT<T> s1 = s1_in;
+  if (MODE >= 0 && !(MODE & kBwdS1)) s1.ptr = nullptr;
+  const uint8_t* code = (MODE >= 0 && !(MODE & kBwdCode)) ? nullptr : code_in;
+  const bool need_split = MODE >= 0 ? (MODE & kBwdSplit) != 0 : (s0.split || (s1.ptr && s1.split));
   const unsigned nthr = blockDim.x, tid = threadIdx.x;
   const uint32_t ring_s = smem_u32(ring);
   uint8_t codes[kRing];
@@ -299,8 +307,9 @@ __device__ __forceinline__ void stream_grad_z(const GradSrcT<T>& s0, const GradS
 
 // sums per channel over all pixels: [0] g', [1] g'*z, [2] r*g', [3] r*z, [4] r   (g' = g * act'(z*scale+shift))
 // block = 256 threads = (C/8 channel vectors) x (256/(C/8) pixel lanes); partial[block][5][C]
-template <typename T, int kR>
-__global__ void bn_bwd_reduce_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, long M,
+template <typename T, int kR, int MODE, int kMinB>
+__global__ void __launch_bounds__(256, kMinB)      // specialised bf16 launches: three CTAs per SM (80 registers instead of 110)
+bn_bwd_reduce_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, long M,
                                      int C, int H, int W, const float* __restrict__ scale,
                                      const float* __restrict__ shift, int act, float slope,
                                      const uint8_t* __restrict__ code, const float* __restrict__ lut,
@@ -319,7 +328,8 @@ __global__ void bn_bwd_reduce_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __
   float sc[8], sh[8];
   ldg8f(scale + c, sc);
   ldg8f(shift + c, sh);
-  stream_grad_z<T, kR>(s0, s1, z, static_cast<unsigned>(M), C, H, W, c, blockIdx.x * lanes + my_lane, gridDim.x * lanes, code, lut,
+  if (MODE >= 0) act = (MODE & kBwdLeaky) ? 2 : 1;
+  stream_grad_z<T, kR, MODE>(s0, s1, z, static_cast<unsigned>(M), C, H, W, c, blockIdx.x * lanes + my_lane, gridDim.x * lanes, code, lut,
                 reinterpret_cast<uint4*>(red), [&](unsigned, const float (&g)[8], const float (&zz)[8], float r) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
@@ -396,7 +406,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, doubl
 
 // gz[p][c] = r[p] * scale[c] * (g' - c1[c] - zhat * c2[c]) = r[p] * (A[c]*g' + Bz[c]*z + Cc[c])
 // Channel-stationary like bn_apply_kernel: the five per-channel coefficients live in registers.
-template <typename T, int kR>
+template <typename T, int kR, int MODE>
 __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 1)      // bf16: three CTAs per SM (the bytes in flight are what hides HBM latency)
 bn_bwd_apply_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, unsigned M, int C, int H, int W,
                     const float* __restrict__ shift, const float* __restrict__ coeff, int act, float slope,
@@ -422,7 +432,8 @@ bn_bwd_apply_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, uns
     }
   }
   extern __shared__ uint4 apply_ring[];
-  stream_grad_z<T, kR>(s0, s1, z, M, C, H, W, static_cast<int>(c), blockIdx.x * lanes + lane, gridDim.x * lanes, code, lut, apply_ring,
+  if (MODE >= 0) act = (MODE & kBwdLeaky) ? 2 : 1;
+  stream_grad_z<T, kR, MODE>(s0, s1, z, M, C, H, W, static_cast<int>(c), blockIdx.x * lanes + lane, gridDim.x * lanes, code, lut, apply_ring,
                 [&](unsigned p, const float (&g)[8], const float (&zz)[8], float r) {
                   float o[8];
 #pragma unroll
@@ -437,19 +448,24 @@ bn_bwd_apply_kernel(GradSrcT<T> s0, GradSrcT<T> s1, const T* __restrict__ z, uns
                 });
 }
 
-static int ew_grid(long n, int block) {
-  long g = (n + block - 1) / block;
-  const long cap = static_cast<long>(num_sms() > 0 ? num_sms() : 148) * 8;
-  if (g > cap) g = cap;
-  if (g < 1) g = 1;
-  return static_cast<int>(g);
-}
-
-// experiment switch: TG_BN_RING_REDUCE / TG_BN_RING_APPLY = 2 select a shallower ring (A/B timing)
-static int ring_override(const char* name, int dflt) {
-  const char* e = getenv(name);
-  if (e == nullptr) return dflt;
-  return atoi(e) == 2 ? 2 : dflt;
+// compile-time feature set of a backward launch (see stream_grad_z); -1 = decided at run time
+template <typename T>
+static int bwd_mode(const tg_grad_src* g0, const tg_grad_src* g1, int act, const uint8_t* code) {
+  static const bool off = [] { const char* e = getenv("TG_BN_BWD_GENERIC"); return e != nullptr && e[0] == '1'; }();
+  if (off || sizeof(T) != 2 || (act != 1 && act != 2)) return -1;
+  const bool has1 = g1 != nullptr && g1->ptr != nullptr;
+  const bool split = g0->split != 0 || (has1 && g1->split != 0);
+  // (which of the sources is parity-split stays a run-time flag per source; the bit only says "walk the split position")
+  const int m = (has1 ? kBwdS1 : 0) | (split ? kBwdSplit : 0) | (code ? kBwdCode : 0) | (act == 2 ? kBwdLeaky : 0);
+  switch (m) {
+    case kBwdCode:                                   // decoder layers, enc7
+    case kBwdCode | kBwdS1 | kBwdSplit:              // enc1..enc6: skip gradient + parity-split gradient of the next layer
+    case kBwdLeaky:                                  // Discriminator model[8]
+    case kBwdLeaky | kBwdSplit:                      // Discriminator model[2], model[5]
+      return m;
+    default:
+      return -1;
+  }
 }
 
 template <typename T>
@@ -479,7 +495,7 @@ static int bn_apply_impl(const void* z, int B, int H, int W, int C, const float*
   TG_REQUIRE(!(mask_split && y_split) || code, "tg_bn_apply: mask_split needs code");
   const long M = static_cast<long>(B) * H * W;
   TG_REQUIRE(C / 8 <= 256 && 256 % (C / 8) == 0 && M < (1L << 31), "tg_bn_apply: unsupported C=%d or too many pixels", C);
-  bn_apply_kernel<T><<<ew_grid(M * (C / 8), 512), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  bn_apply_kernel<T><<<wave_grid(bn_apply_kernel<T>, 256, 0, (M * (C / 8) + 511) / 512), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const T*>(z), static_cast<unsigned>(M), C, H, W, scale, shift, act, slope, code,
       reinterpret_cast<T*>(y_nhwc), reinterpret_cast<T*>(y_split), mask_split);
   TG_CHECK_CUDA(cudaGetLastError());
@@ -497,25 +513,41 @@ static int bn_bwd_reduce_impl(const tg_grad_src* g0, const tg_grad_src* g1, cons
   const long M = static_cast<long>(B) * H * W;
   const int cv = C / 8, lanes = 256 / cv;
   long grid = (M + lanes - 1) / lanes;
-  const long cap = static_cast<long>(num_sms()) * 4;
+  // one wave: every CTA resident from the start with the same share of the pixels. The specialised bf16 kernels are built
+  // for three CTAs per SM; TG_BN_REDUCE_OCC=1 selects the earlier build (no register cap, 4 x SMs CTAs) for A/B timing.
+  static const bool occ3 = [] { const char* e = getenv("TG_BN_REDUCE_OCC"); return !(e != nullptr && e[0] == '1'); }();
+  const int mode = bwd_mode<T>(g0, g1, act, code);
+  const bool three = occ3 && sizeof(T) == 2 && mode >= 0;
+  const long cap = static_cast<long>(num_sms()) * (three ? 3 : 4);
   if (grid > cap) grid = cap;
   if (grid > rows_cap) grid = rows_cap;
   TG_REQUIRE(grid >= 1, "tg_bn_bwd_reduce: rows_cap must be >= 1");
   *rows_used = static_cast<int>(grid);
   size_t smem = static_cast<size_t>(lanes) * cv * 40 * sizeof(float);
   constexpr int kR = ring_reduce<T>();
-  const int ring = ring_override("TG_BN_RING_REDUCE", kR);
-  const size_t ring_bytes = static_cast<size_t>(ring) * 3 * 256 * 8 * sizeof(T);
+  const size_t ring_bytes = static_cast<size_t>(kR) * 3 * 256 * 8 * sizeof(T);
   if (smem < ring_bytes) smem = ring_bytes;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define TG_LAUNCH_REDUCE(R)                                                                                          \
+#define TG_LAUNCH_REDUCE(MODE)                                                                                       \
   {                                                                                                                  \
-    TG_SET_SMEM_ONCE((bn_bwd_reduce_kernel<T, R>), 100 * 1024);                                                      \
-    bn_bwd_reduce_kernel<T, R><<<static_cast<int>(grid), 256, smem, st>>>(to_src<T>(g0), to_src<T>(g1),              \
-        reinterpret_cast<const T*>(z), M, C, H, W, scale, shift, act, slope, code, lut_dev, partial);                \
+    constexpr int kOcc = (sizeof(T) == 2 && (MODE) >= 0) ? 3 : 1;                                                    \
+    if (three) {                                                                                                     \
+      TG_SET_SMEM_ONCE((bn_bwd_reduce_kernel<T, kR, MODE, kOcc>), 100 * 1024);                                       \
+      bn_bwd_reduce_kernel<T, kR, MODE, kOcc><<<static_cast<int>(grid), 256, smem, st>>>(to_src<T>(g0), to_src<T>(g1), \
+          reinterpret_cast<const T*>(z), M, C, H, W, scale, shift, act, slope, code, lut_dev, partial);              \
+    } else {                                                                                                         \
+      TG_SET_SMEM_ONCE((bn_bwd_reduce_kernel<T, kR, MODE, 1>), 100 * 1024);                                          \
+      bn_bwd_reduce_kernel<T, kR, MODE, 1><<<static_cast<int>(grid), 256, smem, st>>>(to_src<T>(g0), to_src<T>(g1),  \
+          reinterpret_cast<const T*>(z), M, C, H, W, scale, shift, act, slope, code, lut_dev, partial);              \
+    }                                                                                                                \
   }
-  if (ring == kR) TG_LAUNCH_REDUCE(kR)
-  else TG_LAUNCH_REDUCE(2)
+  switch (mode) {
+    case kBwdCode: TG_LAUNCH_REDUCE(kBwdCode) break;
+    case kBwdCode | kBwdS1 | kBwdSplit: TG_LAUNCH_REDUCE(kBwdCode | kBwdS1 | kBwdSplit) break;
+    case kBwdLeaky: TG_LAUNCH_REDUCE(kBwdLeaky) break;
+    case kBwdLeaky | kBwdSplit: TG_LAUNCH_REDUCE(kBwdLeaky | kBwdSplit) break;
+    default: TG_LAUNCH_REDUCE(-1) break;
+  }
 #undef TG_LAUNCH_REDUCE
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -530,17 +562,22 @@ static int bn_bwd_apply_impl(const tg_grad_src* g0, const tg_grad_src* g1, const
   TG_REQUIRE(!code || lut_dev, "tg_bn_bwd_apply: code needs a device LUT");
   const long M = static_cast<long>(B) * H * W;
   constexpr int kR = ring_apply<T>();
-  const int ring = ring_override("TG_BN_RING_APPLY", kR);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define TG_LAUNCH_APPLY(R)                                                                                           \
+#define TG_LAUNCH_APPLY(MODE)                                                                                        \
   {                                                                                                                  \
-    TG_SET_SMEM_ONCE((bn_bwd_apply_kernel<T, R>), 100 * 1024);                                                       \
-    bn_bwd_apply_kernel<T, R><<<ew_grid(M * (C / 8), 256), 256, R * 3 * 256 * 8 * sizeof(T), st>>>(                  \
+    TG_SET_SMEM_ONCE((bn_bwd_apply_kernel<T, kR, MODE>), 100 * 1024);                                                \
+    bn_bwd_apply_kernel<T, kR, MODE><<<wave_grid(bn_bwd_apply_kernel<T, kR, MODE>, 256, kR * 3 * 256 * 8 * sizeof(T), \
+                                                 (M * (C / 8) + 255) / 256), 256, kR * 3 * 256 * 8 * sizeof(T), st>>>(  \
         to_src<T>(g0), to_src<T>(g1), reinterpret_cast<const T*>(z), static_cast<unsigned>(M), C, H, W, shift, coeff, act,  \
         slope, code, lut_dev, reinterpret_cast<T*>(gz));                                                             \
   }
-  if (ring == kR) TG_LAUNCH_APPLY(kR)
-  else TG_LAUNCH_APPLY(2)
+  switch (bwd_mode<T>(g0, g1, act, code)) {
+    case kBwdCode: TG_LAUNCH_APPLY(kBwdCode) break;
+    case kBwdCode | kBwdS1 | kBwdSplit: TG_LAUNCH_APPLY(kBwdCode | kBwdS1 | kBwdSplit) break;
+    case kBwdLeaky: TG_LAUNCH_APPLY(kBwdLeaky) break;
+    case kBwdLeaky | kBwdSplit: TG_LAUNCH_APPLY(kBwdLeaky | kBwdSplit) break;
+    default: TG_LAUNCH_APPLY(-1) break;
+  }
 #undef TG_LAUNCH_APPLY
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -311,7 +311,7 @@ extern "C" int tg_l1_bf16_bwd(const void* a, const void* b, long n, const float*
                               void* stream) {
   using namespace tg;
   TG_REQUIRE(a && b && grad_out && ga && n > 0 && n % 8 == 0, "tg_l1_bf16_bwd: bad arguments");
-  l1_bf16_bwd_kernel<__nv_bfloat16><<<ls_grid(n / 8, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  l1_bf16_bwd_kernel<__nv_bfloat16><<<wave_grid(l1_bf16_bwd_kernel<__nv_bfloat16>, 256, 0, (n / 8 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), n / 8, grad_out,
       static_cast<float>(1.0 / static_cast<double>(n)), relu_gate, reinterpret_cast<__nv_bfloat16*>(ga));
   TG_CHECK_CUDA(cudaGetLastError());

@@ -312,14 +312,6 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict
   }
 }
 
-static int rs_grid(long n, int block) {
-  long g = (n + block - 1) / block;
-  const long cap = static_cast<long>(num_sms() > 0 ? num_sms() : 148) * 8;
-  if (g > cap) g = cap;
-  if (g < 1) g = 1;
-  return static_cast<int>(g);
-}
-
 template <typename T>
 static int upsample_concat_impl(const void* up, int B, int h, int w, int Cu, const void* skip, int Cs,
                                 const uint8_t* merged_mask, void* out, void* stream) {
@@ -327,7 +319,7 @@ static int upsample_concat_impl(const void* up, int B, int h, int w, int Cu, con
   TG_REQUIRE(Cs == 0 || skip, "tg_upsample_concat: skip missing");
   const long total = static_cast<long>(B) * h * w * ((Cu + Cs) / 8);     // one thread per 2x2 output block
   TG_REQUIRE(total < (1L << 31), "tg_upsample_concat: tensor too large for 32-bit indexing");
-  upsample_concat_kernel<T><<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  upsample_concat_kernel<T><<<wave_grid(upsample_concat_kernel<T>, 256, 0, (total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const T*>(up), B, h, w, Cu, reinterpret_cast<const T*>(skip), Cs, merged_mask,
       reinterpret_cast<T*>(out));
   TG_CHECK_CUDA(cudaGetLastError());
@@ -341,7 +333,7 @@ static int upsample_concat_bwd_impl(const void* d_merged, int B, int h, int w, i
              "tg_upsample_concat_bwd: bad arguments");
   const long total = static_cast<long>(B) * ((h + kUbSeg - 1) / kUbSeg) * w * (Cu / 8);   // column strips
   TG_REQUIRE(total < (1L << 31), "tg_upsample_concat_bwd: tensor too large for 32-bit indexing");
-  upsample_concat_bwd_kernel<T><<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  upsample_concat_bwd_kernel<T><<<wave_grid(upsample_concat_bwd_kernel<T>, 256, 0, (total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const T*>(d_merged), B, h, w, Cu, Ctot, reinterpret_cast<T*>(d_up));
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -351,7 +343,7 @@ template <typename T>
 static int maxpool2_impl(const void* x, int B, int H, int W, int C, void* y, void* stream) {
   TG_REQUIRE(x && y && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "tg_maxpool2: bad arguments");
   const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2_kernel<T><<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  maxpool2_kernel<T><<<wave_grid(maxpool2_kernel<T>, 256, 0, (total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const T*>(x), B, H, W, C, reinterpret_cast<T*>(y));
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -362,7 +354,7 @@ static int maxpool2_bwd_impl(const void* x, const void* gy, int B, int H, int W,
                              void* stream) {
   TG_REQUIRE(x && gy && gx && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "tg_maxpool2_bwd: bad arguments");
   const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2_bwd_kernel<T><<<rs_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  maxpool2_bwd_kernel<T><<<wave_grid(maxpool2_bwd_kernel<T>, 256, 0, (total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(gy), B, H, W, C, relu_gate, reinterpret_cast<T*>(gx));
   TG_CHECK_CUDA(cudaGetLastError());
   return 0;

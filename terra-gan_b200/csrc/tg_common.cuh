@@ -55,6 +55,31 @@ int num_sms();  // cached SM count of the current device
     }                                                                                              \
   } while (0)
 
+// Grid of a grid-stride kernel as WHOLE waves: `resident` = CTAs of this kernel that fit on one SM (occupancy API, asked
+// once per kernel and dynamic shared-memory size), grid = min(blocks_needed, resident * SMs). Every CTA is resident from
+// the start and does the same share of the work. The fixed 8 x SMs grids this replaces ran 3 + 3 + 2 (or 6 + 2) CTAs
+// per SM in turn for kernels with 3 (6) resident CTAs: a last, partly filled wave at a fraction of the HBM bandwidth.
+// TG_WAVE_GRID=0 restores the old sizing (A/B timing). Returns <= 0 on error.
+int wave_grid_lookup(const void* kernel, int block, size_t smem, int* resident);   // tg_runtime.cu (cache)
+void wave_grid_store(const void* kernel, int block, size_t smem, int resident);
+bool wave_grid_enabled();
+template <typename K>
+inline int wave_grid(K kernel, int block, size_t smem, long blocks_needed, int legacy_per_sm = 8) {
+  const long sms = num_sms() > 0 ? num_sms() : 148;
+  long per_sm = legacy_per_sm;
+  if (wave_grid_enabled()) {
+    int resident = 0;
+    if (!wave_grid_lookup(reinterpret_cast<const void*>(kernel), block, smem, &resident)) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, block, smem) != cudaSuccess || resident < 1)
+        resident = legacy_per_sm;
+      wave_grid_store(reinterpret_cast<const void*>(kernel), block, smem, resident);
+    }
+    per_sm = resident;
+  }
+  long g = blocks_needed < per_sm * sms ? blocks_needed : per_sm * sms;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
 // Perf-experiment switches (skip stores / loads / MMAs) used to live behind run-time `p.debug` bits that every
 // epilogue tile evaluated; they are compiled out unless the library is built with -DTG_PERF_DEBUG.
 #ifdef TG_PERF_DEBUG

@@ -5,6 +5,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include <cudaTypedefs.h>
 
 #include "tg_common.cuh"
@@ -31,6 +34,35 @@ int num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// ---- wave_grid cache (tg_common.cuh) ------------------------------------------------------------
+// Resident CTAs per SM of a (kernel, block size, dynamic smem) triple; a handful of entries, linear scan under a mutex.
+namespace {
+struct WaveEntry { const void* k; int block; size_t smem; int dev; int resident; };
+std::mutex g_wave_mu;
+std::vector<WaveEntry> g_wave;
+}  // namespace
+int wave_grid_lookup(const void* kernel, int block, size_t smem, int* resident) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_wave_mu);
+  for (const WaveEntry& e : g_wave)
+    if (e.k == kernel && e.block == block && e.smem == smem && e.dev == dev) {
+      *resident = e.resident;
+      return 1;
+    }
+  return 0;
+}
+void wave_grid_store(const void* kernel, int block, size_t smem, int resident) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_wave_mu);
+  g_wave.push_back({kernel, block, smem, dev, resident});
+}
+bool wave_grid_enabled() {
+  static const bool on = [] { const char* e = getenv("TG_WAVE_GRID"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
