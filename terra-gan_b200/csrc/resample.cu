@@ -39,6 +39,11 @@ __device__ __forceinline__ void raw_load(Raw8<float>& r, const float* p) {
   r.a = *reinterpret_cast<const float4*>(p);
   r.b = *(reinterpret_cast<const float4*>(p) + 1);
 }
+__device__ __forceinline__ void raw_store(__nv_bfloat16* p, const Raw8<__nv_bfloat16>& r) { *reinterpret_cast<uint4*>(p) = r.v; }
+__device__ __forceinline__ void raw_store(float* p, const Raw8<float>& r) {
+  *reinterpret_cast<float4*>(p) = r.a;
+  *(reinterpret_cast<float4*>(p) + 1) = r.b;
+}
 __device__ __forceinline__ void raw_unpack(const Raw8<__nv_bfloat16>& r, float (&f)[8]) {
   unpack_bf16x2(r.v.x, f[0], f[1]);
   unpack_bf16x2(r.v.y, f[2], f[3]);
@@ -65,41 +70,38 @@ __device__ __forceinline__ void bilinear_src(int o, int n, int& i0, int& i1, flo
 // One thread = one 8-channel vector of a 2x2 output block: the four outputs of source pixel (i, j)
 // share its 3x3 neighbourhood (9 loads for 4 outputs instead of 16), index math is 32-bit and
 // amortised over the block. Exact PyTorch weights: 0.75/0.25 with edge clamping.
-template <typename T>
-__global__ void __launch_bounds__(256)
-upsample_concat_kernel(const T* __restrict__ up, int B, int h, int w, int Cu,
-                       const T* __restrict__ skip, int Cs, const uint8_t* __restrict__ mm,
-                       T* __restrict__ out) {
-  const int H = 2 * h, W = 2 * w, C = Cu + Cs;
-  const unsigned cv = C >> 3;
-  const unsigned total = static_cast<unsigned>(B) * h * w * cv;
-  const unsigned hw = static_cast<unsigned>(h) * w;
-  // item i = ((b * h + ii) * w + jj) * cv + channel vector; a thread's items are a constant stride apart, so the four
-  // digits are walked with carries instead of three integer divisions per item (they were ~60 of the ~130 instructions
-  // of a skip-part item and ~15 % of an up-sampled one; the kernel is issue-bound)
-  const unsigned i_first = blockIdx.x * blockDim.x + threadIdx.x, i_step = gridDim.x * blockDim.x;
+// Two passes in one launch: first every (block, up-sampled channel vector) item, then every (block, skip channel vector)
+// item. With one mixed item space (channel vector fastest) a warp held both kinds whenever (Cu + Cs) / 8 is not a
+// multiple of 32 (dec2: 24) and executed the interpolation AND the copy path for every item; the skip part is a
+// masked raw 16-byte copy (no unpack / repack).
+// item = ((b * h + ii) * w + jj) * cv + channel vector; a thread's items are a constant stride apart, so the four
+// digits are walked with carries instead of three integer divisions per item (they were ~60 of the ~130 instructions
+// of a skip-part item and ~15 % of an up-sampled one; the kernel is issue-bound)
+struct BlockWalk {
   int cvi, jj, ii;
   unsigned b;
   int d_cv, d_j, d_i;
   unsigned d_b;
-  {
-    unsigned blk = i_first / cv;
-    cvi = static_cast<int>(i_first - blk * cv);
+  int cv, w, h;
+  __device__ __forceinline__ BlockWalk(unsigned first, unsigned step, unsigned cv_, int h_, int w_) : cv(static_cast<int>(cv_)), w(w_), h(h_) {
+    const unsigned hw = static_cast<unsigned>(h_) * w_;
+    unsigned blk = first / cv_;
+    cvi = static_cast<int>(first - blk * cv_);
     b = blk / hw;
     unsigned rem = blk - b * hw;
-    ii = static_cast<int>(rem / w);
-    jj = static_cast<int>(rem - ii * w);
-    blk = i_step / cv;
-    d_cv = static_cast<int>(i_step - blk * cv);
+    ii = static_cast<int>(rem / w_);
+    jj = static_cast<int>(rem - ii * w_);
+    blk = step / cv_;
+    d_cv = static_cast<int>(step - blk * cv_);
     d_b = blk / hw;
     rem = blk - d_b * hw;
-    d_i = static_cast<int>(rem / w);
-    d_j = static_cast<int>(rem - d_i * w);
+    d_i = static_cast<int>(rem / w_);
+    d_j = static_cast<int>(rem - d_i * w_);
   }
-  auto advance = [&]() {
+  __device__ __forceinline__ void advance() {
     cvi += d_cv;
-    int cy = cvi >= static_cast<int>(cv) ? 1 : 0;
-    cvi -= cy ? static_cast<int>(cv) : 0;
+    int cy = cvi >= cv ? 1 : 0;
+    cvi -= cy ? cv : 0;
     jj += d_j + cy;
     cy = jj >= w ? 1 : 0;
     jj -= cy ? w : 0;
@@ -107,16 +109,30 @@ upsample_concat_kernel(const T* __restrict__ up, int B, int h, int w, int Cu,
     cy = ii >= h ? 1 : 0;
     ii -= cy ? h : 0;
     b += d_b + cy;
-  };
-  for (unsigned i = i_first; i < total; i += i_step, advance()) {
-    const int c = cvi << 3;
-    const size_t obase = (static_cast<size_t>(b) * H + 2 * ii) * W + 2 * jj;   // pixel (2i, 2j)
-    const size_t opix[4] = {obase, obase + 1, obase + W, obase + W + 1};
-    bool on[4];
+  }
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample_concat_kernel(const T* __restrict__ up, int B, int h, int w, int Cu,
+                       const T* __restrict__ skip, int Cs, const uint8_t* __restrict__ mm,
+                       T* __restrict__ out) {
+  const int H = 2 * h, W = 2 * w, C = Cu + Cs;
+  const unsigned hw = static_cast<unsigned>(h) * w;
+  const unsigned i_first = blockIdx.x * blockDim.x + threadIdx.x, i_step = gridDim.x * blockDim.x;
+  // ---- pass 1: the bilinearly up-sampled channels ----
+  {
+    const unsigned cv = Cu >> 3;
+    const unsigned total = static_cast<unsigned>(B) * hw * cv;
+    BlockWalk wk(i_first, i_step, cv, h, w);
+    for (unsigned i = i_first; i < total; i += i_step, wk.advance()) {
+      const int c = wk.cvi << 3, ii = wk.ii, jj = wk.jj;
+      const unsigned b = wk.b;
+      const size_t obase = (static_cast<size_t>(b) * H + 2 * ii) * W + 2 * jj;   // pixel (2i, 2j)
+      const size_t opix[4] = {obase, obase + 1, obase + W, obase + W + 1};
+      bool on[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) on[q] = (mm == nullptr) || (mm[opix[q]] != 0);
-    float o[4][8];
-    if (c < Cu) {
+      for (int q = 0; q < 4; ++q) on[q] = (mm == nullptr) || (mm[opix[q]] != 0);
+      float o[4][8];
       if (on[0] || on[1] || on[2] || on[3]) {
         const int im = ii > 0 ? ii - 1 : 0, ip = ii < h - 1 ? ii + 1 : h - 1;
         const int jm = jj > 0 ? jj - 1 : 0, jp = jj < w - 1 ? jj + 1 : w - 1;
@@ -142,18 +158,33 @@ upsample_concat_kernel(const T* __restrict__ up, int B, int h, int w, int Cu,
           o[3][e] = 0.75f * r1b + 0.25f * r2b;
         }
       }
-    } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (on[q]) rs_load8(skip + opix[q] * Cs + (c - Cu), o[q]);
-    }
+      for (int q = 0; q < 4; ++q) {
+        if (!on[q]) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (!on[q]) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[q][e] = 0.f;
+          for (int e = 0; e < 8; ++e) o[q][e] = 0.f;
+        }
+        rs_store8(out + opix[q] * C + c, o[q]);
       }
-      rs_store8(out + opix[q] * C + c, o[q]);
+    }
+  }
+  // ---- pass 2: the skip channels (masked copy) ----
+  if (Cs > 0) {
+    const unsigned cv = Cs >> 3;
+    const unsigned total = static_cast<unsigned>(B) * hw * cv;
+    BlockWalk wk(i_first, i_step, cv, h, w);
+    for (unsigned i = i_first; i < total; i += i_step, wk.advance()) {
+      const int c = wk.cvi << 3;
+      const size_t obase = (static_cast<size_t>(wk.b) * H + 2 * wk.ii) * W + 2 * wk.jj;
+      const size_t opix[4] = {obase, obase + 1, obase + W, obase + W + 1};
+      Raw8<T> r[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        raw_zero(r[q]);
+        if ((mm == nullptr) || (mm[opix[q]] != 0)) raw_load(r[q], skip + opix[q] * Cs + c);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) raw_store(out + opix[q] * C + Cu + c, r[q]);
     }
   }
 }
