@@ -21,11 +21,5 @@ for k in 'conv_igemm_kernel' 'conv_halo_kernel' 'wgrad_wide_kernel' 'bn_bwd_redu
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$k" -c 3 \
       -o $O/r02c_full_$k -f python tools/profile_step.py 64 3 > $O/r02c_ncu_full_$k.log 2>&1 || true
 done
-# A/B: CTA-pair kernel also for the N = 192 layer (dec2 data gradient)
-for v in 0 1 0 1; do
-  TG_CONV_PAIR_192=$v python bench.py --no-cpu-baseline --steps 8 --warmup 3 --per-launch pair192_pl_$v.txt 2>> $O/bench.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('pair192=$v', round(d['value'],1), round(d['ms_per_step'],2), d['clocks']['sm_mhz'])" >> $O/pair192_ab.txt
-done
-cat $O/pair192_ab.txt
+python tools/time_bw.py 64 > $O/r02_streaming_kernels_timing.txt 2>&1
 ls -la $O/*.ncu-rep
