@@ -120,7 +120,12 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t_mark = [], None, index, 0.0
+
+    def mark(self):
+        """Start of the timed region: only samples taken from here on are reported (the sampler itself is started before
+        the warm-up steps, because nvidia-smi needs up to a second to deliver its first sample)."""
+        self.t_mark = time.monotonic()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -128,7 +133,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -136,14 +141,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        inside = [r for t, r in self.rows if t >= self.t_mark]
+        note = None
+        if not inside and self.rows:       # timed region shorter than the sampling period: the last sample of the warm-up (same load)
+            inside, note = [self.rows[-1][1]], "timed region shorter than the 100 ms sampling period: last warm-up sample"
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -152,8 +161,11 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -344,11 +356,12 @@ def run_ours(args):
         state["i"] += 1
 
     ops.profile_pool(2 * 130 * args.steps + 64)      # timing events for every tensor-core launch of the timed steps
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     # ---- timed region 1: resident inputs; tensor-core launches timed with CUDA events ----
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     _lib.CALLS.clear()
     for o in (opt_G, opt_D, getattr(hg_stepper, "opt", None)):
         if hasattr(o, "kernel_launches"):
