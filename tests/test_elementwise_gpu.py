@@ -47,6 +47,31 @@ def test_mask_window_sum_bit_exact(k, s, p):
     assert torch.equal(ops.mask_to_f32(upd), (ref[:, 0] > 0).float())
 
 
+# the packed-byte fast path (four outputs per thread; widths divisible by 4) and the generic kernel (everything else) on
+# non-square grids, arbitrary non-zero mask bytes, a full mask (the largest counts) and a single hole at the corner
+@pytest.mark.parametrize("k,s,p", [(7, 2, 3), (5, 2, 2), (3, 2, 1), (3, 1, 1)])
+@pytest.mark.parametrize("B,H,W", [(2, 8, 24), (3, 40, 72), (1, 4, 4), (2, 6, 10), (2, 512, 512)])
+@pytest.mark.parametrize("fill", ["random", "ones", "corner"])
+def test_mask_window_sum_shapes(k, s, p, B, H, W, fill):
+    g = torch.Generator(device="cpu").manual_seed(k * 100 + s * 10 + H)
+    if fill == "random":
+        mu = (torch.rand(B, H, W, generator=g) < 0.5).to(torch.uint8) * torch.randint(1, 256, (B, H, W), generator=g).to(torch.uint8)
+    elif fill == "ones":
+        mu = torch.full((B, H, W), 255, dtype=torch.uint8)
+    else:
+        mu = torch.ones(B, H, W, dtype=torch.uint8)
+        mu[:, : min(H, 5), : min(W, 5)] = 0
+        mu[:, -1, -1] = 0
+    mu = mu.to(DEV)
+    ref = F.conv2d((mu != 0).float().unsqueeze(1), torch.ones(1, 1, k, k, device=DEV), None, s, p)[:, 0]
+    even = ref.shape[-1] % 2 == 0 and ref.shape[-2] % 2 == 0
+    ssum, upd, upd_split, _ = ops.mask_window_sum(mu, k, s, p, want_upd_split=even)
+    assert torch.equal(ssum.float(), ref)
+    assert torch.equal(upd.float(), (ref > 0).float())
+    if even:
+        assert torch.equal(P.from_parity_split(upd_split.unsqueeze(-1)).squeeze(-1), upd)
+
+
 def test_mask_merge_up_bit_exact():
     torch.manual_seed(1)
     B, H = 2, 32
